@@ -1,0 +1,1022 @@
+// batotp_cuda.cu — extern "C" boundary (include/batotp_cuda.h) and the chunk pipeline that
+// strings the kernels of k_input.cuh / k_sweep.cuh / k_output.cuh together.
+//
+// Build (product):  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -lineinfo
+//                   -shared -Xcompiler -fPIC  -> batotp_b200/lib/libbatotp_cuda.so
+// There is no CPU fallback in that library.  The same file compiles with g++ and
+// -DBATOTP_HOST_EMU into a TEST-ONLY emulation library (see emu.h) used by the CPU CI.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/batotp_cuda.h"
+#include "k_output.cuh"
+#include "k_sweep.cuh"
+#include "k_mvc.cuh"
+
+#ifndef BATOTP_HOST_EMU
+#include <cuda_runtime.h>
+__constant__ DevCfg g_cfg;
+#else
+DevCfg g_cfg;
+thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+#endif
+
+// ----------------------------------------------------------------------------- runtime shims
+namespace {
+
+struct Err {
+  std::string msg;
+};
+
+#ifndef BATOTP_HOST_EMU
+#define CU_CHECK(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      char buf_[512];                                                                       \
+      snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+               __FILE__, __LINE__);                                                         \
+      throw Err{buf_};                                                                      \
+    }                                                                                       \
+  } while (0)
+inline void *g_alloc(size_t bytes) {
+  void *p = nullptr;
+  CU_CHECK(cudaMalloc(&p, bytes ? bytes : 8));
+  return p;
+}
+inline void g_free(void *p) {
+  if (p) cudaFree(p);
+}
+inline void g_zero(void *p, size_t bytes, cudaStream_t s) { CU_CHECK(cudaMemsetAsync(p, 0, bytes, s)); }
+inline void g_h2d(void *d, const void *h, size_t bytes, cudaStream_t s) {
+  CU_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s));
+}
+inline void g_d2h(void *h, const void *d, size_t bytes, cudaStream_t s) {
+  CU_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s));
+}
+inline void g_d2d(void *d, const void *s0, size_t bytes, cudaStream_t s) {
+  CU_CHECK(cudaMemcpyAsync(d, s0, bytes, cudaMemcpyDeviceToDevice, s));
+}
+inline void g_d2h_2d(void *h, size_t hp, const void *d, size_t dp, size_t width, size_t rows, cudaStream_t s) {
+  CU_CHECK(cudaMemcpy2DAsync(h, hp, d, dp, width, rows, cudaMemcpyDeviceToHost, s));
+}
+inline void g_h2d_2d(void *d, size_t dp, const void *h, size_t hp, size_t width, size_t rows, cudaStream_t s) {
+  CU_CHECK(cudaMemcpy2DAsync(d, dp, h, hp, width, rows, cudaMemcpyHostToDevice, s));
+}
+inline void g_d2d_2d(void *d, size_t dp, const void *s0, size_t sp, size_t width, size_t rows, cudaStream_t s) {
+  CU_CHECK(cudaMemcpy2DAsync(d, dp, s0, sp, width, rows, cudaMemcpyDeviceToDevice, s));
+}
+inline void g_sync(cudaStream_t s) { CU_CHECK(cudaStreamSynchronize(s)); }
+inline void g_set_cfg(const DevCfg &c, cudaStream_t s) {
+  CU_CHECK(cudaMemcpyToSymbolAsync(g_cfg, &c, sizeof(DevCfg), 0, cudaMemcpyHostToDevice, s));
+}
+inline void g_check_launch() { CU_CHECK(cudaGetLastError()); }
+#else
+inline void *g_alloc(size_t bytes) { return calloc(1, bytes ? bytes : 8); }
+inline void g_free(void *p) { free(p); }
+inline void g_zero(void *p, size_t bytes, cudaStream_t) { memset(p, 0, bytes); }
+inline void g_h2d(void *d, const void *h, size_t bytes, cudaStream_t) { memcpy(d, h, bytes); }
+inline void g_d2h(void *h, const void *d, size_t bytes, cudaStream_t) { memcpy(h, d, bytes); }
+inline void g_d2d(void *d, const void *s0, size_t bytes, cudaStream_t) { memmove(d, s0, bytes); }
+inline void copy2d(void *d, size_t dp, const void *s0, size_t sp, size_t width, size_t rows) {
+  for (size_t r = 0; r < rows; ++r) memcpy((char *)d + r * dp, (const char *)s0 + r * sp, width);
+}
+inline void g_d2h_2d(void *h, size_t hp, const void *d, size_t dp, size_t width, size_t rows, cudaStream_t) {
+  copy2d(h, hp, d, dp, width, rows);
+}
+inline void g_h2d_2d(void *d, size_t dp, const void *h, size_t hp, size_t width, size_t rows, cudaStream_t) {
+  copy2d(d, dp, h, hp, width, rows);
+}
+inline void g_d2d_2d(void *d, size_t dp, const void *s0, size_t sp, size_t width, size_t rows, cudaStream_t) {
+  copy2d(d, dp, s0, sp, width, rows);
+}
+inline void g_sync(cudaStream_t) {}
+inline void g_set_cfg(const DevCfg &c, cudaStream_t) { g_cfg = c; }
+inline void g_check_launch() {}
+#endif
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// robot.cpp:291-322 — cable attachment points of the CSPR (host, once)
+Pmat make_pmat() {
+  Pmat pm;
+  const double cible1[3] = {1.0941, -4.9074, 2.5542};
+  const double delta1[3] = {-0.765, 0.112, 3.74};
+  const double cible3[3] = {0.2098, 5.3409, 2.6236};
+  const double delta2[3] = {0.43, 0.125, 3.615};
+  double p1[3], p2[3];
+  const double p3[3] = {-5.9751, 0.1399, 6.1543};
+  for (int i = 0; i < 3; ++i) {
+    p1[i] = cible1[i] + delta1[i];
+    p2[i] = cible3[i] + delta2[i];
+  }
+  const int ind[3] = {1, 0, 2};
+  for (int i = 0; i < 3; ++i) {
+    const int it = ind[i];
+    pm.p[i][0] = -p1[it];
+    pm.p[i][1] = -p2[it];
+    pm.p[i][2] = -p3[it];
+  }
+  double cen[3];
+  for (int i = 0; i < 3; ++i) cen[i] = 1 / 3.0 * (pm.p[i][0] + pm.p[i][1] + pm.p[i][2]);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) pm.p[i][j] -= cen[i];
+  return pm;
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------- context
+struct batotp_ctx {
+  int device = 0;
+  cudaStream_t stream = 0;
+  std::string err;
+  int chunk = 16384;
+  long launches = 0;
+  DevCfg cfg;
+  bool haveCfg = false;
+  Ws w;
+  int capB = 0, capNc = 0, capSc = 0, capOc = 0, capOs = 0, capOutC = 0, capR = 0, capRT = 0;
+  bool capTrq = false;
+  std::vector<void *> wsAllocs;
+  // Thomas factor tables
+  double *d_cN = nullptr, *d_cC = nullptr;
+  int tabN = 0;
+  Pmat pm;
+  // staged inputs
+  void *d_theta = nullptr, *d_cart = nullptr;
+  double *d_ts = nullptr, *d_tres = nullptr;
+  int *d_n0 = nullptr;
+  size_t capIn = 0;
+  const void *in_theta = nullptr, *in_cart = nullptr;  // device views used by k_in_load
+  const double *in_ts = nullptr;
+  bool inF64 = false, hasTheta = false, hasCart = false;
+  int B = 0, n0max = 0;
+  // staged outputs
+  float *d_thetaOut = nullptr, *d_cartOut = nullptr, *d_trqOut = nullptr, *d_histOut = nullptr;
+  double *d_cartOutD = nullptr;
+  // which buffers hold the final rows after interp_output
+  const double *finSrc = nullptr, *finM = nullptr, *finTrq = nullptr, *finTrqM = nullptr;
+  // high-water marks so that steady-state chunks need no planning sync
+  int hwNc = 0, hwSc = 0;
+  std::vector<TrajState> hst;
+  int phase = 0;  // 0 none, 1 loaded, 2 input done, 3 sweeps done, 4 output done
+  bool lastHaveN0 = false;
+};
+
+namespace {
+
+#define LAUNCH_T(h, kern, nthreads, ...)                                                    \
+  do {                                                                                      \
+    const int nth_ = (nthreads);                                                            \
+    if (nth_ > 0) {                                                                         \
+      BATOTP_LAUNCH(kern, dim3(cdiv(nth_, 128)), dim3(128), (h)->stream, __VA_ARGS__);      \
+      g_check_launch();                                                                     \
+      (h)->launches++;                                                                      \
+    }                                                                                       \
+  } while (0)
+// (trajectory, point) kernels: nblk blocks of 128 points per trajectory
+#define LAUNCH_TP(h, kern, npts, ...)                                                       \
+  do {                                                                                      \
+    const int nblk_ = cdiv((npts), 128);                                                    \
+    if (nblk_ > 0 && (h)->B > 0) {                                                          \
+      BATOTP_LAUNCH(kern, dim3((unsigned)((size_t)nblk_ * (h)->B)), dim3(128), (h)->stream, \
+                    __VA_ARGS__, nblk_);                                                    \
+      g_check_launch();                                                                     \
+      (h)->launches++;                                                                      \
+    }                                                                                       \
+  } while (0)
+
+void free_ws(batotp_ctx *h) {
+  for (void *p : h->wsAllocs) g_free(p);
+  h->wsAllocs.clear();
+  h->capB = 0;
+}
+
+template <class T>
+T *ws_alloc(batotp_ctx *h, size_t count) {
+  void *p = g_alloc(count * sizeof(T));
+  h->wsAllocs.push_back(p);
+  return (T *)p;
+}
+
+void ensure_tabs(batotp_ctx *h, int n) {
+  if (n <= h->tabN) return;
+  g_free(h->d_cN);
+  g_free(h->d_cC);
+  n = std::max(n + 64, 4096);
+  std::vector<double> cN(n, 1.0), cC(n, 1.0);
+  // spline.cpp:259-268 (natural) and 229-237 (clamped): the same divisions, tabulated
+  cN[0] = 1.0;
+  if (n > 1) cN[1] = 1.0 / 4.0;
+  for (int i = 2; i < n; ++i) cN[i] = 1.0 / (4.0 - 1.0 * cN[i - 1]);
+  cC[0] = 1.0 / 2.0;
+  for (int i = 1; i < n; ++i) cC[i] = 1.0 / (4.0 - 1.0 * cC[i - 1]);
+  h->d_cN = (double *)g_alloc(n * sizeof(double));
+  h->d_cC = (double *)g_alloc(n * sizeof(double));
+  g_h2d(h->d_cN, cN.data(), n * sizeof(double), h->stream);
+  g_h2d(h->d_cC, cC.data(), n * sizeof(double), h->stream);
+  g_sync(h->stream);
+  h->tabN = n;
+}
+
+int oversample_cap(const batotp_ctx *h, int Sc) {
+  // nPtsMVCout bound for nFwd <= Sc (ba.cpp:1667-1685)
+  const batotp_cfg &c = h->cfg.c;
+  double outRes = c.out_res, sm = c.out_smooth_fact;
+  const double integRes = c.is_auto_integ_res ? 0.004 : c.integ_res;  // auto: >= minIntegRes (ba.cpp:512)
+  if (outRes < integRes) {
+    sm *= std::max(c.out_res / integRes, 1.0);
+    outRes = integRes;
+  }
+  const double integMax = c.is_auto_integ_res ? 0.2 : c.integ_res;
+  const double n = sm * (std::ceil(integMax * (double)(Sc - 1) / outRes + 1.0) + 1.0);
+  return std::max((int)n + 8, 16);
+}
+
+// smoothing decided on the host when it is uniform over the batch (ba.cpp:1667-1672, 1838)
+bool smooth_uniform_on(const batotp_ctx *h) {
+  const batotp_cfg &c = h->cfg.c;
+  if (c.is_auto_integ_res) return false;
+  double sm = c.out_smooth_fact;
+  if (c.out_res < c.integ_res) sm *= std::max(c.out_res / c.integ_res, 1.0);
+  return sm > 1.5;
+}
+
+int final_cap(const batotp_ctx *h, int Sc, int Os) {
+  const batotp_cfg &c = h->cfg.c;
+  const double integMax = c.is_auto_integ_res ? 0.2 : c.integ_res;
+  const double tLast = integMax * (double)(Sc - 1);
+  const int n = (int)std::ceil(tLast / c.out_res) + 8;
+  return std::max(std::max(n, 16), Os);
+}
+
+void ensure_ws(batotp_ctx *h, int B, int Nc, int Sc) {
+  const DevCfg &c = h->cfg;
+  const int Oc = oversample_cap(h, Sc);
+  const bool trq = c.trqOn != 0;
+  int Os = Oc;
+  if (!trq && smooth_uniform_on(h)) Os = (int)(Oc / c.c.out_smooth_fact) + 16;
+  const int OutC = final_cap(h, Sc, Os);
+  if (B <= h->capB && Nc <= h->capNc && Sc <= h->capSc && Oc <= h->capOc && Os <= h->capOs &&
+      OutC <= h->capOutC && c.R == h->capR && c.RT == h->capRT && trq == h->capTrq)
+    return;
+  free_ws(h);
+  Ws &w = h->w;
+  memset(&w, 0, sizeof(w));
+  const size_t b = (size_t)B;
+  const int R = c.R, RT = c.RT;
+  w.B = B;
+  w.Nc = Nc;
+  w.Sc = Sc;
+  w.Oc = Oc;
+  w.Os = Os;
+  w.OutC = OutC;
+  w.R = R;
+  w.RT = RT;
+  w.P = ws_alloc<double>(h, b * R * Nc);
+  w.Q = ws_alloc<double>(h, b * R * Nc);
+  w.M = ws_alloc<double>(h, b * R * Nc);
+  w.sC = ws_alloc<double>(h, b * Nc);
+  w.nrm = ws_alloc<double>(h, b * 2 * Nc);
+  w.tab = ws_alloc<double>(h, b * Nc * RT * 4);
+  w.hist = ws_alloc<double>(h, b * 4 * Sc);
+  w.flags = ws_alloc<unsigned char>(h, b * 2 * Sc);
+  w.st = ws_alloc<TrajState>(h, b);
+  w.mS = ws_alloc<double>(h, b * Sc);
+  w.sOut = ws_alloc<double>(h, b * Oc);
+  w.segO = ws_alloc<int>(h, b * Oc);
+  w.tauO = ws_alloc<double>(h, b * Oc);
+  w.O5 = ws_alloc<double>(h, b * R * Oc);
+  w.OA = ws_alloc<double>(h, b * R * Os);
+  w.OM = ws_alloc<double>(h, b * R * Os);
+  if (trq) {
+    w.OD = ws_alloc<double>(h, b * R * Oc);
+    w.OD2 = ws_alloc<double>(h, b * R * Oc);
+    w.Trq = ws_alloc<double>(h, b * MAXD * Oc);
+    w.Trq2 = ws_alloc<double>(h, b * MAXD * Oc);
+    w.TrqM = ws_alloc<double>(h, b * MAXD * Oc);
+    w.A = ws_alloc<double>(h, b * 4 * MAXD * Nc);
+    w.AM = ws_alloc<double>(h, b * 4 * MAXD * Nc);
+    w.GD = ws_alloc<double>(h, b * R * Nc);
+    w.GD2 = ws_alloc<double>(h, b * R * Nc);
+  }
+  w.queue = ws_alloc<int>(h, 4);
+  h->d_thetaOut = ws_alloc<float>(h, b * c.J * OutC);
+  h->d_cartOut = ws_alloc<float>(h, b * std::max(c.Cin, 1) * OutC);
+  h->d_trqOut = trq ? ws_alloc<float>(h, b * c.J * OutC) : nullptr;
+  h->d_cartOutD = (c.C == 7) ? ws_alloc<double>(h, b * 7 * OutC) : nullptr;
+  h->d_histOut = ws_alloc<float>(h, b * 4 * Sc);
+  h->capB = B;
+  h->capNc = Nc;
+  h->capSc = Sc;
+  h->capOc = Oc;
+  h->capOs = Os;
+  h->capOutC = OutC;
+  h->capR = R;
+  h->capRT = RT;
+  h->capTrq = trq;
+  ensure_tabs(h, std::max(std::max(Nc, Sc), Oc) + 8);
+}
+
+void set_cfg(batotp_ctx *h, const batotp_cfg *cfg) {
+  DevCfg d;
+  memset(&d, 0, sizeof(d));
+  d.c = *cfg;
+  d.J = cfg->n_joints;
+  d.Cin = cfg->n_cart;
+  const bool quat = (cfg->path_type == BATOTP_CART || cfg->path_type == BATOTP_BOTH) && cfg->n_cart == 6;
+  d.C = quat ? 7 : cfg->n_cart;
+  d.cartOn = (cfg->is_cart_vel_on || cfg->is_cart_acc_on) ? 1 : 0;
+  d.trqOn = cfg->is_trq_on ? 1 : 0;
+  if (d.C < 3) d.C = 3;  // adjust_s / interpSpecial always read cart rows 0..2 (ba.cpp:463, 697)
+  d.R = d.J + d.C;
+  d.RT = d.J + (d.cartOn ? 3 : 0) + (d.trqOn ? 4 * d.J : 0);
+  d.quadThresh = cfg->cart_thresh * cfg->cart_thresh;
+  const double Bt[6][6] = {{1. / 5, 3. / 40, 44. / 45, 19372. / 6561, 9017. / 3168, 35. / 384},
+                           {0, 9. / 40, -56. / 15, -25360. / 2187, -355. / 33, 0},
+                           {0, 0, 32. / 9, 64448. / 6561, 46732. / 5247, 500. / 1113},
+                           {0, 0, 0, -212. / 729, 49. / 176, 125. / 192},
+                           {0, 0, 0, 0, -5103. / 18656, -2187. / 6784},
+                           {0, 0, 0, 0, 0, 11. / 84}};  // ba.cpp:58-63, literals as written there
+  memcpy(d.B, Bt, sizeof(Bt));
+  h->cfg = d;
+  h->haveCfg = true;
+  g_set_cfg(d, h->stream);
+}
+
+int check_cfg(batotp_ctx *h) {
+  const batotp_cfg &c = h->cfg.c;
+  if (c.n_joints < 1 || c.n_joints > MAXD || c.n_cart < 0 || c.n_cart > MAXD) {
+    h->err = "nJoints/nCart outside 1..7";
+    return -1;
+  }
+  if (c.is_svd) {
+    h->err = "isSVD=1 is outside the accelerated scope (SURVEY §8f rank 3)";
+    return -1;
+  }
+  if (c.is_trq_on && c.is_parallel && !c.is_par2ser) {
+    h->err = "parallel-mechanism torque limits without isPar2Ser are outside the accelerated scope (SURVEY §8f rank 3)";
+    return -1;
+  }
+  if (c.is_trq_on && !((c.robot_type == BATOTP_RR && !c.is_parallel) || (c.robot_type == BATOTP_CSPR3DOF && c.is_parallel))) {
+    h->err = "torque limits need a dynamic model: only RR (serial) and CSPR3DOF (parallel) have one (robot.cpp:349-360, 463-474)";
+    return -1;
+  }
+  if (c.is_interp_only) {
+    h->err = "isInterpOnly is outside the accelerated scope (SURVEY §8f rank 2)";
+    return -1;
+  }
+  return 0;
+}
+
+// ---- strict-parity trig: the host evaluates the trig-bearing point functions with its libm,
+//      exactly as the reference does.  Rows travel D2H/H2D around the call.
+void host_rows_apply(batotp_ctx *h, double *base, int stride, bool over, int kind) {
+  // kind 1: fwdKin (theta rows -> cart rows); kind 2: aa2qVect on cart rows 3..6
+  const DevCfg &c = h->cfg;
+  const int B = h->B, R = c.R, J = c.J;
+  std::vector<double> buf((size_t)B * R * stride);
+  g_d2h(buf.data(), base, buf.size() * sizeof(double), h->stream);
+  h->hst.resize(B);
+  g_d2h(h->hst.data(), h->w.st, (size_t)B * sizeof(TrajState), h->stream);
+  g_sync(h->stream);
+  const int nth = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+  auto work = [&](int tid) {
+    for (int b = tid; b < B; b += nth) {
+      const TrajState &s = h->hst[b];
+      if (s.status & ST_FATAL_MASK) continue;
+      const int n = over ? s.nOver : s.nPts;
+      double *r0 = buf.data() + (size_t)b * R * stride;
+      if (kind == 1) {
+        for (int i = 0; i < n; ++i) {
+          double th[MAXD], xyz[3];
+          for (int j = 0; j < J; ++j) th[j] = r0[(size_t)j * stride + i];
+          if (c.c.robot_type == BATOTP_KUKA) {
+            fk_kuka_point(th, xyz);
+            for (int q = 0; q < 3; ++q) r0[(size_t)(J + q) * stride + i] = xyz[q];
+          } else if (c.c.robot_type == BATOTP_RR) {
+            fk_rr_point(th, xyz);
+            r0[(size_t)J * stride + i] = xyz[0];
+            r0[(size_t)(J + 1) * stride + i] = xyz[1];
+          }
+        }
+      } else if (kind == 2) {
+        double *r3 = r0 + (size_t)(J + 3) * stride, *r4 = r0 + (size_t)(J + 4) * stride,
+               *r5 = r0 + (size_t)(J + 5) * stride, *r6 = r0 + (size_t)(J + 6) * stride;
+        double aa[3] = {r3[0], r4[0], r5[0]}, q[4], qprev[4];
+        aa2q_dev(aa, qprev);
+        for (int i = 0; i < n; ++i) {
+          aa[0] = r3[i];
+          aa[1] = r4[i];
+          aa[2] = r5[i];
+          aa2q_dev(aa, q);
+          double qdir = 0;
+          for (int j = 0; j < 4; ++j) qdir += q[j] * qprev[j];
+          if (qdir < 0.0)
+            for (int j = 0; j < 4; ++j) q[j] = -q[j];
+          for (int j = 0; j < 4; ++j) qprev[j] = q[j];
+          r3[i] = q[0];
+          r4[i] = q[1];
+          r5[i] = q[2];
+          r6[i] = q[3];
+        }
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nth; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto &x : th) x.join();
+  // only the Cartesian rows changed
+  g_h2d_2d(base + (size_t)J * stride, (size_t)R * stride * sizeof(double), buf.data() + (size_t)J * stride,
+           (size_t)R * stride * sizeof(double), (size_t)c.C * stride * sizeof(double), (size_t)B, h->stream);
+  g_sync(h->stream);
+}
+
+// kinematics after a resampling stage (ba.cpp:245-280 mode 0; ba.cpp:616-632 mode 1; ba.cpp:1723-1741 mode 2)
+void apply_kinematics(batotp_ctx *h, int where) {
+  const DevCfg &c = h->cfg;
+  const int pt = c.c.path_type;
+  const bool over = (where == 2);
+  double *base = over ? h->w.O5 : h->w.P;
+  const int stride = over ? h->w.Oc : h->w.Nc;
+  int mode = 0;
+  if (pt == BATOTP_JOINT) {
+    if (where == 0)
+      mode = c.cartOn ? 1 : 3;
+    else
+      mode = (c.c.robot_type == BATOTP_GENJNT) ? (where == 1 ? 3 : 0) : 1;
+    if (mode == 1 && !(c.c.robot_type == BATOTP_KUKA || c.c.robot_type == BATOTP_RR)) mode = 0;  // no model
+  } else if (pt == BATOTP_CART) {
+    if (where == 0)
+      mode = (c.c.is_jnt_vel_on || c.c.is_jnt_acc_on || c.c.is_trq_on) ? 2 : 4;
+    else
+      mode = 2;
+    if (mode == 2 && c.c.robot_type != BATOTP_CSPR3DOF) mode = 0;
+  }
+  if (mode == 0) return;
+  if (mode == 1 && c.c.trig_mode == 1) {
+    host_rows_apply(h, base, stride, over, 1);
+    return;
+  }
+  LAUNCH_TP(h, k_pointfn, stride, h->w, base, stride, mode, over ? 1 : 0, h->pm);
+}
+
+void thomas_rows(batotp_ctx *h, const double *src, double *dst, int stride, int rows, int rowsPerTraj, int nsel,
+                 int clamped) {
+  ThomasTabs t{h->d_cN, h->d_cC};
+  LAUNCH_T(h, k_thomas_rows, h->B * rows, h->w, src, dst, stride, rows, rowsPerTraj, nsel, clamped, t);
+}
+
+template <int J, bool CART, bool TRQ>
+void launch_sweep(batotp_ctx *h) {
+  g_zero(h->w.queue, sizeof(int) * 4, h->stream);
+#ifndef BATOTP_HOST_EMU
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int perSm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_sweep<J, CART, TRQ>, 128, 0);
+  if (perSm < 1) perSm = 1;
+  int blocks = std::min(sms * perSm, cdiv(h->B, 128));
+  if (blocks < 1) blocks = 1;
+#else
+  int blocks = 1;
+#endif
+  BATOTP_LAUNCH((k_sweep<J, CART, TRQ>), dim3(blocks), dim3(128), h->stream, h->w);
+  g_check_launch();
+  h->launches++;
+}
+
+int dispatch_sweep(batotp_ctx *h) {
+  const DevCfg &c = h->cfg;
+  const int key = c.J * 4 + (c.cartOn ? 2 : 0) + (c.trqOn ? 1 : 0);
+  switch (key) {
+    case 7 * 4 + 0: launch_sweep<7, false, false>(h); return 0;  // GEN7DOF
+    case 7 * 4 + 2: launch_sweep<7, true, false>(h); return 0;   // KUKA-LWR-IV
+    case 6 * 4 + 2: launch_sweep<6, true, false>(h); return 0;   // UR5
+    case 6 * 4 + 0: launch_sweep<6, false, false>(h); return 0;
+    case 2 * 4 + 3: launch_sweep<2, true, true>(h); return 0;    // RR
+    case 3 * 4 + 3: launch_sweep<3, true, true>(h); return 0;    // CSPR3DOF (Par2Ser)
+    case 3 * 4 + 2: launch_sweep<3, true, false>(h); return 0;
+    case 2 * 4 + 2: launch_sweep<2, true, false>(h); return 0;
+    default:
+      h->err = "no sweep kernel instantiated for this (nJoints, Cartesian, torque) combination; add a line to dispatch_sweep()";
+      return -1;
+  }
+}
+
+}  // namespace
+#include "host_strict.inl"
+namespace {
+// ---- phases ---------------------------------------------------------------------------
+void stage_inputs(batotp_ctx *h, const batotp_batch_in *in, int first, int B) {
+  const DevCfg &c = h->cfg;
+  const int n0 = in->n0_max;
+  h->inF64 = (in->theta_f64 || in->cart_f64);
+  h->hasTheta = (in->theta_f32 || in->theta_f64);
+  h->hasCart = (in->cart_f32 || in->cart_f64);
+  const size_t es = h->inF64 ? 8 : 4;
+  const size_t thBytes = (size_t)B * c.J * n0 * es, caBytes = (size_t)B * c.Cin * n0 * es;
+  const void *th = h->inF64 ? (const void *)in->theta_f64 : (const void *)in->theta_f32;
+  const void *ca = h->inF64 ? (const void *)in->cart_f64 : (const void *)in->cart_f32;
+  // per-trajectory tres / n0 (small)
+  std::vector<double> tres(B);
+  for (int b = 0; b < B; ++b) tres[b] = in->tres ? in->tres[first + b] : in->tres_all;
+  const size_t need = std::max(thBytes, caBytes);
+  if (need > h->capIn || !h->d_tres) {
+    g_free(h->d_theta);
+    g_free(h->d_cart);
+    g_free(h->d_ts);
+    g_free(h->d_tres);
+    g_free(h->d_n0);
+    const size_t capB = (size_t)std::max(h->chunk, B);
+    h->d_theta = g_alloc(capB * c.J * n0 * 8);
+    h->d_cart = g_alloc(capB * std::max(c.Cin, 1) * n0 * 8);
+    h->d_ts = (double *)g_alloc(capB * n0 * 8);
+    h->d_tres = (double *)g_alloc(capB * 8);
+    h->d_n0 = (int *)g_alloc(capB * 4);
+    h->capIn = capB * (size_t)std::max(c.J, c.Cin) * n0 * 8;
+  }
+  g_h2d(h->d_tres, tres.data(), (size_t)B * 8, h->stream);
+  if (in->on_device) {
+    h->in_theta = th ? (const char *)th + (size_t)first * c.J * n0 * es : nullptr;
+    h->in_cart = ca ? (const char *)ca + (size_t)first * c.Cin * n0 * es : nullptr;
+    h->in_ts = in->timestamp ? in->timestamp + (size_t)first * n0 : nullptr;
+  } else {
+    if (th) g_h2d(h->d_theta, (const char *)th + (size_t)first * c.J * n0 * es, thBytes, h->stream);
+    if (ca) g_h2d(h->d_cart, (const char *)ca + (size_t)first * c.Cin * n0 * es, caBytes, h->stream);
+    if (in->timestamp) g_h2d(h->d_ts, in->timestamp + (size_t)first * n0, (size_t)B * n0 * 8, h->stream);
+    h->in_theta = th ? h->d_theta : nullptr;
+    h->in_cart = ca ? h->d_cart : nullptr;
+    h->in_ts = in->timestamp ? h->d_ts : nullptr;
+  }
+  if (in->n0) g_h2d(h->d_n0, in->n0 + first, (size_t)B * 4, h->stream);
+  g_sync(h->stream);  // `tres` is a local
+  h->B = B;
+  h->n0max = n0;
+}
+
+void run_load_prepare(batotp_ctx *h, bool haveN0) {
+  Ws &w = h->w;
+  w.B = h->B;
+  const int *n0 = haveN0 ? h->d_n0 : nullptr;
+  if (h->inF64)
+    LAUNCH_TP(h, (k_in_load<double>), h->n0max, w, (const double *)h->in_theta, (const double *)h->in_cart, n0,
+              h->d_tres, h->n0max);
+  else
+    LAUNCH_TP(h, (k_in_load<float>), h->n0max, w, (const float *)h->in_theta, (const float *)h->in_cart, n0,
+              h->d_tres, h->n0max);
+  LAUNCH_T(h, k_in_prepare, h->B, w, h->in_ts, h->n0max, h->hasTheta ? 1 : 0, h->hasCart ? 1 : 0);
+}
+
+// returns max over trajectories of (nNew) after the special-pass plan, for capacity planning
+int read_plan_max(batotp_ctx *h, int *anyGridCap) {
+  h->hst.resize(h->B);
+  g_d2h(h->hst.data(), h->w.st, (size_t)h->B * sizeof(TrajState), h->stream);
+  g_sync(h->stream);
+  int mx = 0, cap = 0;
+  for (int b = 0; b < h->B; ++b) {
+    const TrajState &s = h->hst[b];
+    if (s.status & ST_GRID_CAP) cap = 1;
+    if (s.status & ST_FATAL_MASK) continue;
+    mx = std::max(mx, std::max(s.nNew, s.nPts));
+  }
+  if (anyGridCap) *anyGridCap = cap;
+  return mx;
+}
+
+int do_interp_input(batotp_ctx *h, bool haveN0, bool planSync) {
+  const DevCfg &c = h->cfg;
+  Ws &w = h->w;
+  const bool adjust = !(c.c.s_weights[1] + c.c.s_weights[2] < 1e-8);  // ba.cpp:416
+  run_load_prepare(h, haveN0);
+  const int pt = c.c.path_type;
+  if ((pt == BATOTP_CART || pt == BATOTP_BOTH) && c.Cin == 6) {  // ba.cpp:185-192
+    if (c.c.trig_mode == 1)
+      host_rows_apply(h, w.P, w.Nc, false, 2);
+    else
+      LAUNCH_T(h, k_aa2q, h->B, w);
+  }
+  if (c.c.input_decim_fact > 1 || c.c.smooth_window > 1) {
+    LAUNCH_T(h, k_in_smooth_decimate, h->B * c.R, w);
+    LAUNCH_T(h, k_in_decim_fix, h->B, w);
+  }
+  apply_kinematics(h, 0);
+  if (adjust) {
+    LAUNCH_T(h, k_adjust_s, h->B, w, 1);
+    if (planSync) {
+      const int mx = read_plan_max(h, nullptr);
+      const int need = (int)(mx * 1.125) + 64;
+      if (need > w.Nc) return need;  // caller grows the workspace and restarts the chunk
+    }
+    thomas_rows(h, w.P, w.M, w.Nc, c.R, c.R, 0, 0);
+    LAUNCH_T(h, k_march, h->B, w);
+    std::swap(w.P, w.Q);
+    apply_kinematics(h, 1);
+    LAUNCH_T(h, k_adjust_s, h->B, w, 0);
+    thomas_rows(h, w.P, w.M, w.Nc, c.R, c.R, 0, 0);
+    LAUNCH_TP(h, k_resample, w.Nc, w);
+    LAUNCH_T(h, k_resample_commit, h->B, w);
+    std::swap(w.P, w.Q);
+    apply_kinematics(h, 1);
+  }
+  // ba.cpp:297-305: final splines on the uniform grid, then the dynamic model
+  thomas_rows(h, w.P, w.M, w.Nc, c.R, c.R, 0, 0);
+  LAUNCH_T(h, k_final_plan, h->B, w);
+  if (c.trqOn) {
+    LAUNCH_TP(h, k_eval_grid, w.Nc, w, w.GD, w.GD2);
+    if (!c.c.is_parallel && c.c.trig_mode == 1)
+      host_dyn_rr_grid(h);
+    else
+      LAUNCH_TP(h, k_dyn_grid, w.Nc, w, h->pm);
+    thomas_rows(h, w.A, w.AM, w.Nc, 4 * MAXD, 4 * MAXD, 0, 0);
+  }
+  LAUNCH_TP(h, k_build_table, w.Nc, w, w.A, w.AM);
+  h->phase = 2;
+  return 0;
+}
+
+int do_sweeps(batotp_ctx *h) {
+  if (dispatch_sweep(h) != 0) return -1;
+  h->phase = 3;
+  return 0;
+}
+
+void do_interp_output(batotp_ctx *h) {
+  const DevCfg &c = h->cfg;
+  Ws &w = h->w;
+  ThomasTabs t{h->d_cN, h->d_cC};
+  LAUNCH_T(h, k_out_plan, h->B, w, t);
+  LAUNCH_TP(h, k_out_s, w.Oc, w);
+  LAUNCH_T(h, k_out_segs, h->B, w);
+  LAUNCH_TP(h, k_out_eval, w.Oc, w);
+  apply_kinematics(h, 2);
+  const double *cur = w.O5;
+  int curStride = w.Oc;
+  if (c.trqOn) {
+    // re-spline theta(t) (and cart(t) for the parallel robot) to get time derivatives
+    thomas_rows(h, w.O5, w.OM, w.Oc, c.c.is_parallel ? c.R : c.J, c.R, 1, c.c.is_parallel ? 0 : 1);
+    LAUNCH_TP(h, k_out_knot_eval, w.Oc, w);
+    if (!c.c.is_parallel && c.c.trig_mode == 1)
+      host_dyn_rr_out(h);
+    else
+      LAUNCH_TP(h, k_out_trq, w.Oc, w, h->pm);
+    cur = w.OA;
+  }
+  LAUNCH_T(h, k_out_smooth_plan, h->B, w);
+  const double *trqCur = w.Trq;
+  if (smooth_uniform_on(h) || c.c.is_auto_integ_res) {
+    double *dst = (cur == w.O5) ? w.OA : w.O5;
+    const int dstStride = (cur == w.O5) ? w.Os : w.Oc;
+    LAUNCH_TP(h, k_out_smooth, std::min(curStride, dstStride), w, cur, curStride, dst, dstStride);
+    cur = dst;
+    curStride = dstStride;
+    trqCur = w.Trq2;
+  }
+  LAUNCH_T(h, k_out_final_plan, h->B, w);
+  // natural splines of the rows for the final resample (ba.cpp:1889-1915; used where isReinterp).
+  // OM shares the pitch of `cur` by construction (Os == Oc whenever cur can be O5 here).
+  const bool needRe = (c.c.out_res < c.c.integ_res) || c.c.is_auto_integ_res;
+  if (needRe) {
+    thomas_rows(h, cur, w.OM, curStride, c.R, c.R, 2, 0);
+    if (c.trqOn) thomas_rows(h, trqCur, w.TrqM, w.Oc, c.J, MAXD, 2, 0);
+  }
+  h->finSrc = cur;
+  h->finM = w.OM;
+  h->finTrq = trqCur;
+  h->finTrqM = w.TrqM;
+  const bool strictQuat = (c.C == 7 && c.c.trig_mode == 1);
+  LAUNCH_TP(h, k_out_pack, w.OutC, w, cur, (const double *)w.OM, curStride, trqCur, (const double *)w.TrqM,
+            h->d_thetaOut, h->d_cartOut, h->d_trqOut, strictQuat ? h->d_cartOutD : (double *)nullptr);
+  LAUNCH_TP(h, k_pack_hist, w.Sc, w, h->d_histOut);
+  h->phase = 4;
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------- C ABI
+extern "C" {
+
+int batotp_cuda_device_count(void) {
+#ifndef BATOTP_HOST_EMU
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+#else
+  return 1;
+#endif
+}
+
+int batotp_cuda_create(int device, batotp_handle *out) {
+  if (!out) return -1;
+  *out = nullptr;
+#ifndef BATOTP_HOST_EMU
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    fprintf(stderr, "batotp_cuda: no CUDA device available (this library has no CPU fallback)\n");
+    return -1;
+  }
+  if (device < 0 || device >= n) return -1;
+  if (cudaSetDevice(device) != cudaSuccess) return -1;
+#endif
+  batotp_ctx *h = new batotp_ctx();
+  h->device = device;
+  memset(&h->w, 0, sizeof(h->w));
+#ifndef BATOTP_HOST_EMU
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return -1;
+  }
+#endif
+  h->pm = make_pmat();
+  *out = h;
+  return 0;
+}
+
+int batotp_cuda_destroy(batotp_handle h) {
+  if (!h) return -1;
+  free_ws(h);
+  g_free(h->d_cN);
+  g_free(h->d_cC);
+  g_free(h->d_theta);
+  g_free(h->d_cart);
+  g_free(h->d_ts);
+  g_free(h->d_tres);
+  g_free(h->d_n0);
+#ifndef BATOTP_HOST_EMU
+  cudaStreamDestroy(h->stream);
+#endif
+  delete h;
+  return 0;
+}
+
+const char *batotp_cuda_last_error(batotp_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+int batotp_cuda_set_chunk(batotp_handle h, int chunk) {
+  if (!h || chunk < 1) return -1;
+  h->chunk = chunk;
+  return 0;
+}
+
+long batotp_cuda_launch_count(batotp_handle h) { return h ? h->launches : 0; }
+
+static int load_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_in *in, int first, int B) {
+#ifndef BATOTP_HOST_EMU
+  CU_CHECK(cudaSetDevice(h->device));
+#endif
+  if (cfg) {
+    set_cfg(h, cfg);
+    if (check_cfg(h) != 0) return -1;
+  }
+  if (!h->haveCfg) {
+    h->err = "no configuration loaded";
+    return -1;
+  }
+  if (!(in->theta_f32 || in->theta_f64 || in->cart_f32 || in->cart_f64)) {
+    h->err = "batch input holds neither joint nor Cartesian data";
+    return -1;
+  }
+  if ((in->theta_f32 || in->cart_f32) && (in->theta_f64 || in->cart_f64)) {
+    h->err = "mixing float32 and float64 payloads is not supported";
+    return -1;
+  }
+  stage_inputs(h, in, first, B);
+  h->phase = 1;
+  return 0;
+}
+
+// one chunk through interpInputData with capacity planning / retry
+static int chunk_interp_input(batotp_handle h, bool haveN0) {
+  int Nc = std::max(h->hwNc, h->n0max + 8);
+  int Sc = std::max(h->hwSc, 1024);
+  bool plan = (h->hwNc == 0);
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    ensure_ws(h, std::max(h->B, h->capB), Nc, Sc);
+    h->w.B = h->B;
+    const int need = do_interp_input(h, haveN0, plan);
+    if (need > 0) {  // planning pass asked for more room
+      Nc = need;
+      plan = false;
+      continue;
+    }
+    int gridCap = 0;
+    const int mx = read_plan_max(h, &gridCap);
+    if (gridCap) {
+      Nc = std::max((int)(Nc * 1.5), (int)(mx * 1.125) + 64);
+      plan = false;
+      continue;
+    }
+    h->hwNc = std::max(h->hwNc, Nc);
+    return 0;
+  }
+  h->err = "grid capacity retry limit reached";
+  return -1;
+}
+
+static int chunk_sweeps_output(batotp_handle h, bool haveN0) {
+  for (int attempt = 0; attempt < 10; ++attempt) {
+    if (do_sweeps(h) != 0) return -1;
+    h->hst.resize(h->B);
+    g_d2h(h->hst.data(), h->w.st, (size_t)h->B * sizeof(TrajState), h->stream);
+    g_sync(h->stream);
+    bool stepCap = false;
+    int mxF = 0;
+    for (int b = 0; b < h->B; ++b) {
+      if (h->hst[b].status & ST_STEP_CAP) stepCap = true;
+      mxF = std::max(mxF, std::max(h->hst[b].nFwd, h->hst[b].nRev));
+    }
+    if (!stepCap) {
+      h->hwSc = std::max(h->hwSc, std::min(h->w.Sc, (int)(mxF * 1.25) + 64));
+      return 0;
+    }
+    // grow the step capacity and redo the chunk from the start (the status word is sticky)
+    const int Sc = h->w.Sc * 2;
+    const int Nc = h->w.Nc;
+    ensure_ws(h, h->capB, Nc, Sc);
+    h->w.B = h->B;
+    const int need = do_interp_input(h, haveN0, false);
+    (void)need;
+  }
+  h->err = "step capacity retry limit reached";
+  return -1;
+}
+
+int batotp_cuda_load(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_in *in) {
+  if (!h || !in) return -1;
+  try {
+    if (in->B > h->chunk) h->chunk = in->B;
+    h->lastHaveN0 = in->n0 != nullptr;
+    return load_chunk(h, cfg, in, 0, in->B);
+  } catch (const Err &e) {
+    h->err = e.msg;
+    return -1;
+  }
+}
+int batotp_cuda_interp_input(batotp_handle h) {
+  if (!h || h->phase < 1) return -1;
+  try {
+    return chunk_interp_input(h, h->lastHaveN0);
+  } catch (const Err &e) {
+    h->err = e.msg;
+    return -1;
+  }
+}
+int batotp_cuda_sweeps(batotp_handle h) {
+  if (!h || h->phase < 2) return -1;
+  try {
+    return chunk_sweeps_output(h, h->lastHaveN0);
+  } catch (const Err &e) {
+    h->err = e.msg;
+    return -1;
+  }
+}
+int batotp_cuda_interp_output(batotp_handle h) {
+  if (!h || h->phase < 3) return -1;
+  try {
+    do_interp_output(h);
+    g_sync(h->stream);
+    return 0;
+  } catch (const Err &e) {
+    h->err = e.msg;
+    return -1;
+  }
+}
+
+static void fetch_chunk(batotp_handle h, batotp_batch_out *out, int first) {
+  const DevCfg &c = h->cfg;
+  const Ws &w = h->w;
+  const int B = h->B;
+  h->hst.resize(B);
+  g_d2h(h->hst.data(), w.st, (size_t)B * sizeof(TrajState), h->stream);
+  g_sync(h->stream);
+  if (out->on_device) throw Err{"batotp_batch_out.on_device is not implemented yet"};
+  for (int b = 0; b < B; ++b) {
+    const TrajState &s = h->hst[b];
+    const int g = first + b;
+    if (out->status) out->status[g] = s.status;
+    if (out->n_rev) out->n_rev[g] = s.nRev;
+    if (out->n_fwd) out->n_fwd[g] = s.nFwd;
+    if (out->n_out) out->n_out[g] = (s.status & ST_FATAL_MASK) ? 0 : s.nOut;
+    if (out->n_cart_out) out->n_cart_out[g] = (s.status & ST_FATAL_MASK) ? 0 : s.nCartOut;
+    if (out->n_grid) out->n_grid[g] = s.nPtsC;
+    if (out->t_total) out->t_total[g] = s.tFwd;
+    if (out->t_rev) out->t_rev[g] = s.tRev;
+    if (out->s_last_sec) out->s_last_sec[g] = s.sLastSec;
+    if (out->out_sres) out->out_sres[g] = s.sresOut;
+  }
+  const int oc = out->out_cap, wc = std::min(out->out_cap, w.OutC);
+  if (out->theta_out && oc > 0)
+    g_d2h_2d(out->theta_out + (size_t)first * c.J * oc, (size_t)oc * 4, h->d_thetaOut, (size_t)w.OutC * 4,
+             (size_t)wc * 4, (size_t)B * c.J, h->stream);
+  if (out->trq_out && oc > 0 && c.trqOn)
+    g_d2h_2d(out->trq_out + (size_t)first * c.J * oc, (size_t)oc * 4, h->d_trqOut, (size_t)w.OutC * 4,
+             (size_t)wc * 4, (size_t)B * c.J, h->stream);
+  if (out->cart_out && oc > 0 && c.Cin > 0) {
+    if (c.C == 7 && c.c.trig_mode == 1) {
+      host_q2aa_out(h, out, first);
+    } else {
+      g_d2h_2d(out->cart_out + (size_t)first * c.Cin * oc, (size_t)oc * 4, h->d_cartOut, (size_t)w.OutC * 4,
+               (size_t)wc * 4, (size_t)B * c.Cin, h->stream);
+    }
+  }
+  const int hc = out->hist_cap, hw = std::min(out->hist_cap, w.Sc);
+  if (out->hist && hc > 0)
+    g_d2h_2d(out->hist + (size_t)first * 4 * hc, (size_t)hc * 4, h->d_histOut, (size_t)w.Sc * 4, (size_t)hw * 4,
+             (size_t)B * 4, h->stream);
+  if (out->flags && hc > 0)
+    g_d2h_2d(out->flags + (size_t)first * 2 * hc, (size_t)hc, w.flags, (size_t)w.Sc, (size_t)hw, (size_t)B * 2,
+             h->stream);
+  g_sync(h->stream);
+}
+
+int batotp_cuda_fetch(batotp_handle h, batotp_batch_out *out) {
+  if (!h || !out || h->phase < 4) return -1;
+  try {
+    fetch_chunk(h, out, 0);
+    return 0;
+  } catch (const Err &e) {
+    h->err = e.msg;
+    return -1;
+  }
+}
+
+int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_in *in,
+                               batotp_batch_out *out) {
+  if (!h || !cfg || !in || !out) return -1;
+  try {
+    bool first = true;
+    for (int at = 0; at < in->B; at += h->chunk) {
+      const int B = std::min(h->chunk, in->B - at);
+      if (load_chunk(h, first ? cfg : nullptr, in, at, B) != 0) return -1;
+      first = false;
+      h->lastHaveN0 = in->n0 != nullptr;
+      if (chunk_interp_input(h, h->lastHaveN0) != 0) return -1;
+      if (chunk_sweeps_output(h, h->lastHaveN0) != 0) return -1;
+      do_interp_output(h);
+      fetch_chunk(h, out, at);
+    }
+    return 0;
+  } catch (const Err &e) {
+    h->err = e.msg;
+    return -1;
+  }
+}
+
+int batotp_cuda_mvc_per_sample(batotp_handle h, double sdot_start, double *sdot_out, int cap) {
+  if (!h || h->phase < 2 || !sdot_out) return -1;
+  try {
+    return run_mvc_per_sample(h, sdot_start, sdot_out, cap);
+  } catch (const Err &e) {
+    h->err = e.msg;
+    return -1;
+  }
+}
+
+int batotp_cuda_get_f64(batotp_handle h, const char *name, int traj, int row, double *buf, int cap) {
+  if (!h || h->phase < 2 || traj < 0 || traj >= h->B) return -1;
+  try {
+    const DevCfg &c = h->cfg;
+    const Ws &w = h->w;
+    TrajState s;
+    g_d2h(&s, w.st + traj, sizeof(TrajState), h->stream);
+    g_sync(h->stream);
+    const std::string n(name);
+    const double *src = nullptr;
+    int len = 0;
+    auto prow = [&](const double *base, int r) { return base + ((size_t)traj * c.R + r) * w.Nc; };
+    auto arow = [&](const double *base, int k, int r) { return base + (((size_t)traj * 4 + k) * MAXD + r) * w.Nc; };
+    if (n == "thetaC_y") { src = prow(w.P, row); len = s.nPtsC; }
+    else if (n == "thetaC_m") { src = prow(w.M, row); len = s.nPtsC; }
+    else if (n == "cartC_y") { src = prow(w.P, c.J + row); len = s.nPtsC; }
+    else if (n == "cartC_m") { src = prow(w.M, c.J + row); len = s.nPtsC; }
+    else if (n == "theta" && c.trqOn) { src = prow(w.Q, row); len = s.nPts; }
+    else if (n == "cart" && c.trqOn) { src = prow(w.Q, c.J + row); len = s.nPts; }
+    else if (n.size() == 2 && n[0] == 'a' && n[1] >= '1' && n[1] <= '4' && c.trqOn) { src = arow(w.A, n[1] - '1', row); len = s.nPts; }
+    else if (n.size() == 5 && n[0] == 'a' && n.substr(2) == "C_m" && c.trqOn) { src = arow(w.AM, n[1] - '1', row); len = s.nPts; }
+    else if (h->phase >= 3 && n == "s_rev") { src = w.hist + (size_t)traj * 4 * w.Sc + (w.Sc - s.nRev); len = s.nRev; }
+    else if (h->phase >= 3 && n == "sdot_rev") { src = w.hist + (size_t)traj * 4 * w.Sc + w.Sc + (w.Sc - s.nRev); len = s.nRev; }
+    else if (h->phase >= 3 && n == "s_fwd") { src = w.hist + (size_t)traj * 4 * w.Sc + 2 * (size_t)w.Sc; len = s.nFwd; }
+    else if (h->phase >= 3 && n == "sdot_fwd") { src = w.hist + (size_t)traj * 4 * w.Sc + 3 * (size_t)w.Sc; len = s.nFwd; }
+    else return -1;
+    if (s.status & ST_FATAL_MASK) return 0;
+    const int m = std::min(len, cap);
+    if (buf && m > 0) {
+      g_d2h(buf, src, (size_t)m * sizeof(double), h->stream);
+      g_sync(h->stream);
+    }
+    return len;
+  } catch (const Err &e) {
+    h->err = e.msg;
+    return -1;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// host_strict.inl — strict-parity trig (cfg.trig_mode == 1), included by batotp_cuda.cu.
+//
+// batotp's kinematics/dynamics call sin/cos/atan2 of the host libm (robot.cpp:130-136,
+// 196-199, 408-419; util.cpp:544-549, 574).  CUDA's FP64 sin/cos are accurate to 1-2 ulp but
+// not bit-identical to glibc, and the algorithm amplifies a 1-ulp table difference into a
+// different integer step count.  So in strict mode the trig-bearing POINT
+// functions are evaluated by this host layer with the host libm — exactly what the reference
+// does — between device stages; everything else (splines, sweeps, interpolation) stays on the
+// device.  trig_mode == 0 keeps these on the device (CUDA sincos) for throughput.
+namespace {
+
+// dynRR on the final grid (findDynModel, ba.cpp:905-914): Q/GD/GD2 rows -> A rows
+void host_dyn_rr_grid(batotp_ctx *h) {
+  const DevCfg &c = h->cfg;
+  const Ws &w = h->w;
+  const int B = h->B, R = c.R, Nc = w.Nc;
+  std::vector<double> q((size_t)B * R * Nc), d1(q.size()), d2(q.size()), A((size_t)B * 4 * MAXD * Nc, 0.0);
+  g_d2h(q.data(), w.Q, q.size() * 8, h->stream);
+  g_d2h(d1.data(), w.GD, q.size() * 8, h->stream);
+  g_d2h(d2.data(), w.GD2, q.size() * 8, h->stream);
+  h->hst.resize(B);
+  g_d2h(h->hst.data(), w.st, (size_t)B * sizeof(TrajState), h->stream);
+  g_sync(h->stream);
+  for (int b = 0; b < B; ++b) {
+    const TrajState &s = h->hst[b];
+    if (s.status & ST_FATAL_MASK) continue;
+    for (int i = 0; i < s.nPts; ++i) {
+      double th[2], v1[2], v2[2], a1[2], a2[2], a3[2], a4[2];
+      for (int k = 0; k < 2; ++k) {
+        th[k] = q[((size_t)b * R + k) * Nc + i];
+        v1[k] = d1[((size_t)b * R + k) * Nc + i];
+        v2[k] = d2[((size_t)b * R + k) * Nc + i];
+      }
+      dyn_rr_point(th, v1, v2, a1, a2, a3, a4);
+      const double *aa[4] = {a1, a2, a3, a4};
+      for (int k = 0; k < 4; ++k)
+        for (int j = 0; j < 2; ++j) A[(((size_t)b * 4 + k) * MAXD + j) * Nc + i] = aa[k][j];
+    }
+  }
+  g_h2d(w.A, A.data(), A.size() * 8, h->stream);
+  g_sync(h->stream);
+}
+
+// dynRR at the output sites (ba.cpp:1815-1825): OA/OD/OD2 rows -> Trq rows
+void host_dyn_rr_out(batotp_ctx *h) {
+  const DevCfg &c = h->cfg;
+  const Ws &w = h->w;
+  const int B = h->B, R = c.R, Oc = w.Oc;
+  std::vector<double> q((size_t)B * R * Oc), d1(q.size()), d2(q.size()), T((size_t)B * MAXD * Oc, 0.0);
+  g_d2h(q.data(), w.OA, q.size() * 8, h->stream);
+  g_d2h(d1.data(), w.OD, q.size() * 8, h->stream);
+  g_d2h(d2.data(), w.OD2, q.size() * 8, h->stream);
+  h->hst.resize(B);
+  g_d2h(h->hst.data(), w.st, (size_t)B * sizeof(TrajState), h->stream);
+  g_sync(h->stream);
+  for (int b = 0; b < B; ++b) {
+    const TrajState &s = h->hst[b];
+    if (s.status & ST_FATAL_MASK) continue;
+    for (int i = 0; i < s.nOver; ++i) {
+      double th[2], v1[2], v2[2], a1[2], a2[2], a3[2], a4[2];
+      for (int k = 0; k < 2; ++k) {
+        th[k] = q[((size_t)b * R + k) * Oc + i];
+        v1[k] = d1[((size_t)b * R + k) * Oc + i];
+        v2[k] = d2[((size_t)b * R + k) * Oc + i];
+      }
+      dyn_rr_point(th, v1, v2, a1, a2, a3, a4);
+      for (int j = 0; j < 2; ++j) T[((size_t)b * MAXD + j) * Oc + i] = a2[j] + a3[j] + a4[j];
+    }
+  }
+  g_h2d(w.Trq, T.data(), T.size() * 8, h->stream);
+  g_sync(h->stream);
+}
+
+// q2aaVect on the final Cartesian rows (ba.cpp:382-403, 1922-1929) and the float cast
+void host_q2aa_out(batotp_ctx *h, batotp_batch_out *out, int first) {
+  const Ws &w = h->w;
+  const int B = h->B, OutC = w.OutC, oc = out->out_cap;
+  std::vector<double> q((size_t)B * 7 * OutC);
+  g_d2h(q.data(), h->d_cartOutD, q.size() * 8, h->stream);
+  g_sync(h->stream);
+  for (int b = 0; b < B; ++b) {
+    const TrajState &s = h->hst[b];
+    if (s.status & ST_FATAL_MASK) continue;
+    float *o = out->cart_out + (size_t)(first + b) * 6 * oc;
+    for (int i = 0; i < s.nCartOut && i < oc; ++i) {
+      double cv[7], aa[3];
+      for (int r = 0; r < 7; ++r) cv[r] = q[((size_t)b * 7 + r) * OutC + i];
+      q2aa_dev(cv + 3, aa);
+      for (int r = 0; r < 3; ++r) o[(size_t)r * oc + i] = (float)cv[r];
+      for (int r = 0; r < 3; ++r) o[(size_t)(3 + r) * oc + i] = (float)aa[r];
+    }
+  }
+}
+
+template <int J, bool CART, bool TRQ>
+void launch_mvc(batotp_ctx *h, double sdotStart, double *d_out, int cap) {
+  LAUNCH_TP(h, (k_mvc<J, CART, TRQ>), h->w.Nc, h->w, sdotStart, d_out, cap);
+}
+
+int run_mvc_per_sample(batotp_ctx *h, double sdotStart, double *sdot_out, int cap) {
+  const DevCfg &c = h->cfg;
+  double *d_out = (double *)g_alloc((size_t)h->B * cap * 8);
+  g_zero(d_out, (size_t)h->B * cap * 8, h->stream);
+  const int key = c.J * 4 + (c.cartOn ? 2 : 0) + (c.trqOn ? 1 : 0);
+  int rc = 0;
+  switch (key) {
+    case 7 * 4 + 0: launch_mvc<7, false, false>(h, sdotStart, d_out, cap); break;
+    case 7 * 4 + 2: launch_mvc<7, true, false>(h, sdotStart, d_out, cap); break;
+    case 6 * 4 + 2: launch_mvc<6, true, false>(h, sdotStart, d_out, cap); break;
+    case 6 * 4 + 0: launch_mvc<6, false, false>(h, sdotStart, d_out, cap); break;
+    case 2 * 4 + 3: launch_mvc<2, true, true>(h, sdotStart, d_out, cap); break;
+    case 3 * 4 + 3: launch_mvc<3, true, true>(h, sdotStart, d_out, cap); break;
+    case 3 * 4 + 2: launch_mvc<3, true, false>(h, sdotStart, d_out, cap); break;
+    case 2 * 4 + 2: launch_mvc<2, true, false>(h, sdotStart, d_out, cap); break;
+    default: h->err = "no kernel instantiated for this configuration"; rc = -1;
+  }
+  if (rc == 0) {
+    g_d2h(sdot_out, d_out, (size_t)h->B * cap * 8, h->stream);
+    g_sync(h->stream);
+  }
+  g_free(d_out);
+  return rc;
+}
+
+}  // namespace

@@ -1,0 +1,800 @@
+// k_input.cuh — device kernels for BA::interpInputData (batotp/ba.cpp:95-316) and the
+// Spline / util / Robot helpers it calls.  Reference lines are cited per kernel.
+//
+// Kernel shapes:  T  = one thread per trajectory (strictly sequential walkers)
+//                 TR = one thread per (trajectory, coordinate row) (Thomas recurrences)
+//                 TP = one thread per (trajectory, point) (pointwise evaluation, coalesced)
+#pragma once
+#include "ba_dev.cuh"
+
+// ----------------------------------------------------------------------------- spline primitives
+// Thomas elimination factors depend only on the row index, so they are tabulated once on the
+// host with the very divisions spline.cpp performs:  natural (spline.cpp:259-268):
+// cN[1]=1/4, cN[i]=1/(4-cN[i-1]);  clamped (spline.cpp:229-237): cC[0]=1/2, cC[i]=1/(4-cC[i-1]).
+struct ThomasTabs {
+  const double *cN;
+  const double *cC;
+};
+
+// spline.cpp:168-211 + 252-276: y[n] -> second-derivative solution m[n] ("natural", quirk Q4)
+__host__ __device__ inline void thomas_natural(const double *y, double *m, int npts, const double *cN) {
+  const int n = npts - 1;
+  m[0] = 0.0;
+  m[npts - 1] = 0.0;
+  for (int i = 1; i < npts - 1; ++i) m[i] = 6 * (y[i - 1] - 2 * y[i] + y[i + 1]);
+  const double a = 1.0, b = 4.0;
+  m[1] /= b;
+  for (int i = 2; i < n; ++i) m[i] = (m[i] - a * m[i - 1]) / (b - a * cN[i - 1]);
+  m[n] = (m[n] - a * m[n - 1]) / (b - a * cN[n - 1]);
+  for (int i = n; i > 1; --i) m[i - 1] -= cN[i - 1] * m[i];
+}
+
+// spline.cpp:225-243 ("clamped": b0=b_{n-1}=2, back-substitution starts at n-3, quirk Q4)
+__host__ __device__ inline void thomas_clamped(const double *y, double *m, int n, const double *cC) {
+  m[0] = 0.0;
+  m[n - 1] = 0.0;
+  for (int i = 1; i < n - 1; ++i) m[i] = 6 * (y[i - 1] - 2 * y[i] + y[i + 1]);
+  const double a = 1.0;
+  m[0] /= 2.0;
+  for (int i = 1; i < n; ++i) {
+    const double bi = (i == n - 1) ? 2.0 : 4.0;
+    m[i] = (m[i] - a * m[i - 1]) / (bi - a * cC[i - 1]);
+  }
+  for (int i = n - 2; i-- > 0;) m[i] -= cC[i] * m[i + 1];
+}
+
+// spline.cpp:203-209: coefficients of segment k from knot values and the solution
+struct Seg4 {
+  double c0, c1, c2, c3;
+};
+__host__ __device__ __forceinline__ Seg4 seg_coef(const double *y, const double *m, int k) {
+  Seg4 s;
+  s.c3 = (m[k + 1] - m[k]) / 6.0;
+  s.c2 = m[k] / 2.0;
+  s.c1 = y[k + 1] - y[k] - (m[k + 1] + 2 * m[k]) / 6.0;
+  s.c0 = y[k];
+  return s;
+}
+
+// spline.cpp:64-75 for one output site when the sites are non-decreasing: the monotone cursor
+// stops at the first segment with aOut < aIn[seg+1] (capped at nIn-2) == this binary search.
+template <class AIn>
+__host__ __device__ __forceinline__ int find_seg(const AIn &aIn, int nIn, double aOut) {
+  int lo = 0, hi = nIn - 2;  // answer in [lo, hi]
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (aOut < aIn(mid + 1))
+      hi = mid;
+    else
+      lo = mid + 1;
+  }
+  return lo;
+}
+
+struct UniformSites {  // a[k] = res * k   (util.h:101-107 applied to an iota, e.g. ba.cpp:803-805)
+  double res;
+  __host__ __device__ __forceinline__ double operator()(int k) const { return res * (double)k; }
+};
+struct ArraySites {
+  const double *a;
+  __host__ __device__ __forceinline__ double operator()(int k) const { return a[k]; }
+};
+
+#define TP_DECOMP(nblk)                                 \
+  const int b = (int)(blockIdx.x / (unsigned)(nblk));   \
+  const int i = (int)((blockIdx.x % (unsigned)(nblk)) * blockDim.x + threadIdx.x)
+
+// ----------------------------------------------------------------------------- load (TP)
+// trajReadBIN / trajReadCSV payload -> FP64 rows (ba.cpp:2283-2299, 2417-2437)
+template <typename T>
+__global__ void k_in_load(Ws w, const T *theta, const T *cart, const int *n0, const double *tres,
+                          int n0max, int nblk) {
+  TP_DECOMP(nblk);
+  if (b >= w.B) return;
+  const int n = n0 ? n0[b] : n0max;
+  if (i == 0) {
+    TrajState &s = w.st[b];
+    s.status = 0;
+    s.nPts = n;
+    s.tresInput = tres[b];
+    s.sres = tres[b];
+    s.scaleType = CFG.c.scale_type;
+    s.integRes = CFG.c.integ_res;
+    s.isParallelMech = CFG.c.is_parallel;
+    for (int q = 0; q < 3; ++q) s.sWeights[q] = CFG.c.s_weights[q];
+    for (int q = 0; q < MAXD; ++q) s.cartpt[q] = 0.0;
+    s.sLastSec = 0.0;
+    s.nRev = s.nFwd = s.nOver = s.nSm = s.nOut = 0;
+    s.tRev = s.tFwd = 0.0;
+  }
+  if (i >= n) return;
+  if (theta)
+    for (int j = 0; j < CFG.J; ++j)
+      rowp(w.P, w, b, j)[i] = (double)theta[((size_t)b * CFG.J + j) * n0max + i];
+  for (int j = 0; j < CFG.C; ++j) {
+    double v = 0.0;
+    if (cart && j < CFG.Cin) v = (double)cart[((size_t)b * CFG.Cin + j) * n0max + i];
+    rowp(w.P, w, b, CFG.J + j)[i] = v;
+  }
+}
+
+// ----------------------------------------------------------------------------- helpers (T)
+// ba.cpp:2768-2794 with nPtsOld <= 3 -> 4 points (interpTrajLinear) ; tiny, done in-thread.
+__host__ __device__ inline void traj_linear_to4(const Ws &w, double *base, int b, TrajState &s, int rows) {
+  const int nOld = s.nPts, nNew = 4;
+  UniformSites so{1.0 / (nOld - 1)}, sn{1.0 / (nNew - 1)};
+  int seg[4];
+  double tau[4];
+  for (int i = 0; i < nNew; ++i) {
+    const double a = sn(i);
+    seg[i] = find_seg(so, nOld, a);
+    tau[i] = (a - so(seg[i])) / (so(seg[i] + 1) - so(seg[i]));
+  }
+  for (int r = 0; r < rows; ++r) {
+    double *x = rowp(base, w, b, r);
+    double o[4];
+    for (int i = 0; i < nNew; ++i) o[i] = x[seg[i]] + (x[seg[i] + 1] - x[seg[i]]) * tau[i];
+    for (int i = 0; i < nNew; ++i) x[i] = o[i];
+  }
+  s.sres = s.sres * (nOld - 1) / (nNew - 1);
+  s.nPts = nNew;
+}
+
+// ----------------------------------------------------------------------------- prepare (T)
+// ba.cpp:98-183: timestamp de-duplication, length guards, remClosePts (util.cpp:452-524).
+// `ts` (optional) [B][n0max] timestamps of a CSV path; isRem scratch lives in w.nrm.
+__global__ void k_in_prepare(Ws w, const double *ts, int n0max, int hasTheta, int hasCart) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= w.B) return;
+  TrajState &s = w.st[b];
+  const int J = CFG.J, C = CFG.C, R = CFG.R;
+  int nPts = s.nPts;
+  if (ts) {  // ba.cpp:98-127 — the index list is a vector<uint8_t>, so indices wrap at 256
+    const double *t = ts + (size_t)b * n0max;
+    double *tt = w.sC + (size_t)b * w.Nc;  // working copy of the timestamps
+    for (int i = 0; i < nPts; ++i) tt[i] = t[i];
+    double *rem = w.nrm + (size_t)b * 2 * w.Nc;  // index list (values wrap like the uint8_t vector)
+    int nRem = 0;
+    for (int i = 1; i < nPts; ++i)
+      if (tt[i] == tt[i - 1]) rem[nRem++] = (double)(unsigned char)i;
+    int n = nPts;
+    for (int r = nRem - 1; r >= 0; --r) {
+      const int k = (int)rem[r];
+      for (int i = k; i < n - 1; ++i) tt[i] = tt[i + 1];
+      for (int row = 0; row < R; ++row) {
+        double *x = rowp(w.P, w, b, row);
+        for (int i = k; i < n - 1; ++i) x[i] = x[i + 1];
+      }
+      n--;
+    }
+    nPts = n;
+    s.nPts = nPts;
+    s.tresInput = tt[nPts - 1] / (nPts - 1);
+    s.sres = s.tresInput;
+  }
+  if (nPts == 1) {
+    s.status |= ST_TOO_SHORT;
+    return;
+  }
+  if (nPts < 4) {
+    traj_linear_to4(w, w.P, b, s, R);
+    nPts = s.nPts;
+  }
+  s.sLastSec = -1;
+  // remClosePts(x = driving rows, y = the others, thresh)
+  const bool cartDriven = (CFG.c.path_type == BATOTP_CART);
+  const int x0 = cartDriven ? J : 0, nx = cartDriven ? (hasCart ? CFG.Cin : 0) : (hasTheta ? J : 0);
+  const double thr = cartDriven ? CFG.c.cart_thresh : CFG.c.jnt_thresh;
+  const double thrSQ = thr * thr;
+  double *isRem = w.nrm + (size_t)b * 2 * w.Nc;
+  for (int i = 0; i < nPts; ++i) isRem[i] = 0.0;
+  for (;;) {
+    bool any = false;
+    for (int i = 1; i < nPts; ++i) {
+      double sum = 0;
+      for (int j = 0; j < nx; ++j) {
+        const double *x = rowp(w.P, w, b, x0 + j);
+        const double d = x[i] - x[i - 1];
+        sum += d * d;
+      }
+      if (sum < thrSQ && !(isRem[i - 1] != 0.0)) {
+        isRem[i] = 1.0;
+        any = true;
+      }
+    }
+    if (isRem[nPts - 1] != 0.0 && nPts > 2) {
+      isRem[nPts - 1] = 0.0;
+      isRem[nPts - 2] = 1.0;
+      isRem[nPts - 3] = 0.0;
+    }
+    if (!any) break;
+    int cur = 0;
+    for (int i = 0; i < nPts; ++i) {
+      if (!(isRem[i] != 0.0)) {
+        for (int row = 0; row < R; ++row) {
+          double *x = rowp(w.P, w, b, row);
+          x[cur] = x[i];
+        }
+        cur++;
+      }
+    }
+    nPts = cur;
+    for (int i = 0; i < nPts; ++i) isRem[i] = 0.0;
+  }
+  s.nPts = nPts;
+  if (nPts == 1) {
+    s.status |= ST_TOO_SHORT;
+    return;
+  }
+  if (nPts < 4) traj_linear_to4(w, w.P, b, s, R);
+  (void)C;
+}
+
+// ----------------------------------------------------------------------------- smooth/decimate (TR)
+// util.cpp:254-288 (smooth), 343-352 (decimate) as used by ba.cpp:195-242 (quirk Q6: the
+// smoothWindow branch smooths with inputDecimFact as the window).  tmp row = Q.
+__host__ __device__ inline void smooth_row(double *x, double *x2, int n, int w) {
+  w = imin_(w, n);
+  const int wMid = w / 2 + w % 2 - 1;
+  w = 2 * wMid + 1;
+  x2[0] = x[0];
+  x2[n - 1] = x[n - 1];
+  for (int i = 1; i < wMid; ++i) {
+    double xt = 0, xte = 0;
+    const int nT = 2 * i + 1;
+    for (int j = 0; j < nT; ++j) {
+      xt += x[j];
+      xte += x[n - j - 1];
+    }
+    x2[i] = xt / nT;
+    x2[n - i - 1] = xte / nT;
+  }
+  for (int i = wMid; i < n - wMid; ++i) {
+    double xt = 0;
+    for (int j = i - wMid; j < i + wMid + 1; ++j) xt += x[j];
+    x2[i] = xt / w;
+  }
+  for (int i = 0; i < n; ++i) x[i] = x2[i];
+}
+
+__global__ void k_in_smooth_decimate(Ws w) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = t / CFG.R, row = t % CFG.R;
+  if (b >= w.B) return;
+  TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  const int pt = CFG.c.path_type;
+  const bool isJ = row < CFG.J;
+  const bool active = isJ ? (pt == BATOTP_JOINT || pt == BATOTP_BOTH) : (pt == BATOTP_CART || pt == BATOTP_BOTH);
+  if (!active) return;
+  double *x = rowp(w.P, w, b, row), *tmp = rowp(w.Q, w, b, row);
+  int n = s.nPts;
+  const int df = CFG.c.input_decim_fact;
+  if (df > 1) {
+    smooth_row(x, tmp, n, df);
+    const int nOut = (n - 1) / df + 1;
+    for (int i = 0; i < nOut; ++i) x[i] = x[df * i];
+    if (df * (nOut - 1) + 1 != n) x[nOut - 1] = x[n - 1];
+    n = nOut;
+  }
+  if (CFG.c.smooth_window > 1) smooth_row(x, tmp, n, df);
+}
+// after k_in_smooth_decimate: nPts, tresInput, sres bookkeeping (ba.cpp:207-223) (T)
+__global__ void k_in_decim_fix(Ws w) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= w.B) return;
+  TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  const int df = CFG.c.input_decim_fact;
+  if (df > 1) {
+    s.nPts = (s.nPts - 1) / df + 1;
+    s.tresInput *= df;
+    s.sres *= df;
+  }
+}
+
+// ----------------------------------------------------------------------------- Robot point functions (TP)
+// mode: 1 = fwdKin (theta rows -> cart rows), 2 = invKin (cart -> theta), 3 = zero cart rows,
+//       4 = zero theta rows.  Evaluated on `base` rows for i < st.nPts (or nOver for the output).
+// robot.cpp:105-176 (KUKA; 3x3 products accumulated left to right as in oracle/eigen_standin),
+// 185-202 (RR), 243-278 + 291-322 (CSPR inverse kinematics / attachment points).
+struct Pmat {
+  double p[3][3];
+};
+__host__ __device__ inline void fk_kuka_point(const double *th, double *xyz) {
+  const double D2R = 3.14159265358979323846 / 180.0;
+  double c[7], s[7];
+  for (int k = 0; k < 7; ++k) {
+    const double tk = D2R * th[k];
+#ifdef BATOTP_HOST_EMU
+    c[k] = cos(tk);
+    s[k] = sin(tk);
+#else
+    sincos(tk, &s[k], &c[k]);
+#endif
+  }
+  const double c1 = c[0], c2 = c[1], c3 = c[2], c4 = c[3], c5 = c[4], c6 = c[5], c7 = c[6];
+  const double s1 = s[0], s2 = s[1], s3 = s[2], s4 = s[3], s5 = s[4], s6 = s[5], s7 = s[6];
+  const double Q12[3][3] = {{c1 * c2, -s1, -c1 * s2}, {c2 * s1, c1, -s1 * s2}, {s2, 0, c2}};
+  const double Q34[3][3] = {{c3 * c4, -s3, c3 * s4}, {c4 * s3, c3, s3 * s4}, {-s4, 0, c4}};
+  const double Q567[3][3] = {{c5 * c6 * c7 - s5 * s7, -c7 * s5 - c5 * c6 * s7, -c5 * s6},
+                             {c5 * s7 + c6 * c7 * s5, c5 * c7 - c6 * s5 * s7, -s5 * s6},
+                             {c7 * s6, -s6 * s7, c6}};
+  double Q1234[3][3], Q[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      Q1234[i][j] = Q12[i][0] * Q34[0][j] + Q12[i][1] * Q34[1][j] + Q12[i][2] * Q34[2][j];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      Q[i][j] = Q1234[i][0] * Q567[0][j] + Q1234[i][1] * Q567[1][j] + Q1234[i][2] * Q567[2][j];
+  const double tool[3] = {0, -.08, .545};
+  const double a0 = .3105, a1 = .4, a2 = .39;
+  const double x1 = a1 * Q12[0][2], y1 = a1 * Q12[1][2], z1 = a1 * Q12[2][2] + a0;
+  const double x2 = x1 + a2 * Q1234[0][2], y2 = y1 + a2 * Q1234[1][2], z2 = z1 + a2 * Q1234[2][2];
+  xyz[0] = x2 + (Q[0][0] * tool[0] + Q[0][1] * tool[1] + Q[0][2] * tool[2]);
+  xyz[1] = y2 + (Q[1][0] * tool[0] + Q[1][1] * tool[1] + Q[1][2] * tool[2]);
+  xyz[2] = z2 + (Q[2][0] * tool[0] + Q[2][1] * tool[1] + Q[2][2] * tool[2]);
+}
+__host__ __device__ inline void fk_rr_point(const double *th, double *xy) {
+  const double D2R = 3.14159265358979323846 / 180.0;
+  const double a1 = .4, a2 = .6;
+  const double th1 = D2R * th[0], th2 = D2R * th[1];
+  xy[0] = a1 * cos(th1) + a2 * cos(th1 + th2);
+  xy[1] = a1 * sin(th1) + a2 * sin(th1 + th2);
+}
+__host__ __device__ inline void ik_cspr_point(const Pmat &pm, const double *xyz, double *rho) {
+  for (int k = 0; k < 3; ++k) {
+    const double rv[3] = {xyz[0] - pm.p[0][k], xyz[1] - pm.p[1][k], xyz[2] - pm.p[2][k]};
+    double sumSQ = 0.0;
+    for (int q = 0; q < 3; ++q) sumSQ += rv[q] * rv[q];
+    rho[k] = sqrt(sumSQ);
+  }
+}
+
+__global__ void k_pointfn(Ws w, double *base, int stride, int mode, int useOver, Pmat pm, int nblk) {
+  TP_DECOMP(nblk);
+  if (b >= w.B) return;
+  const TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  const int n = useOver ? s.nOver : s.nPts;
+  if (i >= n) return;
+  const int J = CFG.J, C = CFG.C;
+  double *r0 = base + (size_t)b * CFG.R * stride;
+  if (mode == 1) {
+    double th[MAXD], xyz[3];
+    for (int j = 0; j < J; ++j) th[j] = r0[(size_t)j * stride + i];
+    if (CFG.c.robot_type == BATOTP_KUKA) {
+      fk_kuka_point(th, xyz);
+      for (int q = 0; q < 3; ++q) r0[(size_t)(J + q) * stride + i] = xyz[q];
+    } else if (CFG.c.robot_type == BATOTP_RR) {
+      fk_rr_point(th, xyz);
+      r0[(size_t)(J + 0) * stride + i] = xyz[0];
+      r0[(size_t)(J + 1) * stride + i] = xyz[1];
+    }
+  } else if (mode == 2) {
+    double xyz[3], rho[3];
+    for (int q = 0; q < 3; ++q) xyz[q] = r0[(size_t)(J + q) * stride + i];
+    ik_cspr_point(pm, xyz, rho);
+    for (int q = 0; q < 3; ++q) r0[(size_t)q * stride + i] = rho[q];
+  } else if (mode == 3) {
+    for (int q = 0; q < C; ++q) r0[(size_t)(J + q) * stride + i] = 0.0;
+  } else if (mode == 4) {
+    for (int q = 0; q < J; ++q) r0[(size_t)q * stride + i] = 0.0;
+  }
+}
+
+// ba.cpp:327-368 aa2qVect (sequential sign continuity) (T);  util.cpp:534-554 aa2q
+__host__ __device__ inline void aa2q_dev(const double aa[3], double q[4]) {
+  const double theta = sqrt(aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2]);
+  if (theta < 1e-6) {
+    q[0] = 1.0;
+    q[1] = q[2] = q[3] = 0.0;
+  } else {
+    const double sh = sin(0.5 * theta);
+    q[0] = cos(0.5 * theta);
+    for (int i = 0; i < 3; ++i) q[i + 1] = aa[i] * sh / theta;
+  }
+}
+__global__ void k_aa2q(Ws w) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= w.B) return;
+  TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  const int J = CFG.J;
+  double *r3 = rowp(w.P, w, b, J + 3), *r4 = rowp(w.P, w, b, J + 4), *r5 = rowp(w.P, w, b, J + 5),
+         *r6 = rowp(w.P, w, b, J + 6);
+  double aa[3] = {r3[0], r4[0], r5[0]}, q[4], qprev[4];
+  aa2q_dev(aa, qprev);
+  for (int i = 0; i < s.nPts; ++i) {
+    aa[0] = r3[i];
+    aa[1] = r4[i];
+    aa[2] = r5[i];
+    aa2q_dev(aa, q);
+    double qdir = 0;
+    for (int j = 0; j < 4; ++j) qdir += q[j] * qprev[j];
+    if (qdir < 0.0)
+      for (int j = 0; j < 4; ++j) q[j] = -q[j];
+    for (int j = 0; j < 4; ++j) qprev[j] = q[j];
+    r3[i] = q[0];
+    r4[i] = q[1];
+    r5[i] = q[2];
+    r6[i] = q[3];
+  }
+}
+
+// ----------------------------------------------------------------------------- adjust_s, first half (T)
+// ba.cpp:412-590: cumulative norms, optional automatic integration resolution, scale selection,
+// the weighted arc-length sites sC, and (regular pass) the resample plan of evalSplineFullTraj
+// (ba.cpp:794-819).  ptsOrig is an iota at both call sites (ba.cpp:283, 778) so ptsOrig[i] == i.
+__global__ void k_adjust_s(Ws w, int special) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= w.B) return;
+  TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  if (s.sWeights[1] + s.sWeights[2] < 1e-8) return;  // handled on the host: stage skipped
+  const int J = CFG.J;
+  double cartNormRes = special ? CFG.c.cart_norm_res : CFG.c.cart_norm_res2;
+  const double thetaNormRes = special ? CFG.c.theta_norm_res : CFG.c.theta_norm_res2;
+  const int nPts = s.nPts;
+  double *thetaNorm = w.nrm + (size_t)b * 2 * w.Nc, *cartPosNorm = thetaNorm + w.Nc;
+  double *sC = w.sC + (size_t)b * w.Nc;
+  const double sResi = s.sres;
+  double MinRatio = 1.0 / CFG.quadThresh;
+  double thetaWindow = 5;
+  double thetaNormLast = 0, cartPosNormLast = 0;
+  const double DEG2RAD = 3.14159265358979323846 / 180.0, RAD2DEG = 180.0 / 3.14159265358979323846;
+  if (!CFG.c.are_jnt_deg) thetaWindow *= DEG2RAD;
+  const double *cx = rowp(w.P, w, b, J), *cy = rowp(w.P, w, b, J + 1), *cz = rowp(w.P, w, b, J + 2);
+  thetaNorm[0] = 0.0;
+  cartPosNorm[0] = 0.0;
+  for (int i = 0; i < nPts - 1; ++i) {
+    double dthetaSQ = 0;
+    for (int j = 0; j < J; ++j) {
+      const double *x = rowp(w.P, w, b, j);
+      const double d = x[i + 1] - x[i];
+      dthetaSQ += d * d;
+    }
+    thetaNorm[i + 1] = thetaNorm[i] + sqrt(dthetaSQ);
+    double dcartSQ = 0;
+    double d = cx[i + 1] - cx[i];
+    dcartSQ += d * d;
+    d = cy[i + 1] - cy[i];
+    dcartSQ += d * d;
+    d = cz[i + 1] - cz[i];
+    dcartSQ += d * d;
+    cartPosNorm[i + 1] = cartPosNorm[i] + sqrt(dcartSQ);
+    if (CFG.c.is_auto_integ_res) {
+      const double thetaChange = thetaNorm[i + 1] - thetaNormLast;
+      const double cartChange = cartPosNorm[i + 1] - cartPosNormLast;
+      if (thetaChange > thetaWindow) {
+        MinRatio = dmin_(MinRatio, 3.0 * cartChange / thetaChange);
+        thetaNormLast = thetaNorm[i + 1];
+        cartPosNormLast = cartPosNorm[i + 1];
+      }
+    }
+  }
+  if (thetaNorm[nPts - 1] < thetaNormRes) {
+    s.status |= ST_IDENTICAL;
+    return;
+  }
+  double sLast = 0, sResNew = 0;
+  if (CFG.c.is_auto_integ_res) {  // ba.cpp:493-556
+    if ((cartPosNorm[nPts - 1] < cartNormRes) && s.scaleType == 2) {
+      s.sWeights[1] = s.sWeights[1] + s.sWeights[2];
+      s.sWeights[2] = 0;
+      s.scaleType = 1;
+    }
+    const double sW12in = s.sWeights[1] + s.sWeights[2];
+    double cartRat = 500.0 * cartPosNorm[nPts - 1];
+    double thetaRat = thetaNorm[nPts - 1];
+    if (!CFG.c.are_jnt_deg) thetaRat *= RAD2DEG;
+    const double minIntegRes = 0.004, maxIntegRes = 0.2, K = 0.0003;
+    double newIntegRes = K * CFG.c.cart_acc_max / CFG.c.cart_vel_max;
+    for (int i = 0; i < J; ++i) newIntegRes = dmax_(newIntegRes, K * CFG.c.jnt_acc_max[i] / CFG.c.jnt_vel_max[i]);
+    newIntegRes = dmin_(newIntegRes, maxIntegRes);
+    const double changeRat = cartRat / thetaRat;
+    double jointIntegRes = maxIntegRes * changeRat * changeRat;
+    double jointWin = maxIntegRes * MinRatio * MinRatio;
+    jointWin = dmax_(jointWin, 0.016);
+    jointIntegRes = dmin_(jointIntegRes, jointWin);
+    if (jointIntegRes < newIntegRes) newIntegRes = jointIntegRes;
+    newIntegRes = dmax_(newIntegRes, minIntegRes);
+    s.integRes = newIntegRes;
+    const double sW12out = cartRat + thetaRat;
+    const double outScale = sW12in / sW12out;
+    cartRat *= outScale;
+    thetaRat *= outScale;
+    if (thetaRat > s.sWeights[1]) {
+      s.sWeights[1] = thetaRat;
+      s.sWeights[2] = cartRat;
+    }
+    if (s.sWeights[2] > 0) cartNormRes = dmin_(cartNormRes, cartNormRes * s.sWeights[2] / s.sWeights[1]);
+  }
+  const double ptsLast = (double)(nPts - 1);
+  switch (s.scaleType) {
+    case 0: sLast = sResi * ptsLast; sResNew = sResi; break;
+    case 1: sLast = thetaNorm[nPts - 1]; sResNew = thetaNormRes; break;
+    case 2: sLast = cartPosNorm[nPts - 1]; sResNew = cartNormRes; break;
+  }
+  double cartPosNormFact;
+  if (cartPosNorm[nPts - 1] >= cartNormRes)
+    cartPosNormFact = s.sWeights[2] * sLast / cartPosNorm[nPts - 1];
+  else
+    cartPosNormFact = 0;
+  const double tTeachFact = s.sWeights[0] * sLast / (sResi * ptsLast);
+  const double thetaNormFact = s.sWeights[1] * sLast / thetaNorm[nPts - 1];
+  s.sres = sLast / (nPts - 1);
+  for (int i = 0; i < nPts; ++i)
+    sC[i] = tTeachFact * sResi * (double)i + thetaNormFact * thetaNorm[i] + cartPosNormFact * cartPosNorm[i];
+  s.sLast = sLast;
+  s.sResNew = sResNew;
+  s.sResi = sResi;
+  s.tTeachFact = tTeachFact;
+  s.thetaNormFact = thetaNormFact;
+  s.cartPosNormFact = cartPosNormFact;
+  if (special) {
+    int nPts2 = (int)ceil(sLast / sResNew) + 1;  // ba.cpp:666-667, capacity estimate for the march
+    s.nNew = imax_(nPts2, 4);
+  } else {
+    for (int i = 1; i < nPts; ++i)
+      if (sC[i] - sC[i - 1] < 1e-12 * s.sres) {
+        s.status |= ST_SRES_SMALL;
+        return;
+      }
+    // evalSplineFullTraj(traj, traj.sres, sResNew) plan: ba.cpp:794-819
+    const double oldRes = s.sres;
+    int nNew = (int)ceil(oldRes / sResNew * (nPts - 1)) + 1;
+    nNew = imax_(nNew, 4);
+    const double newRes = oldRes * (nPts - 1) / (nNew - 1);
+    s.sScale = sC[nPts - 1] / (double)(nNew - 1);
+    s.nNew = nNew;
+    s.sresC = s.sres;
+    s.vFact = 1 / s.sresC;
+    s.aFact = s.vFact * s.vFact;
+    s.sres = newRes;
+    if (nNew > w.Nc) s.status |= ST_GRID_CAP;
+  }
+}
+
+// ----------------------------------------------------------------------------- Thomas (TR)
+// Spline::getSplineCoeffs on every coordinate row of `src` -> solution rows in `dst`.
+// n source: 0 = st.nPts, 1 = st.nOver, 2 = st.nSm
+__global__ void k_thomas_rows(Ws w, const double *src, double *dst, int stride, int rows, int rowsPerTraj,
+                              int nsel, int clamped, ThomasTabs tabs) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = t / rows, row = t % rows;
+  if (b >= w.B) return;
+  const TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  const int n = nsel == 0 ? s.nPts : (nsel == 1 ? s.nOver : s.nSm);
+  const double *y = src + ((size_t)b * rowsPerTraj + row) * stride;
+  double *m = dst + ((size_t)b * rowsPerTraj + row) * stride;
+  if (clamped)
+    thomas_clamped(y, m, n, tabs.cC);
+  else
+    thomas_natural(y, m, n, tabs.cN);
+}
+
+// ----------------------------------------------------------------------------- interpSpecial (T)
+// ba.cpp:651-781: constant-ds march along the weighted arc length.  Source rows P (+M), emits Q.
+// evalSplinePartials (ba.cpp:1341-1380) supplies the values; the Cartesian rows are refreshed
+// only when a Cartesian constraint is on, otherwise Traj::cartpt keeps its previous content.
+__global__ void k_march(Ws w) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= w.B) return;
+  TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  const int J = CFG.J, C = CFG.C, R = CFG.R;
+  const int nPts = s.nPts;
+  const double *sC = w.sC + (size_t)b * w.Nc;
+  const double *P = rowp(w.P, w, b, 0), *M = rowp(w.M, w, b, 0);
+  double *Q = rowp(w.Q, w, b, 0);
+  const int Nc = w.Nc;
+  for (int r = 0; r < R; ++r) Q[(size_t)r * Nc] = P[(size_t)r * Nc];
+  double sPrv = 0, prv_ds = 0;
+  int CurNewPt = 1, CurOldPt = 1;
+  int seg = 0;
+  bool isDone = false;
+  const int lastSeg = nPts - 2;
+  const bool cartEval = CFG.cartOn != 0;
+  double cartpt[MAXD];
+  for (int q = 0; q < MAXD; ++q) cartpt[q] = s.cartpt[q];
+  while (!isDone) {
+    double dthetaSQ = 0;
+    for (int j = 0; j < J; ++j) {
+      const double d = P[(size_t)j * Nc + CurOldPt] - Q[(size_t)j * Nc + CurNewPt - 1];
+      dthetaSQ += d * d;
+    }
+    double dcartSQ = 0;
+    for (int j = 0; j < 3; ++j) {
+      const double d = P[(size_t)(J + j) * Nc + CurOldPt] - Q[(size_t)(J + j) * Nc + CurNewPt - 1];
+      dcartSQ += d * d;
+    }
+    const double cur_ds = s.tTeachFact * s.sResi * (double)CurOldPt + s.thetaNormFact * sqrt(dthetaSQ) +
+                          s.cartPosNormFact * sqrt(dcartSQ);
+    if (cur_ds > s.sResNew) {
+      const double sNew = sPrv + s.sResNew - prv_ds;
+      prv_ds = 0;
+      sPrv = sNew;
+      const double sCur = sPrv;
+      if (sCur > sC[nPts - 1]) isDone = true;
+      if (!isDone) {
+        // updateCurSeg (ba.cpp:1617-1652) on the non-uniform sites
+        double sSeg;
+        int guard = 0;
+        for (;;) {
+          sSeg = sC[seg];
+          if (sCur >= sSeg && sCur <= sC[seg + 1]) break;
+          if (sCur > sSeg) {
+            if (seg >= lastSeg) {
+              seg = lastSeg;
+              break;
+            }
+            seg++;
+          }
+          if (sCur < sSeg) {
+            if (seg <= 0) {
+              seg = 0;
+              break;
+            }
+            seg--;
+          }
+          if (++guard > 4 * nPts + 16) {
+            s.status |= ST_NUMERIC;
+            return;
+          }
+        }
+        const double tau = (sCur - sSeg) / (sC[seg + 1] - sSeg);
+        const double tau2 = tau * tau, tau3 = tau2 * tau;
+        if (CurNewPt >= Nc - 1) {
+          s.status |= ST_GRID_CAP;
+          return;
+        }
+        for (int j = 0; j < J; ++j) {
+          const Seg4 c = seg_coef(P + (size_t)j * Nc, M + (size_t)j * Nc, seg);
+          Q[(size_t)j * Nc + CurNewPt] = c.c3 * tau3 + c.c2 * tau2 + c.c1 * tau + c.c0;
+        }
+        if (cartEval)
+          for (int j = 0; j < C; ++j) {
+            const Seg4 c = seg_coef(P + (size_t)(J + j) * Nc, M + (size_t)(J + j) * Nc, seg);
+            cartpt[j] = c.c3 * tau3 + c.c2 * tau2 + c.c1 * tau + c.c0;
+          }
+        for (int j = 0; j < C; ++j) Q[(size_t)(J + j) * Nc + CurNewPt] = cartpt[j];
+        CurOldPt = seg + 1;
+        CurNewPt++;
+      }
+    } else {
+      if (CurOldPt == nPts - 1) {
+        isDone = true;
+      } else {
+        prv_ds = cur_ds;
+        sPrv = sC[CurOldPt];
+        CurOldPt++;
+      }
+    }
+  }
+  for (int r = 0; r < R; ++r) Q[(size_t)r * Nc + CurNewPt] = P[(size_t)r * Nc + nPts - 1];
+  for (int q = 0; q < MAXD; ++q) s.cartpt[q] = cartpt[q];
+  s.nPts = CurNewPt + 1;
+  s.sres = s.sResNew;
+  if (s.nPts < 4) traj_linear_to4(w, w.Q, b, s, R);
+}
+
+// ----------------------------------------------------------------------------- resample (TP)
+// evalSplineFullTraj, regular pass (ba.cpp:835-859): sites sMVC[i] = sScale*i located in the
+// non-uniform sC by findInterpSegs, values by interp1spline.  Source P/M/sC -> Q.
+__global__ void k_resample(Ws w, int nblk) {
+  TP_DECOMP(nblk);
+  if (b >= w.B) return;
+  const TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  if (i >= s.nNew) return;
+  const double *sC = w.sC + (size_t)b * w.Nc;
+  const int nOld = s.nPts;
+  const double aOut = s.sScale * (double)i;
+  ArraySites in{sC};
+  const int seg = find_seg(in, nOld, aOut);
+  const double den = sC[seg + 1] - sC[seg];
+  const double tau = (aOut - sC[seg]) / den;
+  const double tau2 = tau * tau, tau3 = tau2 * tau;
+  for (int r = 0; r < CFG.R; ++r) {
+    const Seg4 c = seg_coef(rowp(w.P, w, b, r), rowp(w.M, w, b, r), seg);
+    rowp(w.Q, w, b, r)[i] = c.c3 * tau3 + c.c2 * tau2 + c.c1 * tau + c.c0;
+  }
+}
+// spline.cpp:78-87: a zero-length input segment aborts findInterpSegs (status only) (T)
+__global__ void k_resample_commit(Ws w) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= w.B) return;
+  TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  const double *sC = w.sC + (size_t)b * w.Nc;
+  for (int i = 0; i < s.nPts - 1; ++i)
+    if (sC[i + 1] - sC[i] < 1e-20) {
+      s.status |= ST_DIV0;
+      return;
+    }
+  s.nPts = s.nNew;
+}
+
+// ----------------------------------------------------------------------------- final grid (T + TP)
+// ba.cpp:297-300: sC.clear(); evalSplineFullTraj(traj, sres, sres) -> uniform sites sres*k.
+__global__ void k_final_plan(Ws w) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= w.B) return;
+  TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  const int nOld = s.nPts;
+  const double oldRes = s.sres, newResIn = s.sres;
+  int nNew = (int)ceil(oldRes / newResIn * (nOld - 1)) + 1;
+  nNew = imax_(nNew, 4);
+  const double newRes = oldRes * (nOld - 1) / (nNew - 1);
+  const double sBack = s.sres * (double)(nOld - 1);  // sC[nOld-1]
+  s.sScale = sBack / (double)(nNew - 1);
+  s.nPtsC = nOld;
+  s.nNew = nNew;
+  s.sresC = s.sres;
+  s.vFact = 1 / s.sresC;
+  s.aFact = s.vFact * s.vFact;
+  s.sres = newRes;
+  s.nPts = nNew;
+  if (nNew > w.Nc) s.status |= ST_GRID_CAP;
+}
+
+// Sweep table (TP over segments): per (segment k, row r) four doubles.
+//   kinematic rows (joints, then Cartesian xyz when a Cartesian constraint is on):
+//       {3*c3, 2*c2, c1, 6*c3}  — the products evalSplinePartials forms first (ba.cpp:1359-1360)
+//   dynamics rows a1..a4 (torque on): {c3, c2, c1, c0}  (ba.cpp:1387-1405)
+__global__ void k_build_table(Ws w, const double *A, const double *AM, int nblk) {
+  TP_DECOMP(nblk);
+  if (b >= w.B) return;
+  const TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  if (i >= s.nPtsC - 1) return;
+  const int J = CFG.J;
+  double *t = w.tab + ((size_t)b * w.Nc + i) * (size_t)w.RT * 4;
+  int rt = 0;
+  const int nKin = J + (CFG.cartOn ? 3 : 0);
+  for (int r = 0; r < nKin; ++r, ++rt) {
+    const Seg4 c = seg_coef(rowp(w.P, w, b, r), rowp(w.M, w, b, r), i);
+    t[rt * 4 + 0] = 3 * c.c3;
+    t[rt * 4 + 1] = 2 * c.c2;
+    t[rt * 4 + 2] = c.c1;
+    t[rt * 4 + 3] = 6 * c.c3;
+  }
+  if (CFG.trqOn) {
+    for (int a = 0; a < 4; ++a)
+      for (int j = 0; j < J; ++j, ++rt) {
+        const size_t off = (((size_t)b * 4 + a) * MAXD + j) * w.Nc;
+        const Seg4 c = seg_coef(A + off, AM + off, i);
+        t[rt * 4 + 0] = c.c3;
+        t[rt * 4 + 1] = c.c2;
+        t[rt * 4 + 2] = c.c1;
+        t[rt * 4 + 3] = c.c0;
+      }
+  }
+}
+
+// Values and s-derivatives on the final grid (ba.cpp:840-855), needed by the dynamic model
+// (findDynModel, ba.cpp:905-938).  Source P/M -> Q (values), D, D2.   (TP)
+__global__ void k_eval_grid(Ws w, double *D, double *D2, int nblk) {
+  TP_DECOMP(nblk);
+  if (b >= w.B) return;
+  const TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  if (i >= s.nNew) return;
+  UniformSites in{s.sresC};
+  const double aOut = s.sScale * (double)i;
+  const int seg = find_seg(in, s.nPtsC, aOut);
+  const double den = in(seg + 1) - in(seg);
+  const double tau = (aOut - in(seg)) / den;
+  const double tau2 = tau * tau, tau3 = tau2 * tau;
+  const double vfact = 1.0 / s.sresC;  // interp1spline's own 1/tfact with tfact = oldRes (spline.cpp:142-143)
+  const double afact = vfact * vfact;
+  for (int r = 0; r < CFG.R; ++r) {
+    const Seg4 c = seg_coef(rowp(w.P, w, b, r), rowp(w.M, w, b, r), seg);
+    rowp(w.Q, w, b, r)[i] = c.c3 * tau3 + c.c2 * tau2 + c.c1 * tau + c.c0;
+    rowp(D, w, b, r)[i] = (3 * c.c3 * tau2 + 2 * c.c2 * tau + c.c1) * vfact;
+    rowp(D2, w, b, r)[i] = (6 * c.c3 * tau + 2 * c.c2) * afact;
+  }
+}

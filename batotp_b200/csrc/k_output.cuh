@@ -1,0 +1,496 @@
+// k_output.cuh — device kernels for BA::interpOutputData (batotp/ba.cpp:1661-1931), the
+// dynamic model (findDynModel ba.cpp:873-949, Robot::dynRR robot.cpp:377-431, dynCSPR3DOF
+// 487-517, setA 534-558, solveLinSys util.cpp:413-442) and result packing
+// (trajWriteBIN ba.cpp:2617-2647, sdotWrite 2735-2749).
+#pragma once
+#include "k_input.cuh"
+
+// ----------------------------------------------------------------------------- small dense solve
+// util.cpp:413-442 with isSVD=0: x = A.lu().solve(b).  Eigen (un-vendored dependency, "3.3.4",
+// README.md:32-50) PartialPivLU restated: first-max partial pivoting, sub-column divided by the
+// pivot, rank-1 trailing update, column-oriented unit-lower then upper substitution.  Pinned by
+// the prebuilt bin/batest CSPR3DOF fingerprints through the oracle.
+__host__ __device__ inline void lu3_solve(const double A[3][3], const double b[3], double x[3]) {
+  double lu[3][3];
+  int perm[3] = {0, 1, 2};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) lu[i][j] = A[i][j];
+  for (int k = 0; k < 3; ++k) {
+    int p = k;
+    double best = fabs(lu[k][k]);
+    for (int i = k + 1; i < 3; ++i) {
+      const double v = fabs(lu[i][k]);
+      if (v > best) {
+        best = v;
+        p = i;
+      }
+    }
+    if (p != k) {
+      for (int j = 0; j < 3; ++j) {
+        const double t = lu[k][j];
+        lu[k][j] = lu[p][j];
+        lu[p][j] = t;
+      }
+      const int t = perm[k];
+      perm[k] = perm[p];
+      perm[p] = t;
+    }
+    if (best != 0.0) {
+      const double piv = lu[k][k];
+      for (int i = k + 1; i < 3; ++i) lu[i][k] /= piv;
+    }
+    for (int i = k + 1; i < 3; ++i)
+      for (int j = k + 1; j < 3; ++j) lu[i][j] -= lu[i][k] * lu[k][j];
+  }
+  for (int i = 0; i < 3; ++i) x[i] = b[perm[i]];
+  for (int i = 0; i < 3; ++i)
+    for (int r = i + 1; r < 3; ++r) x[r] -= x[i] * lu[r][i];
+  for (int i = 2; i >= 0; --i) {
+    x[i] /= lu[i][i];
+    for (int r = 0; r < i; ++r) x[r] -= x[i] * lu[r][i];
+  }
+}
+
+// robot.cpp:377-431 at one point (theta in degrees; thetaD/thetaD2 are s- or t-derivatives)
+__host__ __device__ inline void dyn_rr_point(const double th[2], const double thD[2], const double thD2[2],
+                                             double a1[2], double a2[2], double a3[2], double a4[2]) {
+  const double D2R = 3.14159265358979323846 / 180.0, g = 9.81;
+  const double A1 = .4, A2 = .6, m1 = 4, m2 = 8;
+  const double th1 = D2R * th[0], th2 = D2R * th[1];
+  const double dth1 = D2R * thD[0], dth2 = D2R * thD[1];
+  const double ddth1 = D2R * thD2[0], ddth2 = D2R * thD2[1];
+  const double c1 = cos(th1), c2 = cos(th2), c12 = cos(th1 + th2);
+  const double A11 = .25 * m1 * A1 * A1 + m2 * (A1 * A1 + .25 * A2 * A2 + A1 * A2 * c2);
+  const double A12 = .5 * m2 * (.5 * A2 * A2 + A1 * A2 * c2);
+  const double A22 = .25 * m2 * A2 * A2;
+  a1[0] = A11 * dth1 + A12 * dth2;
+  a1[1] = A12 * dth1 + A22 * dth2;
+  const double ccFact = m2 * A1 * A2 * sin(th2);
+  a2[0] = A11 * ddth1 + A12 * ddth2 - ccFact * dth2 * (dth1 + .5 * dth2);
+  a2[1] = A12 * ddth1 + A22 * ddth2 - .5 * ccFact * dth1 * dth1;
+  a3[0] = 10 * dth1;
+  a3[1] = 10 * dth2;
+  a4[0] = .5 * g * (m1 * A1 * c1 + m2 * (2.0 * A1 * c1 + A2 * c12));
+  a4[1] = .5 * g * m2 * A2 * c12;
+}
+
+// findDynModel on the grid (TP): values in Q, s-derivatives in GD/GD2 -> A rows (+Par2Ser)
+__global__ void k_dyn_grid(Ws w, Pmat pm, int nblk) {
+  TP_DECOMP(nblk);
+  if (b >= w.B) return;
+  TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  if (i >= s.nPts) return;
+  const int J = CFG.J;
+  const size_t aStride = (size_t)MAXD * w.Nc;
+  double *Ab = w.A + (size_t)b * 4 * aStride;
+  double a[4][MAXD];
+  for (int k = 0; k < 4; ++k)
+    for (int q = 0; q < MAXD; ++q) a[k][q] = 0.0;
+  if (CFG.c.is_parallel) {  // dynCSPR3DOF (robot.cpp:487-517)
+    for (int q = 0; q < 3; ++q) {
+      a[0][q] = -rowp(w.GD, w, b, J + q)[i];
+      a[1][q] = -rowp(w.GD2, w, b, J + q)[i];
+    }
+    a[3][2] = 9.81;
+    if (CFG.c.is_par2ser) {  // ba.cpp:916-938: a_k <- A^-1 a_k with A from setA
+      double Am[3][3], cart[3], th[3];
+      for (int q = 0; q < 3; ++q) {
+        cart[q] = rowp(w.Q, w, b, J + q)[i];
+        th[q] = rowp(w.Q, w, b, q)[i];
+      }
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) Am[r][c] = (cart[r] - pm.p[r][c]) / th[c];
+      for (int k = 0; k < 4; ++k) {
+        double x[3], bb[3] = {a[k][0], a[k][1], a[k][2]};
+        lu3_solve(Am, bb, x);
+        for (int q = 0; q < 3; ++q) a[k][q] = x[q];
+      }
+    }
+  } else {  // dynRR
+    double th[2], d1[2], d2[2];
+    for (int q = 0; q < 2; ++q) {
+      th[q] = rowp(w.Q, w, b, q)[i];
+      d1[q] = rowp(w.GD, w, b, q)[i];
+      d2[q] = rowp(w.GD2, w, b, q)[i];
+    }
+    dyn_rr_point(th, d1, d2, a[0], a[1], a[2], a[3]);
+  }
+  for (int k = 0; k < 4; ++k)
+    for (int q = 0; q < J; ++q) Ab[(size_t)k * aStride + (size_t)q * w.Nc + i] = a[k][q];
+}
+
+// ----------------------------------------------------------------------------- output plan (T)
+// ba.cpp:1664-1706: output resolution bookkeeping, oversampled size, natural spline of sMVC(t).
+__global__ void k_out_plan(Ws w, ThomasTabs tabs) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= w.B) return;
+  TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  const double outResT = CFG.c.out_res;
+  double outRes = outResT, outSmooth = CFG.c.out_smooth_fact;
+  int isReinterp = 0;
+  if (outRes < s.integRes) {
+    isReinterp = 1;
+    outRes = s.integRes;
+    outSmooth *= dmax_(outResT / outRes, 1.);
+  }
+  const double tLast = s.tStep * (double)(s.nFwd - 1);
+  int nOver = (int)(outSmooth * ceil(tLast / outRes + 1.));
+  nOver = imax_(nOver, 4);
+  s.isReinterp = isReinterp;
+  s.outResEff = outRes;
+  s.outSmooth = outSmooth;
+  s.outResT = outResT;
+  s.nOver = nOver;
+  if (nOver > w.Oc) {
+    s.status |= ST_STEP_CAP;
+    return;
+  }
+  const double *sF = w.hist + (size_t)b * 4 * w.Sc + 2 * (size_t)w.Sc;
+  thomas_natural(sF, w.mS + (size_t)b * w.Sc, s.nFwd, tabs.cN);
+}
+
+// tMVCout[i] (ba.cpp:1693-1699) -> s at that time (TP)
+__host__ __device__ __forceinline__ double tmvc_out(int i, int n, double tLast) {
+  const double last = (double)(n - 3);
+  double v;
+  if (i == 0)
+    v = 0;
+  else if (i == 1)
+    v = 1.0 / 3.0;
+  else if (i == n - 1)
+    v = last;
+  else if (i == n - 2)
+    v = last - 1.0 / 3.0;
+  else
+    v = (double)(i - 1);
+  if (n == 4 && i == 2) v = last - 1.0 / 3.0;
+  return (tLast / last) * v;
+}
+
+__global__ void k_out_s(Ws w, int nblk) {
+  TP_DECOMP(nblk);
+  if (b >= w.B) return;
+  const TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  if (i >= s.nOver) return;
+  const double tLast = s.tStep * (double)(s.nFwd - 1);
+  const double t = tmvc_out(i, s.nOver, tLast);
+  UniformSites in{s.tStep};
+  const int seg = find_seg(in, s.nFwd, t);
+  const double tau = (t - in(seg)) / (in(seg + 1) - in(seg));
+  const double *sF = w.hist + (size_t)b * 4 * w.Sc + 2 * (size_t)w.Sc;
+  const Seg4 c = seg_coef(sF, w.mS + (size_t)b * w.Sc, seg);
+  const double tau2 = tau * tau, tau3 = tau2 * tau;
+  w.sOut[(size_t)b * w.Oc + i] = c.c3 * tau3 + c.c2 * tau2 + c.c1 * tau + c.c0;
+}
+
+// findInterpSegs(traj.sC, sMVCout) (ba.cpp:1708, spline.cpp:56-99): the interpolated s(t) need not
+// be monotone, so the reference's forward-only cursor is kept as a sequential walk (T).
+__global__ void k_out_segs(Ws w) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= w.B) return;
+  const TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  const double *sOut = w.sOut + (size_t)b * w.Oc;
+  int *seg = w.segO + (size_t)b * w.Oc;
+  double *tau = w.tauO + (size_t)b * w.Oc;
+  const int nIn = s.nPtsC;
+  const double res = s.sresC;
+  int cur = 0;
+  for (int i = 0; i < s.nOver; ++i) {
+    const double a = sOut[i];
+    for (;;) {
+      if (a < res * (double)(cur + 1) || cur == nIn - 2) break;
+      cur++;
+    }
+    seg[i] = cur;
+    const double lo = res * (double)cur;
+    tau[i] = (a - lo) / (res * (double)(cur + 1) - lo);
+  }
+}
+
+// theta(t) / cart(t) at the oversampled sites (ba.cpp:1713-1742) (TP).  Rows that are not
+// path-driven are filled by the kinematics kernel afterwards (or are the generic robot's zeros).
+__global__ void k_out_eval(Ws w, int nblk) {
+  TP_DECOMP(nblk);
+  if (b >= w.B) return;
+  const TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  if (i >= s.nOver) return;
+  const int seg = w.segO[(size_t)b * w.Oc + i];
+  const double tau = w.tauO[(size_t)b * w.Oc + i];
+  const double tau2 = tau * tau, tau3 = tau2 * tau;
+  const int pt = CFG.c.path_type, J = CFG.J;
+  for (int r = 0; r < CFG.R; ++r) {
+    const bool isJ = r < J;
+    const bool driven = isJ ? (pt == BATOTP_JOINT || pt == BATOTP_BOTH) : (pt == BATOTP_CART || pt == BATOTP_BOTH);
+    double v = 0.0;
+    if (driven) {
+      const Seg4 c = seg_coef(rowp(w.P, w, b, r), rowp(w.M, w, b, r), seg);
+      v = c.c3 * tau3 + c.c2 * tau2 + c.c1 * tau + c.c0;
+    }  // non-driven rows: filled by the kinematics kernel; the generic robot's Cartesian rows are zeros
+    orow(w.O5, w, b, r)[i] = v;
+  }
+}
+
+// Torque branch, part 1 (ba.cpp:1746-1765 / 1807-1812): values and time derivatives of the
+// re-splined rows at their own knots (seg=i-1, tau=1; i=0: seg=0, tau=0).  O5/OM -> OA, OD, OD2.  (TP)
+__global__ void k_out_knot_eval(Ws w, int nblk) {
+  TP_DECOMP(nblk);
+  if (b >= w.B) return;
+  const TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  if (i >= s.nOver) return;
+  const int J = CFG.J;
+  const int seg = (i == 0) ? 0 : i - 1;
+  const double tau = (i == 0) ? 0.0 : 1.0;
+  const double tau2 = tau * tau, tau3 = tau2 * tau;
+  const double tfact = s.outResEff / s.outSmooth;
+  const double vfact = 1.0 / tfact, afact = vfact * vfact;
+  for (int r = 0; r < CFG.R; ++r) {
+    const bool resplined = (r < J) || CFG.c.is_parallel;
+    if (resplined) {
+      const Seg4 c = seg_coef(orow(w.O5, w, b, r), orow(w.OM, w, b, r), seg);
+      orow(w.OA, w, b, r)[i] = c.c3 * tau3 + c.c2 * tau2 + c.c1 * tau + c.c0;
+      orow(w.OD, w, b, r)[i] = (3 * c.c3 * tau2 + 2 * c.c2 * tau + c.c1) * vfact;
+      orow(w.OD2, w, b, r)[i] = (6 * c.c3 * tau + 2 * c.c2) * afact;
+    } else {
+      orow(w.OA, w, b, r)[i] = orow(w.O5, w, b, r)[i];
+    }
+  }
+}
+
+// Torque branch, part 2 (ba.cpp:1770-1803 / 1815-1825): generalized forces at the output sites (TP)
+__global__ void k_out_trq(Ws w, Pmat pm, int nblk) {
+  TP_DECOMP(nblk);
+  if (b >= w.B) return;
+  const TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  if (i >= s.nOver) return;
+  const int J = CFG.J;
+  double *trq = w.Trq + (size_t)b * MAXD * w.Oc;
+  if (CFG.c.is_parallel) {
+    double a2[3], a3[3] = {0, 0, 0}, a4[3] = {0, 0, 9.81}, cart[3], th[3], bStar[3], x[3], Am[3][3];
+    for (int q = 0; q < 3; ++q) {
+      a2[q] = -orow(w.OD2, w, b, J + q)[i];
+      cart[q] = orow(w.OA, w, b, J + q)[i];
+      th[q] = orow(w.OA, w, b, q)[i];
+    }
+    for (int q = 0; q < 3; ++q) bStar[q] = a2[q] + a3[q] + a4[q];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) Am[r][c] = (cart[r] - pm.p[r][c]) / th[c];
+    lu3_solve(Am, bStar, x);
+    for (int q = 0; q < J; ++q) trq[(size_t)q * w.Oc + i] = x[q];
+  } else {
+    double th[2], d1[2], d2[2], a1[2], a2[2], a3[2], a4[2];
+    for (int q = 0; q < 2; ++q) {
+      th[q] = orow(w.OA, w, b, q)[i];
+      d1[q] = orow(w.OD, w, b, q)[i];
+      d2[q] = orow(w.OD2, w, b, q)[i];
+    }
+    dyn_rr_point(th, d1, d2, a1, a2, a3, a4);
+    for (int q = 0; q < 2; ++q) trq[(size_t)q * w.Oc + i] = a2[q] + a3[q] + a4[q];
+  }
+}
+
+// ----------------------------------------------------------------------------- smoothing (TP)
+// util.cpp:254-288 evaluated pointwise: x2[p] for a row of length n, window w (valid for n >= 2*wMid).
+__host__ __device__ __forceinline__ double smooth_at(const double *x, int n, int wIn, int p) {
+  int w = imin_(wIn, n);
+  const int wMid = w / 2 + w % 2 - 1;
+  w = 2 * wMid + 1;
+  if (p >= wMid && p < n - wMid) {
+    double xt = 0;
+    for (int j = p - wMid; j < p + wMid + 1; ++j) xt += x[j];
+    return xt / w;
+  }
+  if (p == 0) return x[0];
+  if (p == n - 1) return x[n - 1];
+  if (p < wMid) {
+    double xt = 0;
+    const int nT = 2 * p + 1;
+    for (int j = 0; j < nT; ++j) xt += x[j];
+    return xt / nT;
+  }
+  const int q = n - 1 - p;
+  double xte = 0;
+  const int nT = 2 * q + 1;
+  for (int j = 0; j < nT; ++j) xte += x[n - j - 1];
+  return xte / nT;
+}
+
+// ba.cpp:1838-1871 plan (T): nSm
+__global__ void k_out_smooth_plan(Ws w) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= w.B) return;
+  TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  if (s.outSmooth > 1.5) {
+    const int nIn = s.nOver;
+    s.nSm = imax_((int)((nIn - 1) / s.outSmooth) + 1, 4);
+    int wv = imin_((int)s.outSmooth, nIn);
+    const int wMid = wv / 2 + wv % 2 - 1;
+    if (nIn < 2 * wMid + 1) s.status |= ST_UNSUPPORTED;  // degenerate window/length combination
+  } else
+    s.nSm = s.nOver;
+}
+
+// smooth + linear decimation of every row (src -> dst) and of the torque rows (TP over nSm).
+// Trajectories whose smoothing factor is <= 1.5 (ba.cpp:1838) are copied through unchanged.
+__global__ void k_out_smooth(Ws w, const double *src, int srcStride, double *dst, int dstStride, int nblk) {
+  TP_DECOMP(nblk);
+  if (b >= w.B) return;
+  const TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  if (i >= s.nSm) return;
+  const bool sm = s.outSmooth > 1.5;
+  const int nIn = s.nOver, nOut = s.nSm;
+  int seg = i;
+  double tau = 0;
+  if (sm) {
+    const double aOut = ((double)(nIn - 1) / (double)(nOut - 1)) * (double)i;
+    UniformSites in{1.0};
+    seg = find_seg(in, nIn, aOut);
+    tau = (aOut - (double)seg) / ((double)(seg + 1) - (double)seg);
+  }
+  const int wv = (int)s.outSmooth;
+  for (int r = 0; r < CFG.R; ++r) {
+    const double *x = src + ((size_t)b * CFG.R + r) * srcStride;
+    double v;
+    if (sm) {
+      const double v0 = smooth_at(x, nIn, wv, seg), v1 = smooth_at(x, nIn, wv, seg + 1);
+      v = v0 + (v1 - v0) * tau;
+    } else
+      v = x[i];
+    dst[((size_t)b * CFG.R + r) * dstStride + i] = v;
+  }
+  if (CFG.trqOn)
+    for (int r = 0; r < CFG.J; ++r) {
+      const double *x = w.Trq + ((size_t)b * MAXD + r) * w.Oc;
+      double v;
+      if (sm) {
+        const double v0 = smooth_at(x, nIn, wv, seg), v1 = smooth_at(x, nIn, wv, seg + 1);
+        v = v0 + (v1 - v0) * tau;
+      } else
+        v = x[i];
+      w.Trq2[((size_t)b * MAXD + r) * w.Oc + i] = v;
+    }
+}
+
+// ----------------------------------------------------------------------------- final (T + TP)
+// ba.cpp:1873-1921: final sizes
+__global__ void k_out_final_plan(Ws w) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= w.B) return;
+  TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  const double tLast = s.tStep * (double)(s.nFwd - 1);
+  if (s.isReinterp) {
+    s.nOut = imax_((int)(ceil(tLast / s.outResT)), 4);
+    s.sresOut = s.outResT;
+    s.nCartOut = CFG.c.robot_type == BATOTP_GENJNT ? s.nSm : s.nOut;
+  } else {
+    s.nOut = s.nSm;
+    s.sresOut = s.outResEff;
+    s.nCartOut = s.nSm;
+  }
+  if (s.nOut > w.OutC) s.status |= ST_STEP_CAP;
+}
+
+// util.cpp:563-580
+__host__ __device__ inline void q2aa_dev(const double q[4], double aa[3]) {
+  const double nrm = sqrt(q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (nrm < 1e-6) {
+    aa[0] = aa[1] = aa[2] = 0.0;
+  } else {
+    const double theta = 2.0 * atan2(nrm, q[0]) / nrm;
+    for (int i = 0; i < 3; ++i) aa[i] = theta * q[i + 1];
+  }
+}
+
+// Final resample (when outRes < integRes, ba.cpp:1880-1915) and float32 packing in trajWriteBIN
+// row order.  src rows hold nSm points, srcM their natural-spline solutions.   (TP over OutC)
+// Output rows are stored as FP64 too (outD) when requested, for the strict-parity trig path.
+__global__ void k_out_pack(Ws w, const double *src, const double *srcM, int sStride, const double *trqSrc,
+                           const double *trqM, float *thetaOut, float *cartOut, float *trqOut,
+                           double *cartOutD, int nblk) {
+  TP_DECOMP(nblk);
+  if (b >= w.B) return;
+  const TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  const int J = CFG.J, C = CFG.C, Cin = CFG.Cin;
+  const bool generic = CFG.c.robot_type == BATOTP_GENJNT;
+  int seg = 0;
+  double tau = 0, tau2 = 0, tau3 = 0;
+  const bool re = s.isReinterp != 0;
+  if (re && i < s.nOut) {
+    UniformSites s1{1. / (double)(s.nSm - 1)}, s2{1. / (double)(s.nOut - 1)};
+    const double a = s2(i);
+    seg = find_seg(s1, s.nSm, a);
+    tau = (a - s1(seg)) / (s1(seg + 1) - s1(seg));
+    tau2 = tau * tau;
+    tau3 = tau2 * tau;
+  }
+  if (i < s.nOut) {
+    for (int r = 0; r < J; ++r) {
+      double v;
+      if (re) {
+        const Seg4 c = seg_coef(src + ((size_t)b * CFG.R + r) * sStride, srcM + ((size_t)b * CFG.R + r) * sStride, seg);
+        v = c.c3 * tau3 + c.c2 * tau2 + c.c1 * tau + c.c0;
+      } else
+        v = src[((size_t)b * CFG.R + r) * sStride + i];
+      thetaOut[((size_t)b * J + r) * w.OutC + i] = (float)v;
+    }
+    if (trqOut && CFG.trqOn)
+      for (int r = 0; r < J; ++r) {
+        double v;
+        if (re) {
+          const Seg4 c = seg_coef(trqSrc + ((size_t)b * MAXD + r) * w.Oc, trqM + ((size_t)b * MAXD + r) * w.Oc, seg);
+          v = c.c3 * tau3 + c.c2 * tau2 + c.c1 * tau + c.c0;
+        } else
+          v = trqSrc[((size_t)b * MAXD + r) * w.Oc + i];
+        trqOut[((size_t)b * J + r) * w.OutC + i] = (float)v;
+      }
+  }
+  if (i < s.nCartOut && (cartOut || cartOutD)) {
+    double cv[MAXD];
+    for (int r = 0; r < C; ++r) {
+      if (re && !generic) {
+        const Seg4 c = seg_coef(src + ((size_t)b * CFG.R + J + r) * sStride, srcM + ((size_t)b * CFG.R + J + r) * sStride, seg);
+        cv[r] = c.c3 * tau3 + c.c2 * tau2 + c.c1 * tau + c.c0;
+      } else
+        cv[r] = src[((size_t)b * CFG.R + J + r) * sStride + i];
+    }
+    if (C == 7) {
+      if (cartOutD) {  // strict-parity path: the host applies q2aa with its own libm
+        for (int r = 0; r < 7; ++r) cartOutD[((size_t)b * 7 + r) * w.OutC + i] = cv[r];
+      } else {
+        double aa[3];
+        q2aa_dev(cv + 3, aa);
+        for (int r = 0; r < 3; ++r) cv[3 + r] = aa[r];
+      }
+    }
+    if (cartOut && !(C == 7 && cartOutD))
+      for (int r = 0; r < Cin; ++r) cartOut[((size_t)b * Cin + r) * w.OutC + i] = (float)cv[r];
+  }
+}
+
+// s-sdot histories in sdotWrite order (ascending s for the reverse sweep) as float32 (TP over Sc)
+__global__ void k_pack_hist(Ws w, float *histOut, int nblk) {
+  TP_DECOMP(nblk);
+  if (b >= w.B) return;
+  const TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  const double *hb = w.hist + (size_t)b * 4 * w.Sc;
+  float *o = histOut + (size_t)b * 4 * w.Sc;
+  if (i < s.nRev) {
+    o[i] = (float)hb[(w.Sc - s.nRev) + i];
+    o[(size_t)w.Sc + i] = (float)hb[(size_t)w.Sc + (w.Sc - s.nRev) + i];
+  }
+  if (i < s.nFwd) {
+    o[2 * (size_t)w.Sc + i] = (float)hb[2 * (size_t)w.Sc + i];
+    o[3 * (size_t)w.Sc + i] = (float)hb[3 * (size_t)w.Sc + i];
+  }
+}

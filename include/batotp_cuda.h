@@ -1,0 +1,123 @@
+/* batotp_cuda.h — the extern "C" boundary of the B200-native Bisection Algorithm path.
+ *
+ * This layer does not exist in the reference; it is what a host-language
+ * binding of batotp's time-optimisation step binds to.  Every entry point replaces a
+ * BATOTP::BA member (reference file:line cited on each); buffers are plain pointers
+ * and sizes, caller-owned (pin them for full copy bandwidth), the return convention is
+ * the reference's: 0 = ok, -1 = error (+ message via batotp_cuda_last_error).
+ *
+ * There is no CPU fallback: every call fails with -1 when no CUDA device is usable.
+ */
+#ifndef BATOTP_CUDA_H
+#define BATOTP_CUDA_H
+
+#include "batotp_cfg.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct batotp_ctx *batotp_handle;
+
+/* per-trajectory status word (bit set); 0 = optimised.  Mirrors BA's -1 returns and
+ * BA::ErrorOptimization (ba.h:176) without aborting the batch. */
+#define BATOTP_ST_TOO_SHORT 1        /* ba.cpp:129-133,175-179 */
+#define BATOTP_ST_IDENTICAL 2        /* ba.cpp:484-488 */
+#define BATOTP_ST_SRES_SMALL 4       /* ba.cpp:607-611 */
+#define BATOTP_ST_GRID_CAP 8         /* internal capacity; retried automatically */
+#define BATOTP_ST_MAX_INTEG_TIME 16  /* ba.cpp:1117-1122 = BA::MAX_INTEGRATION_TIME */
+#define BATOTP_ST_STEP_CAP 32        /* internal capacity; retried automatically */
+#define BATOTP_ST_NUMERIC 64         /* NaN in a segment search (the reference would not return) */
+#define BATOTP_ST_BISECT_FAIL 128    /* informational: ba.cpp:1307-1319 returned -1 somewhere (sweep ignores it) */
+#define BATOTP_ST_DIV0 256           /* spline.cpp:82-86 */
+#define BATOTP_ST_UNSUPPORTED 512    /* option outside the accelerated scope */
+#define BATOTP_ST_FATAL_MASK (1 | 2 | 4 | 8 | 16 | 32 | 64 | 256 | 512)
+
+/* ---- device enumeration / lifetime ---------------------------------------------------- */
+int batotp_cuda_device_count(void);
+/* one context per device and host thread; owns the chunk workspace in HBM */
+int batotp_cuda_create(int device, batotp_handle *out);
+int batotp_cuda_destroy(batotp_handle h);
+const char *batotp_cuda_last_error(batotp_handle h);
+/* trajectories processed per device pass (workspace is sized for one chunk); default 16384 */
+int batotp_cuda_set_chunk(batotp_handle h, int chunk);
+/* number of kernels launched by this context since creation (for the benchmark's gpu_launches) */
+long batotp_cuda_launch_count(batotp_handle h);
+
+/* ---- batch input: what BA::loadTrajectoryData leaves in Traj (ba.cpp:2206-2461) -------- */
+typedef struct batotp_batch_in {
+  int B;                  /* trajectories */
+  int n0_max;             /* row pitch (points) of the payload arrays */
+  const int *n0;          /* [B] points per path, or NULL: all n0_max   (always a HOST pointer) */
+  const double *tres;     /* [B] tresInput per path, or NULL: tres_all  (always a HOST pointer) */
+  double tres_all;
+  /* BIN-file payload layout (ba.cpp:2283-2299): [B][coordinate][n0_max]; NULL = block absent.
+   * float32 as in the files, or float64 for CSV-sourced paths (exactly one family non-NULL) */
+  const float *theta_f32;
+  const float *cart_f32;
+  const double *theta_f64;
+  const double *cart_f64;
+  const double *timestamp; /* [B][n0_max] CSV timestamps or NULL (ba.cpp:98-127) */
+  int on_device;           /* 1: the payload pointers are device pointers already resident in HBM */
+} batotp_batch_in;
+
+/* ---- batch output: what BA::writeOutputData would serialise (ba.cpp:2510-2759) --------- */
+typedef struct batotp_batch_out {
+  int out_cap;   /* in: row pitch (points) of theta_out/cart_out/trq_out */
+  int hist_cap;  /* in: row pitch (points) of hist/flags */
+  /* per trajectory [B]; any pointer may be NULL */
+  int *status;
+  int *n_rev, *n_fwd;    /* points of the reverse / forward s-sdot curves (switching counts) */
+  int *n_out;            /* Traj::nPts after interpOutputData */
+  int *n_cart_out;       /* length of the Cartesian rows (trajWriteBIN's is_cartFull test) */
+  int *n_grid;           /* knots of the s-grid after interpInputData */
+  double *t_total;       /* Traj::tTotalTraj (forward sweep) */
+  double *t_rev;         /* reverse-sweep time */
+  double *s_last_sec;    /* Traj::sLastSec */
+  double *out_sres;      /* Traj::sres after interpOutputData */
+  /* float32 rows in trajWriteBIN order */
+  float *theta_out;      /* [B][nJoints][out_cap] */
+  float *cart_out;       /* [B][nCart][out_cap] */
+  float *trq_out;        /* [B][nJoints][out_cap] */
+  float *hist;           /* [B][4][hist_cap]: s_rev, sdot_rev (ascending s), s_fwd, sdot_fwd  (sdotWrite) */
+  unsigned char *flags;  /* [B][2][hist_cap]: per RK step, integration order:
+                            bits0-2 sub-steps limited by a velocity limit/MVC (ba.cpp:1093),
+                            bits3-5 sub-steps with an active bisection, bit6 isOn_sdot (ba.cpp:1211) */
+  int on_device;         /* 1: the pointers above are device pointers */
+} batotp_batch_out;
+
+/* BA::optimize (ba.cpp:2538-2573) over a batch: interpInputData -> sweep(-1) -> sweep(+1) ->
+ * interpOutputData for every path, chunked through the device. */
+int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_in *in,
+                               batotp_batch_out *out);
+
+/* ---- phase-wise calls, mirroring batest's sequence (test/main.cpp:55-86) ---------------- */
+/* They operate on one resident chunk (B <= chunk size) so that a BATOTP::BA facade can fill
+ * Traj between calls.  batotp_cuda_load replaces loadTrajectoryData's hand-over,
+ * _interp_input = BA::interpInputData (ba.cpp:95), _sweeps = BA::sweep x2 (ba.cpp:979; the
+ * reverse pass must precede the forward pass, so both run in one launch),
+ * _interp_output = BA::interpOutputData (ba.cpp:1661), _fetch = copy results out. */
+int batotp_cuda_load(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_in *in);
+int batotp_cuda_interp_input(batotp_handle h);
+int batotp_cuda_sweeps(batotp_handle h);
+int batotp_cuda_interp_output(batotp_handle h);
+int batotp_cuda_fetch(batotp_handle h, batotp_batch_out *out);
+
+/* Derived product: per-sample maximum-velocity curve on the s-grid, one
+ * thread per (path, sample): the sweep's own per-point functions evaluated at every knot.
+ * Call after batotp_cuda_interp_input.  sdot_out: [B][cap] host doubles. */
+int batotp_cuda_mvc_per_sample(batotp_handle h, double sdot_start, double *sdot_out, int cap);
+
+/* FP64 inspection of the resident chunk (tests, and Traj filling by the facade).
+ * name: "theta","cart" (grid/out rows), "thetaC_y","thetaC_m","cartC_y","cartC_m" (spline knots /
+ * second-derivative solution), "a1".."a4","a1C_m".."a4C_m", "s_rev","sdot_rev","s_fwd","sdot_fwd",
+ * "theta_out","cart_out","trq_out" (FP64 before the float cast).  Returns the length or -1. */
+int batotp_cuda_get_f64(batotp_handle h, const char *name, int traj, int row, double *buf, int cap);
+
+/* host-side helpers shared with the facade */
+int batotp_read_config(const char *path, batotp_cfg *cfg, char *traj_file_name, int name_cap); /* ba.cpp:1942-2087 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BATOTP_CUDA_H */
