@@ -21,9 +21,7 @@
 
 #ifndef BATOTP_HOST_EMU
 #include <cuda_runtime.h>
-__constant__ DevCfg g_cfg;
 #else
-DevCfg g_cfg;
 thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 #endif
 
@@ -161,6 +159,8 @@ struct batotp_ctx {
   // staged outputs
   float *d_thetaOut = nullptr, *d_cartOut = nullptr, *d_trqOut = nullptr, *d_histOut = nullptr;
   double *d_cartOutD = nullptr;
+  double *d_outD = nullptr;  // [B][R+J][OutC] FP64 final rows (keepF64)
+  bool keepF64 = false, capKeep = false;
   // which buffers hold the final rows after interp_output
   const double *finSrc = nullptr, *finM = nullptr, *finTrq = nullptr, *finTrqM = nullptr;
   // high-water marks so that steady-state chunks need no planning sync
@@ -168,6 +168,14 @@ struct batotp_ctx {
   std::vector<TrajState> hst;
   int phase = 0;  // 0 none, 1 loaded, 2 input done, 3 sweeps done, 4 output done
   bool lastHaveN0 = false;
+  // measurement (bench.py): device time of the sweep kernel and whole-context event timer
+  double sweepMs = 0;
+  long sweepLaunches = 0;
+  long long cntVerify = 0, cntSteps = 0, cntTraj = 0;
+#ifndef BATOTP_HOST_EMU
+  cudaEvent_t evS0 = nullptr, evS1 = nullptr, evT[2] = {nullptr, nullptr};
+  bool sweepPending = false;
+#endif
 };
 
 namespace {
@@ -265,7 +273,7 @@ void ensure_ws(batotp_ctx *h, int B, int Nc, int Sc) {
   if (!trq && smooth_uniform_on(h)) Os = (int)(Oc / c.c.out_smooth_fact) + 16;
   const int OutC = final_cap(h, Sc, Os);
   if (B <= h->capB && Nc <= h->capNc && Sc <= h->capSc && Oc <= h->capOc && Os <= h->capOs &&
-      OutC <= h->capOutC && c.R == h->capR && c.RT == h->capRT && trq == h->capTrq)
+      OutC <= h->capOutC && c.R == h->capR && c.RT == h->capRT && trq == h->capTrq && h->keepF64 == h->capKeep)
     return;
   free_ws(h);
   Ws &w = h->w;
@@ -313,6 +321,8 @@ void ensure_ws(batotp_ctx *h, int B, int Nc, int Sc) {
   h->d_trqOut = trq ? ws_alloc<float>(h, b * c.J * OutC) : nullptr;
   h->d_cartOutD = (c.C == 7) ? ws_alloc<double>(h, b * 7 * OutC) : nullptr;
   h->d_histOut = ws_alloc<float>(h, b * 4 * Sc);
+  h->d_outD = h->keepF64 ? ws_alloc<double>(h, b * (R + c.J) * OutC) : nullptr;
+  h->capKeep = h->keepF64;
   h->capB = B;
   h->capNc = Nc;
   h->capSc = Sc;
@@ -490,9 +500,21 @@ void launch_sweep(batotp_ctx *h) {
 #else
   int blocks = 1;
 #endif
+#ifndef BATOTP_HOST_EMU
+  if (!h->evS0) {
+    CU_CHECK(cudaEventCreate(&h->evS0));
+    CU_CHECK(cudaEventCreate(&h->evS1));
+  }
+  CU_CHECK(cudaEventRecord(h->evS0, h->stream));
+#endif
   BATOTP_LAUNCH((k_sweep<J, CART, TRQ>), dim3(blocks), dim3(128), h->stream, h->w);
   g_check_launch();
+#ifndef BATOTP_HOST_EMU
+  CU_CHECK(cudaEventRecord(h->evS1, h->stream));
+  h->sweepPending = true;
+#endif
   h->launches++;
+  h->sweepLaunches++;
 }
 
 int dispatch_sweep(batotp_ctx *h) {
@@ -695,12 +717,39 @@ void do_interp_output(batotp_ctx *h) {
   h->finTrqM = w.TrqM;
   const bool strictQuat = (c.C == 7 && c.c.trig_mode == 1);
   LAUNCH_TP(h, k_out_pack, w.OutC, w, cur, (const double *)w.OM, curStride, trqCur, (const double *)w.TrqM,
-            h->d_thetaOut, h->d_cartOut, h->d_trqOut, strictQuat ? h->d_cartOutD : (double *)nullptr);
+            h->d_thetaOut, h->d_cartOut, h->d_trqOut, strictQuat ? h->d_cartOutD : (double *)nullptr, h->d_outD);
   LAUNCH_TP(h, k_pack_hist, w.Sc, w, h->d_histOut);
   h->phase = 4;
 }
 
 }  // namespace
+
+// FP64 pipe peak of this device, measured (MEASURED_PEAKS.json has no FP64 entry): 16 independent
+// accumulator chains per thread, either fused multiply-adds (2 flop each) or alternating
+// multiply / add (1 flop each: the ceiling of a -fmad=false kernel).  Returns TFLOP/s.
+#ifndef BATOTP_HOST_EMU
+template <bool FMA>
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, double a, double b) {
+  double x[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) x[q] = 1.0 + 1e-9 * (threadIdx.x + q);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      if (FMA)
+        x[q] = __fma_rn(x[q], a, b);
+      else {
+        x[q] = __dmul_rn(x[q], a);
+        x[q] = __dadd_rn(x[q], b);
+      }
+    }
+  }
+  double sacc = 0;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) sacc += x[q];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = sacc;
+}
+#endif
 
 // ----------------------------------------------------------------------------- C ABI
 extern "C" {
@@ -768,6 +817,100 @@ int batotp_cuda_set_chunk(batotp_handle h, int chunk) {
 
 long batotp_cuda_launch_count(batotp_handle h) { return h ? h->launches : 0; }
 
+int batotp_cuda_fp64_peak(batotp_handle h, double *tflops_fma, double *tflops_nofma) {
+#ifndef BATOTP_HOST_EMU
+  if (!h) return -1;
+  try {
+    CU_CHECK(cudaSetDevice(h->device));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    double *d = (double *)g_alloc((size_t)blocks * threads * 8);
+    cudaEvent_t e0, e1;
+    CU_CHECK(cudaEventCreate(&e0));
+    CU_CHECK(cudaEventCreate(&e1));
+    double best[2] = {0, 0};
+    for (int mode = 0; mode < 2; ++mode)
+      for (int rep = 0; rep < 6; ++rep) {
+        CU_CHECK(cudaEventRecord(e0, h->stream));
+        if (mode == 0)
+          k_fp64_peak<true><<<blocks, threads, 0, h->stream>>>(d, iters, 1.0000001, 1e-9);
+        else
+          k_fp64_peak<false><<<blocks, threads, 0, h->stream>>>(d, iters, 1.0000001, 1e-9);
+        CU_CHECK(cudaEventRecord(e1, h->stream));
+        CU_CHECK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flop = (double)blocks * threads * iters * 16 * 2;  // both variants: 2 flop per chain step
+        const double tf = flop / (ms * 1e-3) * 1e-12;
+        if (rep > 0 && tf > best[mode]) best[mode] = tf;
+      }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    g_free(d);
+    if (tflops_fma) *tflops_fma = best[0];
+    if (tflops_nofma) *tflops_nofma = best[1];
+    return 0;
+  } catch (const Err &e) {
+    h->err = e.msg;
+    return -1;
+  }
+#else
+  if (tflops_fma) *tflops_fma = 0;
+  if (tflops_nofma) *tflops_nofma = 0;
+  return h ? 0 : -1;
+#endif
+}
+
+int batotp_cuda_set_keep_f64(batotp_handle h, int on) {
+  if (!h) return -1;
+  h->keepF64 = on != 0;
+  return 0;
+}
+
+int batotp_cuda_stats(batotp_handle h, double *out, int n) {
+  if (!h || !out) return -1;
+  const double v[6] = {h->sweepMs, (double)h->sweepLaunches, (double)h->cntVerify, (double)h->cntSteps,
+                       (double)h->cntTraj, (double)h->launches};
+  for (int i = 0; i < n && i < 6; ++i) out[i] = v[i];
+  return 0;
+}
+int batotp_cuda_stats_reset(batotp_handle h) {
+  if (!h) return -1;
+  h->sweepMs = 0;
+  h->sweepLaunches = 0;
+  h->cntVerify = h->cntSteps = h->cntTraj = 0;
+  h->launches = 0;
+  return 0;
+}
+int batotp_cuda_timer(batotp_handle h, int which, double *elapsed_ms) {
+#ifndef BATOTP_HOST_EMU
+  if (!h || which < 0 || which > 1) return -1;
+  try {
+    CU_CHECK(cudaSetDevice(h->device));
+    if (!h->evT[0]) {
+      CU_CHECK(cudaEventCreate(&h->evT[0]));
+      CU_CHECK(cudaEventCreate(&h->evT[1]));
+    }
+    CU_CHECK(cudaEventRecord(h->evT[which], h->stream));
+    if (which == 1) {
+      CU_CHECK(cudaEventSynchronize(h->evT[1]));
+      float ms = 0;
+      CU_CHECK(cudaEventElapsedTime(&ms, h->evT[0], h->evT[1]));
+      if (elapsed_ms) *elapsed_ms = ms;
+    }
+    return 0;
+  } catch (const Err &e) {
+    h->err = e.msg;
+    return -1;
+  }
+#else
+  (void)which;
+  if (elapsed_ms) *elapsed_ms = 0;
+  return h ? 0 : -1;
+#endif
+}
+
 static int load_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_in *in, int first, int B) {
 #ifndef BATOTP_HOST_EMU
   CU_CHECK(cudaSetDevice(h->device));
@@ -827,6 +970,14 @@ static int chunk_sweeps_output(batotp_handle h, bool haveN0) {
     h->hst.resize(h->B);
     g_d2h(h->hst.data(), h->w.st, (size_t)h->B * sizeof(TrajState), h->stream);
     g_sync(h->stream);
+#ifndef BATOTP_HOST_EMU
+    if (h->sweepPending) {
+      float ms = 0;
+      CU_CHECK(cudaEventElapsedTime(&ms, h->evS0, h->evS1));
+      h->sweepMs += ms;
+      h->sweepPending = false;
+    }
+#endif
     bool stepCap = false;
     int mxF = 0;
     for (int b = 0; b < h->B; ++b) {
@@ -834,6 +985,13 @@ static int chunk_sweeps_output(batotp_handle h, bool haveN0) {
       mxF = std::max(mxF, std::max(h->hst[b].nFwd, h->hst[b].nRev));
     }
     if (!stepCap) {
+      for (int b = 0; b < h->B; ++b) {
+        const TrajState &t = h->hst[b];
+        if (t.status & ST_FATAL_MASK) continue;
+        h->cntVerify += t.nVerify;
+        h->cntSteps += (t.nRev - 1) + (t.nFwd - 1);
+        h->cntTraj++;
+      }
       h->hwSc = std::max(h->hwSc, std::min(h->w.Sc, (int)(mxF * 1.25) + 64));
       return 0;
     }
@@ -1005,6 +1163,29 @@ int batotp_cuda_get_f64(batotp_handle h, const char *name, int traj, int row, do
     else if (h->phase >= 3 && n == "sdot_rev") { src = w.hist + (size_t)traj * 4 * w.Sc + w.Sc + (w.Sc - s.nRev); len = s.nRev; }
     else if (h->phase >= 3 && n == "s_fwd") { src = w.hist + (size_t)traj * 4 * w.Sc + 2 * (size_t)w.Sc; len = s.nFwd; }
     else if (h->phase >= 3 && n == "sdot_fwd") { src = w.hist + (size_t)traj * 4 * w.Sc + 3 * (size_t)w.Sc; len = s.nFwd; }
+    else if (h->phase >= 4 && h->d_outD && (n == "theta_out" || n == "cart_out" || n == "trq_out")) {
+      const int rows = c.R + c.J;
+      auto orow_ = [&](int r) { return h->d_outD + ((size_t)traj * rows + r) * w.OutC; };
+      if (n == "theta_out") { src = orow_(row); len = s.nOut; }
+      else if (n == "trq_out") { src = orow_(c.R + row); len = s.nOut; }
+      else {
+        len = s.nCartOut;
+        if (c.C == 7 && row >= 3) {  // q2aaVect (ba.cpp:382-403) with the host libm
+          if (s.status & ST_FATAL_MASK) return 0;
+          std::vector<double> q((size_t)4 * std::max(len, 1));
+          for (int k = 0; k < 4; ++k) g_d2h(q.data() + (size_t)k * len, orow_(c.J + 3 + k), (size_t)len * 8, h->stream);
+          g_sync(h->stream);
+          for (int i = 0; i < len && i < cap; ++i) {
+            const double qq[4] = {q[i], q[(size_t)len + i], q[(size_t)2 * len + i], q[(size_t)3 * len + i]};
+            double aa[3];
+            q2aa_dev(qq, aa);
+            if (buf) buf[i] = aa[row - 3];
+          }
+          return len;
+        }
+        src = orow_(c.J + row);
+      }
+    }
     else return -1;
     if (s.status & ST_FATAL_MASK) return 0;
     const int m = std::min(len, cap);

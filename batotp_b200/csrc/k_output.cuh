@@ -415,12 +415,26 @@ __host__ __device__ inline void q2aa_dev(const double q[4], double aa[3]) {
 // Output rows are stored as FP64 too (outD) when requested, for the strict-parity trig path.
 __global__ void k_out_pack(Ws w, const double *src, const double *srcM, int sStride, const double *trqSrc,
                            const double *trqM, float *thetaOut, float *cartOut, float *trqOut,
-                           double *cartOutD, int nblk) {
+                           double *cartOutD, double *outD, int nblk) {
   TP_DECOMP(nblk);
   if (b >= w.B) return;
   const TrajState &s = w.st[b];
-  if (s.status & ST_FATAL_MASK) return;
   const int J = CFG.J, C = CFG.C, Cin = CFG.Cin;
+  if (i >= w.OutC) return;
+  const bool fatal = (s.status & ST_FATAL_MASK) != 0;
+  // rows are zero beyond their length (and for trajectories that were not optimised)
+  if (fatal || i >= s.nOut) {
+    for (int r = 0; r < J; ++r) thetaOut[((size_t)b * J + r) * w.OutC + i] = 0.f;
+    if (trqOut && CFG.trqOn)
+      for (int r = 0; r < J; ++r) trqOut[((size_t)b * J + r) * w.OutC + i] = 0.f;
+  }
+  if (fatal || i >= s.nCartOut) {
+    if (cartOut)
+      for (int r = 0; r < Cin; ++r) cartOut[((size_t)b * Cin + r) * w.OutC + i] = 0.f;
+    if (cartOutD && C == 7)
+      for (int r = 0; r < 7; ++r) cartOutD[((size_t)b * 7 + r) * w.OutC + i] = 0.0;
+  }
+  if (fatal) return;
   const bool generic = CFG.c.robot_type == BATOTP_GENJNT;
   int seg = 0;
   double tau = 0, tau2 = 0, tau3 = 0;
@@ -442,6 +456,7 @@ __global__ void k_out_pack(Ws w, const double *src, const double *srcM, int sStr
       } else
         v = src[((size_t)b * CFG.R + r) * sStride + i];
       thetaOut[((size_t)b * J + r) * w.OutC + i] = (float)v;
+      if (outD) outD[((size_t)b * (CFG.R + J) + r) * w.OutC + i] = v;
     }
     if (trqOut && CFG.trqOn)
       for (int r = 0; r < J; ++r) {
@@ -452,9 +467,10 @@ __global__ void k_out_pack(Ws w, const double *src, const double *srcM, int sStr
         } else
           v = trqSrc[((size_t)b * MAXD + r) * w.Oc + i];
         trqOut[((size_t)b * J + r) * w.OutC + i] = (float)v;
+        if (outD) outD[((size_t)b * (CFG.R + J) + CFG.R + r) * w.OutC + i] = v;
       }
   }
-  if (i < s.nCartOut && (cartOut || cartOutD)) {
+  if (i < s.nCartOut && (cartOut || cartOutD || outD)) {
     double cv[MAXD];
     for (int r = 0; r < C; ++r) {
       if (re && !generic) {
@@ -463,6 +479,8 @@ __global__ void k_out_pack(Ws w, const double *src, const double *srcM, int sStr
       } else
         cv[r] = src[((size_t)b * CFG.R + J + r) * sStride + i];
     }
+    if (outD)
+      for (int r = 0; r < C; ++r) outD[((size_t)b * (CFG.R + J) + J + r) * w.OutC + i] = cv[r];
     if (C == 7) {
       if (cartOutD) {  // strict-parity path: the host applies q2aa with its own libm
         for (int r = 0; r < 7; ++r) cartOutD[((size_t)b * 7 + r) * w.OutC + i] = cv[r];
@@ -481,16 +499,27 @@ __global__ void k_out_pack(Ws w, const double *src, const double *srcM, int sStr
 __global__ void k_pack_hist(Ws w, float *histOut, int nblk) {
   TP_DECOMP(nblk);
   if (b >= w.B) return;
+  if (i >= w.Sc) return;
   const TrajState &s = w.st[b];
-  if (s.status & ST_FATAL_MASK) return;
+  const bool fatal = (s.status & ST_FATAL_MASK) != 0;
+  const int nRev = fatal ? 0 : s.nRev, nFwd = fatal ? 0 : s.nFwd;
   const double *hb = w.hist + (size_t)b * 4 * w.Sc;
   float *o = histOut + (size_t)b * 4 * w.Sc;
-  if (i < s.nRev) {
-    o[i] = (float)hb[(w.Sc - s.nRev) + i];
-    o[(size_t)w.Sc + i] = (float)hb[(size_t)w.Sc + (w.Sc - s.nRev) + i];
+  unsigned char *fl = w.flags + (size_t)b * 2 * w.Sc;
+  if (i < nRev) {
+    o[i] = (float)hb[(w.Sc - nRev) + i];
+    o[(size_t)w.Sc + i] = (float)hb[(size_t)w.Sc + (w.Sc - nRev) + i];
+  } else {
+    o[i] = 0.f;
+    o[(size_t)w.Sc + i] = 0.f;
+    fl[i] = 0;
   }
-  if (i < s.nFwd) {
+  if (i < nFwd) {
     o[2 * (size_t)w.Sc + i] = (float)hb[2 * (size_t)w.Sc + i];
     o[3 * (size_t)w.Sc + i] = (float)hb[3 * (size_t)w.Sc + i];
+  } else {
+    o[2 * (size_t)w.Sc + i] = 0.f;
+    o[3 * (size_t)w.Sc + i] = 0.f;
+    fl[(size_t)w.Sc + i] = 0;
   }
 }

@@ -64,6 +64,11 @@ def load(path: Optional[str] = None):
     L.batotp_cuda_set_chunk.argtypes = [C.c_void_p, C.c_int]
     L.batotp_cuda_launch_count.argtypes = [C.c_void_p]
     L.batotp_cuda_launch_count.restype = C.c_long
+    L.batotp_cuda_stats.argtypes = [C.c_void_p, _dp, C.c_int]
+    L.batotp_cuda_set_keep_f64.argtypes = [C.c_void_p, C.c_int]
+    L.batotp_cuda_fp64_peak.argtypes = [C.c_void_p, _dp, _dp]
+    L.batotp_cuda_stats_reset.argtypes = [C.c_void_p]
+    L.batotp_cuda_timer.argtypes = [C.c_void_p, C.c_int, _dp]
     L.batotp_cuda_optimize_batch.argtypes = [C.c_void_p, C.POINTER(BatotpCfg), C.POINTER(BatchIn), C.POINTER(BatchOut)]
     L.batotp_cuda_load.argtypes = [C.c_void_p, C.POINTER(BatotpCfg), C.POINTER(BatchIn)]
     for f in ("batotp_cuda_interp_input", "batotp_cuda_sweeps", "batotp_cuda_interp_output"):
@@ -155,8 +160,33 @@ class Context:
     def set_chunk(self, n: int):
         self.L.batotp_cuda_set_chunk(self.h, n)
 
+    def set_keep_f64(self, on: bool):
+        self.L.batotp_cuda_set_keep_f64(self.h, int(on))
+
     def launch_count(self) -> int:
         return int(self.L.batotp_cuda_launch_count(self.h))
+
+    def stats(self) -> dict:
+        v = (C.c_double * 6)()
+        self.L.batotp_cuda_stats(self.h, v, 6)
+        return dict(sweep_ms=v[0], sweep_launches=int(v[1]), verifies=int(v[2]), steps=int(v[3]),
+                    trajectories=int(v[4]), launches=int(v[5]))
+
+    def fp64_peak(self):
+        a, b = C.c_double(0), C.c_double(0)
+        self.L.batotp_cuda_fp64_peak(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def stats_reset(self):
+        self.L.batotp_cuda_stats_reset(self.h)
+
+    def timer_start(self):
+        self.L.batotp_cuda_timer(self.h, 0, None)
+
+    def timer_stop_ms(self) -> float:
+        ms = C.c_double(0)
+        self.L.batotp_cuda_timer(self.h, 1, C.byref(ms))
+        return ms.value
 
     @staticmethod
     def make_in(theta=None, cart=None, tres=0.01, n0=None, timestamp=None, device_ptrs=None) -> BatchIn:

@@ -43,6 +43,18 @@ const char *batotp_cuda_last_error(batotp_handle h);
 int batotp_cuda_set_chunk(batotp_handle h, int chunk);
 /* number of kernels launched by this context since creation (for the benchmark's gpu_launches) */
 long batotp_cuda_launch_count(batotp_handle h);
+/* measurement hooks for bench.py.
+ * _stats: out[0] device ms spent in the sweep kernel (CUDA events on the launching stream),
+ *         out[1] sweep launches, out[2] constraint verifications (ba.cpp:1449 calls),
+ *         out[3] RK steps, out[4] trajectories, out[5] all kernel launches — since the last reset.
+ * _timer(which=0) records an event on the context's stream, _timer(which=1) records a second one,
+ *         waits for it and returns the elapsed device milliseconds between the two. */
+int batotp_cuda_stats(batotp_handle h, double *out, int n);
+int batotp_cuda_stats_reset(batotp_handle h);
+int batotp_cuda_timer(batotp_handle h, int which, double *elapsed_ms);
+/* measured FP64-pipe peak of the device in TFLOP/s: fused multiply-add chains, and separate
+ * multiply + add chains (the ceiling of this library's -fmad=false kernels) */
+int batotp_cuda_fp64_peak(batotp_handle h, double *tflops_fma, double *tflops_nofma);
 
 /* ---- batch input: what BA::loadTrajectoryData leaves in Traj (ba.cpp:2206-2461) -------- */
 typedef struct batotp_batch_in {
@@ -114,8 +126,27 @@ int batotp_cuda_mvc_per_sample(batotp_handle h, double sdot_start, double *sdot_
  * "theta_out","cart_out","trq_out" (FP64 before the float cast).  Returns the length or -1. */
 int batotp_cuda_get_f64(batotp_handle h, const char *name, int traj, int row, double *buf, int cap);
 
-/* host-side helpers shared with the facade */
-int batotp_read_config(const char *path, batotp_cfg *cfg, char *traj_file_name, int name_cap); /* ba.cpp:1942-2087 */
+/* keep FP64 copies of the final rows on the device so that batotp_cuda_get_f64 can return
+ * "theta_out"/"cart_out"/"trq_out" before the float cast (the facade fills Traj with them). */
+int batotp_cuda_set_keep_f64(batotp_handle h, int on);
+
+/* ---- host-side file formats, byte-compatible with the reference (no CUDA involved) ------ */
+int batotp_read_config(const char *path, batotp_cfg *cfg, char *traj_file_name, int name_cap); /* BA::readConfigData ba.cpp:1942-2087 */
+/* BA::trajReadBIN ba.cpp:2257-2312: rows are malloc'ed [coord][n0] float32 (NULL if the block is absent); free with batotp_free */
+int batotp_read_traj_bin(const char *path, int n_joints, int n_cart, double *tres, int *n0, float **theta, float **cart);
+/* BA::trajReadCSV ba.cpp:2322-2461: FP64 rows + timestamps; header names ';'-joined */
+int batotp_read_traj_csv(const char *path, int n_joints, int n_cart, int is_generic, double *tres, int *n0,
+                         double **theta, double **cart, double **timestamp, char *header, int header_cap);
+void batotp_free(void *p);
+/* BA::trajWriteBIN ba.cpp:2582-2651 (cart / trq NULL = block absent; pitch = row stride in points) */
+int batotp_write_traj_bin(const char *path, double sres, unsigned n_pts, int n_joints, const float *theta, int n_cart,
+                          const float *cart, const float *trq, int pitch);
+/* BA::sdotWrite ba.cpp:2726-2759 */
+int batotp_write_s_sdot(const char *path, double sres, int n_rev, const float *s_rev, const float *sdot_rev,
+                        int n_fwd, const float *s_fwd, const float *sdot_fwd);
+/* BA::trajWriteCSV ba.cpp:2660-2717 */
+int batotp_write_traj_csv(const char *path, const char *header, double sres, int n_pts, int n_joints,
+                          const float *theta, int n_cart, const float *cart, int pitch);
 
 #ifdef __cplusplus
 }

@@ -1054,8 +1054,12 @@ static void ba_interp_traj_linear(orc_traj *t, int nNew) {
   dv_scale(&pNew, 1.0 / (nNew - 1));
   segs_t sg = {0};
   spl_find_segs(&pOld, &pNew, &sg);
-  for (int i = 0; i < t->nJoints; ++i) spl_interp_linear(&t->theta[i], &sg);
-  for (int i = 0; i < t->nCart; ++i) spl_interp_linear(&t->cart[i], &sg);
+  /* rows that do not exist yet (e.g. the generic robot's Cartesian block before ba.cpp:257) are out-of-bounds
+   * reads in the reference (undefined behaviour); here they are skipped and stay empty */
+  for (int i = 0; i < t->nJoints; ++i)
+    if (t->theta[i].n == nOld) spl_interp_linear(&t->theta[i], &sg);
+  for (int i = 0; i < t->nCart; ++i)
+    if (t->cart[i].n == nOld) spl_interp_linear(&t->cart[i], &sg);
   t->sres = t->sres * (nOld - 1) / (nNew - 1);
   t->nPts = nNew;
   segs_free(&sg);

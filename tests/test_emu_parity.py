@@ -1,0 +1,84 @@
+"""CPU: the kernel sources compiled for the host (tests/_emu, -DBATOTP_HOST_EMU: every kernel
+body run sequentially, see batotp_b200/csrc/emu.h) against the oracle.  This checks the exact
+per-thread program that runs on the B200 — and the chunk pipeline / C-ABI around it — without a
+GPU; the `-m gpu` tests repeat it on the device."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import _parity as P
+from batotp_b200 import native
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import __graft_entry__ as g
+    c = native.Context(0, g.build_emu())
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("name", P.STOCK)
+def test_stock_folders_reproduce_reference_files(ctx, name):
+    cfg, tres, th, ca, ts = P.load_stock(name)
+    res = P.run_device(ctx, cfg, tres, th, ca, ts)
+    assert res.status[0] & native.ST_FATAL_MASK == 0
+    d = P.GOLD + "/stock/" + name
+    assert P.device_traj_out_bytes(cfg, res, 0) == open(d + "/ref_traj_out.dat", "rb").read()
+    assert P.device_s_sdot_bytes(res, 0) == open(d + "/ref_s-sdot.dat", "rb").read()
+    orc = P.OracleRun(cfg, tres, None if th is None else th[0], None if ca is None else ca[0],
+                      None if ts is None else ts[0])
+    assert P.compare(cfg, res, 0, orc) == []
+
+
+@pytest.mark.parametrize("name,count", [("GEN7DOF", 24), ("KUKA", 2), ("CSPR3DOF", 3)])
+def test_synthetic_batches_match_oracle_and_golden(ctx, name, count):
+    g = P.synthetic_json()[name]
+    cfg, tres, th, ca = P.load_synth(name, 0, count)
+    res = P.run_device(ctx, cfg, tres, th, ca)
+    for b in range(count):
+        orc = P.OracleRun(cfg, tres, None if th is None else th[b], None if ca is None else ca[b])
+        assert P.compare(cfg, res, b, orc) == [], b
+        assert (res.n_rev[b], res.n_fwd[b], res.n_out[b]) == (g["n_rev"][b], g["n_fwd"][b], g["n_out"][b])
+        assert hashlib.sha256(res.theta_out[b, :, :res.n_out[b]].tobytes()).hexdigest() == g["theta_out_sha256"][b]
+
+
+def test_chunking_and_capacity_retries_do_not_change_results(ctx):
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 40, 10)
+    ctx.set_chunk(4)  # 3 chunks: 4 + 4 + 2
+    a = P.run_device(ctx, cfg, tres, th, None)
+    ctx.set_chunk(16384)
+    b = P.run_device(ctx, cfg, tres, th, None)
+    for nm in ("status", "n_rev", "n_fwd", "n_out", "t_total", "theta_out", "hist", "flags"):
+        assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
+
+
+def test_ragged_short_and_degenerate_inputs(ctx):
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 7, 6)
+    th = th.copy()
+    n0 = np.array([400, 57, 3, 2, 1, 400], dtype=np.int32)
+    th[5, :, :] = th[5, :, :1]  # all points identical -> "no optimization" (ba.cpp:484-488)
+    th[1, :, 20:25] = th[1, :, 19:20]  # repeated points -> remClosePts removes them (util.cpp:452)
+    res = P.run_device(ctx, cfg, tres, th, None, n0=n0)
+    for b in range(6):
+        orc = P.OracleRun(cfg, tres, th[b], None, n0=int(n0[b]))
+        assert P.compare(cfg, res, b, orc) == [], (b, res.status[b])
+    assert res.status[4] & 1 and res.status[5] & (1 | 2)
+    assert res.status[0] == 0 or res.status[0] == native.ST_BISECT_FAIL
+
+
+def test_per_sample_mvc_matches_oracle(ctx):
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 3, 2)
+    bi = ctx.make_in(th, None, tres)
+    ctx.load(cfg, bi)
+    ctx.interp_input()
+    from _oracle import Oracle
+    got = ctx.mvc_per_sample(2, 2048, 1.0e3)
+    for b in range(2):
+        o = Oracle(cfg)
+        o.load_raw(400, tres, th[b])
+        assert o.interp_input() == 0
+        want = o.mvc_per_sample(1.0e3)
+        assert np.array_equal(got[b, :len(want)], want)
+        assert want.min() > 0 and want.max() < 1.0e3

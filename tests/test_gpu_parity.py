@@ -1,0 +1,128 @@
+"""GPU (-m gpu): the product library batotp_b200/lib/libbatotp_cuda.so on a B200, through the C-ABI,
+against the oracle restatement, the golden reference files and size-independent properties."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import _parity as P
+from batotp_b200 import native
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = native.Context(0)  # product library; raises without a CUDA device
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("name", P.STOCK)
+def test_stock_folders_reproduce_reference_files(ctx, name):
+    cfg, tres, th, ca, ts = P.load_stock(name)
+    res = P.run_device(ctx, cfg, tres, th, ca, ts)
+    assert res.status[0] & native.ST_FATAL_MASK == 0
+    g = P.golden_json()[name]
+    assert (res.n_grid[0], res.n_rev[0], res.n_fwd[0], res.n_out[0]) == (g["n_grid"], g["n_rev"], g["n_fwd"], g["n_out"])
+    assert res.t_total[0] == g["t_total"]  # total trajectory time: exact, hence within 1e-9 relative
+    d = P.GOLD + "/stock/" + name
+    assert P.device_traj_out_bytes(cfg, res, 0) == open(d + "/ref_traj_out.dat", "rb").read()
+    assert P.device_s_sdot_bytes(res, 0) == open(d + "/ref_s-sdot.dat", "rb").read()
+    orc = P.OracleRun(cfg, tres, None if th is None else th[0], None if ca is None else ca[0],
+                      None if ts is None else ts[0])
+    assert P.compare(cfg, res, 0, orc) == []  # includes the limit-active switching flags
+
+
+@pytest.mark.parametrize("name,count,check", [("GEN7DOF", 512, 48), ("KUKA", 8, 4), ("CSPR3DOF", 32, 8)])
+def test_synthetic_batches_match_oracle_and_golden(ctx, name, count, check):
+    g = P.synthetic_json()[name]
+    cfg, tres, th, ca = P.load_synth(name, 0, count)
+    res = P.run_device(ctx, cfg, tres, th, ca)
+    for b in range(min(count, g["B"])):
+        assert (res.n_rev[b], res.n_fwd[b], res.n_out[b]) == (g["n_rev"][b], g["n_fwd"][b], g["n_out"][b]), b
+        assert res.t_total[b] == g["t_total"][b]
+        assert hashlib.sha256(res.theta_out[b, :, :res.n_out[b]].tobytes()).hexdigest() == g["theta_out_sha256"][b]
+    rng = np.random.RandomState(1)
+    for b in rng.choice(count, check, replace=False):
+        orc = P.OracleRun(cfg, tres, None if th is None else th[b], None if ca is None else ca[b])
+        assert P.compare(cfg, res, b, orc) == [], b
+
+
+def test_chunking_does_not_change_results(ctx):
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 1000, 300)
+    ctx.set_chunk(128)
+    a = P.run_device(ctx, cfg, tres, th, None, out_cap=4096, hist_cap=4096)
+    ctx.set_chunk(16384)
+    b = P.run_device(ctx, cfg, tres, th, None, out_cap=4096, hist_cap=4096)
+    for nm in ("status", "n_rev", "n_fwd", "n_out", "t_total", "theta_out", "hist", "flags"):
+        assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
+
+
+def test_ragged_short_and_degenerate_inputs(ctx):
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 7, 6)
+    th = th.copy()
+    n0 = np.array([400, 57, 3, 2, 1, 400], dtype=np.int32)
+    th[5, :, :] = th[5, :, :1]
+    th[1, :, 20:25] = th[1, :, 19:20]
+    res = P.run_device(ctx, cfg, tres, th, None, n0=n0)
+    for b in range(6):
+        orc = P.OracleRun(cfg, tres, th[b], None, n0=int(n0[b]))
+        assert P.compare(cfg, res, b, orc) == [], (b, res.status[b])
+    assert res.status[4] & 1 and res.status[5] & (1 | 2)
+
+
+def test_large_batch_properties(ctx):
+    """BASELINE-size behaviour through properties that need no oracle run per path: every path is
+    optimised, total time == integRes * steps, results do not depend on the position in the batch or on
+    the run (idempotence), and the output respects the joint limits the config imposes."""
+    B = 16384
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 50000, B)
+    res = native.BatchResult(B, 7, 0, 3200, 0, False, want_hist=False)
+    ctx.optimize_batch(cfg, ctx.make_in(th, None, tres), res)
+    assert np.all(res.status & native.ST_FATAL_MASK == 0)
+    assert np.array_equal(res.t_total, cfg.integ_res * (res.n_fwd - 1))
+    assert res.n_fwd.min() > 1000 and res.n_fwd.max() < 3200 and np.all(res.n_fwd > res.n_rev)
+    perm = np.random.RandomState(3).permutation(B)
+    res2 = native.BatchResult(B, 7, 0, 3200, 0, False, want_hist=False)
+    ctx.optimize_batch(cfg, ctx.make_in(np.ascontiguousarray(th[perm]), None, tres), res2)
+    assert np.array_equal(res2.n_fwd, res.n_fwd[perm]) and np.array_equal(res2.n_rev, res.n_rev[perm])
+    assert np.array_equal(res2.theta_out, res.theta_out[perm])
+    # joint velocity of the output trajectory stays within the 5 rad/s limit (+ bisection/interp tolerance)
+    n = int(res.n_out[0])
+    v = np.diff(res.theta_out[:64, :, :n].astype(np.float64), axis=2) / res.out_sres[0]
+    assert np.abs(v).max() < 5.0 * 1.05
+    # spot-check 8 random paths against the oracle
+    for b in np.random.RandomState(5).choice(B, 8, replace=False):
+        orc = P.OracleRun(cfg, tres, th[b], None)
+        assert P.compare(cfg, res, b, orc, check_hist=False) == [], b
+
+
+def test_per_sample_mvc_matches_oracle(ctx):
+    from _oracle import Oracle
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 3, 4)
+    ctx.load(cfg, ctx.make_in(th, None, tres))
+    ctx.interp_input()
+    got = ctx.mvc_per_sample(4, 2048, 1.0e3)
+    for b in range(4):
+        o = Oracle(cfg)
+        o.load_raw(400, tres, th[b])
+        assert o.interp_input() == 0
+        want = o.mvc_per_sample(1.0e3)
+        assert np.array_equal(got[b, :len(want)], want)
+
+
+def test_device_trig_mode_is_within_tolerance(ctx):
+    """trig_mode 0 (CUDA sincos in the KUKA forward kinematics) is not bit-identical to the host libm;
+    it must stay within the bisection tolerance (1e-3 relative) on the s-sdot profile and within
+    a handful of RK steps on the switching counts."""
+    cfg, tres, th, ca, ts = P.load_stock("KUKA-LWR-IV")
+    strict = P.run_device(ctx, cfg, tres, th, ca, ts)
+    cfg2 = cfg.copy()
+    cfg2.trig_mode = 0
+    fast = P.run_device(ctx, cfg2, tres, th, ca, ts)
+    assert fast.status[0] & native.ST_FATAL_MASK == 0
+    assert abs(int(fast.n_fwd[0]) - int(strict.n_fwd[0])) <= 8
+    assert abs(fast.t_total[0] - strict.t_total[0]) / strict.t_total[0] < 2e-3
+    n = min(int(fast.n_out[0]), int(strict.n_out[0]))
+    assert np.abs(fast.theta_out[0, :, :n] - strict.theta_out[0, :, :n]).max() < 0.5  # degrees, over a 20 s move

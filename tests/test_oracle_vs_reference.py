@@ -1,0 +1,96 @@
+"""CPU: the oracle restatement against the UNMODIFIED reference sources compiled into
+oracle/_ref (skipped when that library is absent, i.e. where /root/reference never existed)."""
+import numpy as np
+import pytest
+
+import _parity as P
+from _oracle import Oracle, Ref, ref_available
+
+pytestmark = pytest.mark.skipif(not ref_available(), reason="oracle/_ref/libbatotp_ref.so not built")
+
+
+def _pair(name, tmp_path):
+    d = P.GOLD + "/stock/" + name + "/"
+    r = Ref(d + "config.dat", d, str(tmp_path) + "/")
+    assert r.load_file() == 0
+    cfg, tres, th, ca, ts = P.load_stock(name)
+    rc = r.cfg()
+    import ctypes as C
+    assert bytes(C.string_at(C.byref(cfg), C.sizeof(cfg))) == bytes(C.string_at(C.byref(rc), C.sizeof(rc))), \
+        "Python config parser disagrees with BA::readConfigData"
+    o = Oracle(cfg)
+    n0 = (th if th is not None else ca).shape[2]
+    o.load_raw(n0, tres, None if th is None else th[0], None if ca is None else ca[0], None if ts is None else ts[0])
+    return cfg, r, o
+
+
+@pytest.mark.parametrize("name", P.STOCK)
+def test_every_stage_matches_bit_for_bit(name, tmp_path):
+    cfg, r, o = _pair(name, tmp_path)
+    J = cfg.n_joints
+    assert r.interp_input() == 0 and o.interp_input() == 0
+    assert r.scalar("nPts") == o.scalar("nPts")
+    for nm in ("theta", "thetaD", "thetaD2", "thetaC_y", "thetaC_m"):
+        for j in range(J):
+            x, y = r.vec(nm, j), o.vec(nm, j)
+            if nm.startswith("thetaC"):
+                x, y = x[:-1], y[:-1]  # the last coefficient slot is never written (spline.cpp:203)
+            assert np.array_equal(x, y), (nm, j)
+    if cfg.is_trq_on:
+        for nm in ("a1", "a2", "a3", "a4", "a1C_m", "a4C_m"):
+            for j in range(J):
+                x, y = r.vec(nm, j), o.vec(nm, j)
+                if nm.endswith("_m"):
+                    x, y = x[:-1], y[:-1]
+                assert np.array_equal(x, y), (nm, j)
+    for d, last in ((-1, 0), (1, 1)):
+        assert r.sweep(d, last) == 0 and o.sweep(d, last) == 0
+        assert np.array_equal(r.vec("sMVC"), o.vec("sMVC")) and np.array_equal(r.vec("sdot"), o.vec("sdot"))
+    assert r.scalar("tTotalTraj") == o.scalar("tTotalTraj") and r.scalar("sLastSec") == o.scalar("sLastSec")
+    r.interp_output()
+    o.interp_output()
+    for nm, n in (("theta", J), ("cart", int(r.scalar("cartRows"))), ("trq", int(r.scalar("trqRows")))):
+        assert n == int(o.scalar({"theta": "nCart", "cart": "cartRows", "trq": "trqRows"}[nm])) or nm == "theta"
+        for j in range(n):
+            assert np.array_equal(r.vec(nm, j), o.vec(nm, j)), (nm, j)
+
+
+@pytest.mark.parametrize("name", P.STOCK)
+def test_switching_flags_match_instrumented_reference(name, tmp_path):
+    """The per-step switching flags: the reference's own per-point functions driven by the harness
+    loop (ref_sweep_flags) must (a) reproduce BA::sweep's history bit for bit and (b) give the
+    flags the oracle records."""
+    cfg, r, o = _pair(name, tmp_path)
+    assert r.interp_input() == 0 and o.interp_input() == 0
+    s, sd, fl = r.sweep_flags(-1)
+    assert o.sweep(-1, 0) == 0
+    hs, hsd = o.vec("hist_s0"), o.vec("hist_sdot0")
+    assert len(s) == len(hs)
+    # integration order vs ascending-s storage; the last integrated point is snapped afterwards
+    assert np.array_equal(s[:-1][::-1], hs[1:]) and np.array_equal(sd[:-1][::-1], hsd[1:])
+    assert np.array_equal(fl, o.vec("flags0").astype(np.uint8))
+    assert r.sweep(-1, 0) == 0  # the real reverse sweep, to set up the forward pass identically
+    s, sd, fl = r.sweep_flags(1)
+    assert o.sweep(1, 1) == 0
+    assert np.array_equal(s[:-1], o.vec("hist_s1")[:-1]) and np.array_equal(sd[:-1], o.vec("hist_sdot1")[:-1])
+    assert np.array_equal(fl, o.vec("flags1").astype(np.uint8))
+
+
+def test_batch_runner_agrees(tmp_path):
+    import ctypes as C
+    from _oracle import orc_lib, ref_lib
+    B = 12
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 500, B)
+    cfgp = (P.GOLD + "/synthetic/GEN7DOF_config.dat").encode()
+    fp, dp, ip = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int)
+    outs = []
+    for fn, first in ((ref_lib().ref_batch_run, cfgp), (orc_lib().orc_batch_run, C.byref(cfg))):
+        tt = np.zeros(B); nr = np.zeros(B, np.int32); nf = np.zeros(B, np.int32); no = np.zeros(B, np.int32)
+        st = np.zeros(B, np.int32); out = np.zeros((B, 7, 4096), np.float32)
+        el = fn(first, B, th.shape[2], tres, th.ctypes.data_as(fp), None, 2, tt.ctypes.data_as(dp),
+                nr.ctypes.data_as(ip), nf.ctypes.data_as(ip), no.ctypes.data_as(ip), st.ctypes.data_as(ip),
+                out.ctypes.data_as(fp), 4096)
+        assert el > 0
+        outs.append((tt, nr, nf, no, st, out))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
