@@ -356,6 +356,10 @@ void set_cfg(batotp_ctx *h, const batotp_cfg *cfg) {
                            {0, 0, 0, 0, -5103. / 18656, -2187. / 6784},
                            {0, 0, 0, 0, 0, 11. / 84}};  // ba.cpp:58-63, literals as written there
   memcpy(d.B, Bt, sizeof(Bt));
+  if (!h->haveCfg || memcmp(&h->cfg.c, cfg, sizeof(batotp_cfg)) != 0) {
+    h->hwNc = 0;  // capacity high-water marks belong to one configuration
+    h->hwSc = 0;
+  }
   h->cfg = d;
   h->haveCfg = true;
   g_set_cfg(d, h->stream);

@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--chunk", type=int, default=32768, help="paths per device pass")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     return ap.parse_args()
 
 
@@ -291,11 +292,11 @@ def main_b200(args):
             chk += float(res_e.t_total[:n].sum())
         return chk
 
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(0 if args.skip_e2e else max(1, min(args.warmup, 2))):
         step_e2e()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(1 if args.skip_e2e else args.steps):
         step_e2e()
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
