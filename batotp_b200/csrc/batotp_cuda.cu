@@ -492,26 +492,27 @@ void thomas_rows(batotp_ctx *h, const double *src, double *dst, int stride, int 
 template <int J, bool CART, bool TRQ>
 void launch_sweep(batotp_ctx *h) {
   g_zero(h->w.queue, sizeof(int) * 4, h->stream);
+  constexpr int RT = J + (CART ? 3 : 0) + (TRQ ? 4 * J : 0);
+  const size_t smem = (size_t)(36 + (RT * 4 + 14) * SW_NT) * sizeof(double);
 #ifndef BATOTP_HOST_EMU
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CU_CHECK(cudaFuncSetAttribute(k_sweep<J, CART, TRQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int perSm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_sweep<J, CART, TRQ>, 128, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_sweep<J, CART, TRQ>, SW_NT, smem);
   if (perSm < 1) perSm = 1;
-  int blocks = std::min(sms * perSm, cdiv(h->B, 128));
+  int blocks = std::min(sms * perSm, cdiv(h->B, SW_NT));
   if (blocks < 1) blocks = 1;
-#else
-  int blocks = 1;
-#endif
-#ifndef BATOTP_HOST_EMU
   if (!h->evS0) {
     CU_CHECK(cudaEventCreate(&h->evS0));
     CU_CHECK(cudaEventCreate(&h->evS1));
   }
   CU_CHECK(cudaEventRecord(h->evS0, h->stream));
+#else
+  int blocks = 1;
 #endif
-  BATOTP_LAUNCH((k_sweep<J, CART, TRQ>), dim3(blocks), dim3(128), h->stream, h->w);
+  BATOTP_LAUNCH_SMEM((k_sweep<J, CART, TRQ>), dim3(blocks), dim3(SW_NT), smem, h->stream, h->w);
   g_check_launch();
 #ifndef BATOTP_HOST_EMU
   CU_CHECK(cudaEventRecord(h->evS1, h->stream));
@@ -755,6 +756,57 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, doubl
 }
 #endif
 
+// Self-test of the shared-reciprocal division (k_sweep.cuh sdiv::) against the compiler's '/':
+// pseudo-random operand pairs (full-range mantissas; exponents concentrated in the working range,
+// a share of them near and beyond the fast-path window so that the fallback is exercised too).
+#ifndef BATOTP_HOST_EMU
+__device__ __forceinline__ unsigned long long st_mix(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ double st_operand(unsigned long long bits, unsigned long long sel) {
+  const unsigned long long mant = bits & 0x000FFFFFFFFFFFFFull, sign = bits & 0x8000000000000000ull;
+  long long e;
+  const unsigned k = (unsigned)(sel & 15u);
+  if (k < 12)
+    e = 1023 + (long long)((sel >> 8) % 81) - 40;  // 2^-40 .. 2^40
+  else if (k < 14)
+    e = 1023 + (long long)((sel >> 8) % 2001) - 1000;  // anywhere
+  else
+    e = ((sel >> 8) & 1) ? (long long)((sel >> 16) % 80) : 2046 - (long long)((sel >> 16) % 80);  // extremes
+  if (e < 0) e = 0;
+  if (e > 2046) e = 2046;
+  return __longlong_as_double((long long)(sign | ((unsigned long long)e << 52) | mant));
+}
+__global__ void k_selftest_div(unsigned long long seed, int perThread, unsigned long long *mismatch,
+                               unsigned long long *fastTaken) {
+  const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long bad = 0, fast = 0;
+  unsigned long long z = st_mix(seed ^ (t * 0xD1342543DE82EF95ull));
+  for (int it = 0; it < perThread; ++it) {
+    const unsigned long long ba = st_mix(z), bb = st_mix(ba), sel = st_mix(bb);
+    z = sel;
+    const double b = st_operand(bb, sel >> 20);
+    const sdiv::Rcp rc = sdiv::prep(b);
+    // several numerators per denominator, like the kernels use it
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double a = st_operand(st_mix(ba + k), sel + k * 977);
+      const double q1 = sdiv::div(a, b, rc);
+      const double q2 = a / b;
+      if (__double_as_longlong(q1) != __double_as_longlong(q2) && !(q1 != q1 && q2 != q2)) bad++;
+      const double q0 = __dmul_rn(a, rc.r);
+      const double q = __fma_rn(rc.r, __fma_rn(-b, q0, a), q0);
+      if (rc.ok && sdiv::exp_ok(a) && sdiv::exp_ok(q)) fast++;
+    }
+  }
+  atomicAdd(mismatch, bad);
+  atomicAdd(fastTaken, fast);
+}
+#endif
+
 // ----------------------------------------------------------------------------- C ABI
 extern "C" {
 
@@ -862,6 +914,39 @@ int batotp_cuda_fp64_peak(batotp_handle h, double *tflops_fma, double *tflops_no
 #else
   if (tflops_fma) *tflops_fma = 0;
   if (tflops_nofma) *tflops_nofma = 0;
+  return h ? 0 : -1;
+#endif
+}
+
+int batotp_cuda_selftest_div(batotp_handle h, unsigned long long seed, long long n, long long *mismatches,
+                             long long *fast_path_taken) {
+#ifndef BATOTP_HOST_EMU
+  if (!h) return -1;
+  try {
+    CU_CHECK(cudaSetDevice(h->device));
+    unsigned long long *d = (unsigned long long *)g_alloc(16);
+    g_zero(d, 16, h->stream);
+    const int threads = 256, perThread = 256;
+    long long blocks = (n / 3 + (long long)threads * perThread - 1) / ((long long)threads * perThread);
+    if (blocks < 1) blocks = 1;
+    k_selftest_div<<<(unsigned)blocks, threads, 0, h->stream>>>(seed, perThread, d, d + 1);
+    CU_CHECK(cudaGetLastError());
+    unsigned long long out[2] = {0, 0};
+    g_d2h(out, d, 16, h->stream);
+    g_sync(h->stream);
+    g_free(d);
+    if (mismatches) *mismatches = (long long)out[0];
+    if (fast_path_taken) *fast_path_taken = (long long)out[1];
+    return 0;
+  } catch (const Err &e) {
+    h->err = e.msg;
+    return -1;
+  }
+#else
+  (void)seed;
+  (void)n;
+  if (mismatches) *mismatches = 0;
+  if (fast_path_taken) *fast_path_taken = 0;
   return h ? 0 : -1;
 #endif
 }

@@ -47,6 +47,7 @@ static inline void emu_launch(dim3 grid, dim3 block, F f) {
           }
 }
 #define BATOTP_LAUNCH(kern, grid, block, stream, ...) emu_launch((grid), (block), [&] { kern(__VA_ARGS__); })
+#define BATOTP_LAUNCH_SMEM(kern, grid, block, smem, stream, ...) emu_launch((grid), (block), [&] { kern(__VA_ARGS__); })
 
 static inline int atomicAdd(int *p, int v) {
   int o = *p;
@@ -65,4 +66,5 @@ static inline int atomicMax(int *p, int v) {
 }
 #else
 #define BATOTP_LAUNCH(kern, grid, block, stream, ...) kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define BATOTP_LAUNCH_SMEM(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif

@@ -14,63 +14,35 @@ __global__ void k_mvc(Ws w, double sdotStart, double *out, int cap, int nblk) {
   const TrajState &s = w.st[b];
   if (s.status & ST_FATAL_MASK) return;
   if (i >= s.nPtsC || i >= cap) return;
-  SweepLane<J, CART, TRQ> L;
-  L.b = b;
-  L.status = 0;
-  L.dir = -1;
-  L.absh = s.integRes;
-  L.h = -L.absh;
-  L.sresC = s.sresC;
-  L.vFact = s.vFact;
-  L.aFact = s.aFact;
-  L.nPtsC = s.nPtsC;
-  L.lastSeg = s.nPtsC - 2;
-  L.sBack = s.sresC * (double)(s.nPtsC - 1);
-  L.sdotCap = L.sBack / L.absh;
-  L.sddotmax = 2 * L.sBack / (L.absh * L.absh);
-  L.thrV = CFG.c.jnt_thresh * L.vFact;
-  L.thrA = CFG.c.jnt_thresh * L.aFact;
-  L.thrQ = CFG.quadThresh * L.aFact;
-  L.thrQ2 = CFG.quadThresh * CFG.quadThresh * L.aFact * L.aFact;
-  L.amaxSQ = CFG.c.cart_acc_max * CFG.c.cart_acc_max;
-  L.tab = w.tab + (size_t)b * w.Nc * (size_t)w.RT * 4;
-  L.nM = 0;
-  L.sM = L.sdM = nullptr;
-  L.segM = 0;
-  L.seg = imin_(i, s.nPtsC - 2);
-  L.segLoaded = -1;
-  L.sCur = s.sresC * (double)i;
-  L.sdotMin = 0.0;
-  L.limT = 0;
-  L.isOn = 0;
-  L.sLastSec = 0;
-  L.eval_partials(w.Nc);
-  const double sd = L.sdot_lim(sdotStart);
-  L.bisect_begin(sd);
-  for (;;) {  // ba.cpp:1270-1321
-    const bool viol = L.verify(L.sdotCur);
-    if (viol) {
-      L.sdotH = L.sdotCur;
-      if (!L.anyGood) {
-        L.lowFact *= 2.0;
-        L.sdotL = dmax_(.999 * 0.0, (1.0 - L.lowFact) * L.sdotH);
-      }
-    } else {
-      if (L.nIter == 0) break;
-      L.anyGood = 1;
-      const double last = L.sdotGood;
-      L.sdotGood = L.sdotCur;
-      const double err = fabs(L.sdotGood - last) / L.sdotGood;
-      if (err < .001 || L.sdotCur < 0.0) {
-        L.sdotIn = L.sdotCur;
-        break;
-      }
-      L.sdotL = L.sdotCur;
-    }
-    L.nIter++;
-    if (L.nIter > 100) break;
-    if (L.sdotCur < 0 || ((L.sdotH - L.sdotL) / L.sdotH < 1e-20 && !L.anyGood)) break;
-    L.sdotCur = .5 * (L.sdotH + L.sdotL);
+  constexpr int NK = J + (CART ? 3 : 0);
+  constexpr int RT = NK + (TRQ ? 4 * J : 0);
+  const double absh = s.integRes;
+  const double sBack = s.sresC * (double)(s.nPtsC - 1);
+  TrajConsts C;
+  traj_consts(C, s, sBack, absh);
+  int seg = imin_(i, s.nPtsC - 2);
+  const double sCur = s.sresC * (double)i;
+  double sSeg;
+  cursor_uniform(C.sresC, s.nPtsC - 2, sCur, seg, sSeg);
+  const double tau = (sCur - sSeg) / (C.sresC * (double)(seg + 1) - sSeg);
+  struct KGlobal {
+    const double *t;
+    __host__ __device__ __forceinline__ double operator()(int r, int q) const { return t[r * 4 + q]; }
+  };
+  const KGlobal K{w.tab + ((size_t)b * w.Nc + seg) * (size_t)RT * 4};
+  PointVals<J, CART, TRQ> P;
+  eval_point<J, CART, TRQ>(P, K, tau, C);
+  // sdotLim without the MVC term and with _sdotMin = 0
+  double sd = sdotStart;
+  sd = dmin_(sd, sBack / absh);
+  sd = dmax_(sd, 0.0);
+  sd = dmin_(sd, P.velLim);
+  Bisect bis;
+  bis.begin(sd);
+  double Lo, Hi;
+  for (;;) {
+    const bool viol = verify_point<J, CART, TRQ>(P, C, bis.sdotCur, Lo, Hi);
+    if (bis.step(viol) != 0) break;
   }
-  out[(size_t)b * cap + i] = L.sdotIn;
+  out[(size_t)b * cap + i] = bis.sdotIn;
 }

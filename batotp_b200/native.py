@@ -67,6 +67,8 @@ def load(path: Optional[str] = None):
     L.batotp_cuda_stats.argtypes = [C.c_void_p, _dp, C.c_int]
     L.batotp_cuda_set_keep_f64.argtypes = [C.c_void_p, C.c_int]
     L.batotp_cuda_fp64_peak.argtypes = [C.c_void_p, _dp, _dp]
+    L.batotp_cuda_selftest_div.argtypes = [C.c_void_p, C.c_ulonglong, C.c_longlong, C.POINTER(C.c_longlong),
+                                           C.POINTER(C.c_longlong)]
     L.batotp_cuda_stats_reset.argtypes = [C.c_void_p]
     L.batotp_cuda_timer.argtypes = [C.c_void_p, C.c_int, _dp]
     L.batotp_cuda_optimize_batch.argtypes = [C.c_void_p, C.POINTER(BatotpCfg), C.POINTER(BatchIn), C.POINTER(BatchOut)]
@@ -176,6 +178,12 @@ class Context:
         a, b = C.c_double(0), C.c_double(0)
         self.L.batotp_cuda_fp64_peak(self.h, C.byref(a), C.byref(b))
         return a.value, b.value
+
+    def selftest_div(self, seed: int, n: int):
+        bad, fast = C.c_longlong(0), C.c_longlong(0)
+        if self.L.batotp_cuda_selftest_div(self.h, seed, n, C.byref(bad), C.byref(fast)) != 0:
+            self._err('batotp_cuda_selftest_div')
+        return bad.value, fast.value
 
     def stats_reset(self):
         self.L.batotp_cuda_stats_reset(self.h)

@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--lib", default=None, help="experiments only: alternative build of libbatotp_cuda.so")
     return ap.parse_args()
 
 
@@ -234,7 +235,7 @@ def main_b200(args):
     n0 = theta.shape[2]
     h_theta = torch.from_numpy(theta).pin_memory()
     d_theta = h_theta.cuda()
-    ctx = native.Context(local)
+    ctx = native.Context(local, args.lib)
     ctx.set_chunk(args.chunk)
     peak_fma, peak_nofma = ctx.fp64_peak()
 

@@ -55,6 +55,10 @@ int batotp_cuda_timer(batotp_handle h, int which, double *elapsed_ms);
 /* measured FP64-pipe peak of the device in TFLOP/s: fused multiply-add chains, and separate
  * multiply + add chains (the ceiling of this library's -fmad=false kernels) */
 int batotp_cuda_fp64_peak(batotp_handle h, double *tflops_fma, double *tflops_nofma);
+/* device self-test: the kernels' shared-reciprocal division against the compiler's IEEE '/' on about n
+ * pseudo-random operand pairs; reports bitwise mismatches (must be 0) and how many took the fast path */
+int batotp_cuda_selftest_div(batotp_handle h, unsigned long long seed, long long n, long long *mismatches,
+                             long long *fast_path_taken);
 
 /* ---- batch input: what BA::loadTrajectoryData leaves in Traj (ba.cpp:2206-2461) -------- */
 typedef struct batotp_batch_in {
