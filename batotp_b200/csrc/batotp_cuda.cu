@@ -140,9 +140,12 @@ struct batotp_ctx {
   DevCfg cfg;
   bool haveCfg = false;
   Ws w;
-  int capB = 0, capNc = 0, capSc = 0, capOc = 0, capOs = 0, capOutC = 0, capR = 0, capRT = 0;
+  int capB = 0, capNc = 0, capSc = 0, capR = 0, capRT = 0;
   bool capTrq = false;
-  std::vector<void *> wsAllocs;
+  std::vector<void *> wsAllocs;   // chunk-resident arrays
+  int capBo = 0, capOc = 0, capOs = 0, capOutC = 0, capOSc = 0;
+  std::vector<void *> outAllocs;  // output sub-chunk arrays
+  int outChunk = 8192;            // trajectories per output pass
   // Thomas factor tables
   double *d_cN = nullptr, *d_cC = nullptr;
   int tabN = 0;
@@ -159,10 +162,12 @@ struct batotp_ctx {
   // staged outputs
   float *d_thetaOut = nullptr, *d_cartOut = nullptr, *d_trqOut = nullptr, *d_histOut = nullptr;
   double *d_cartOutD = nullptr;
-  double *d_outD = nullptr;  // [B][R+J][OutC] FP64 final rows (keepF64)
+  double *d_outD = nullptr;  // [Bo][R+J][OutC] FP64 final rows (keepF64)
+  double *o_mS = nullptr, *o_sOut = nullptr, *o_tauO = nullptr, *o_O5 = nullptr, *o_OA = nullptr, *o_OM = nullptr;
+  double *o_OD = nullptr, *o_OD2 = nullptr, *o_Trq = nullptr, *o_Trq2 = nullptr, *o_TrqM = nullptr;
+  int *o_segO = nullptr;
   bool keepF64 = false, capKeep = false;
   // which buffers hold the final rows after interp_output
-  const double *finSrc = nullptr, *finM = nullptr, *finTrq = nullptr, *finTrqM = nullptr;
   // high-water marks so that steady-state chunks need no planning sync
   int hwNc = 0, hwSc = 0;
   std::vector<TrajState> hst;
@@ -189,13 +194,13 @@ namespace {
       (h)->launches++;                                                                      \
     }                                                                                       \
   } while (0)
-// (trajectory, point) kernels: nblk blocks of 128 points per trajectory
-#define LAUNCH_TP(h, kern, npts, ...)                                                       \
+// (trajectory, point) kernels: npts x nb threads; the kernel receives (..., npts, nb) last
+#define LAUNCH_TP(h, kern, npts, nb, ...)                                                   \
   do {                                                                                      \
-    const int nblk_ = cdiv((npts), 128);                                                    \
-    if (nblk_ > 0 && (h)->B > 0) {                                                          \
-      BATOTP_LAUNCH(kern, dim3((unsigned)((size_t)nblk_ * (h)->B)), dim3(128), (h)->stream, \
-                    __VA_ARGS__, nblk_);                                                    \
+    const long long tot_ = (long long)(npts) * (long long)(nb);                             \
+    if (tot_ > 0) {                                                                         \
+      BATOTP_LAUNCH(kern, dim3((unsigned)((tot_ + 127) / 128)), dim3(128), (h)->stream,     \
+                    __VA_ARGS__, (int)(npts), (int)(nb));                                   \
       g_check_launch();                                                                     \
       (h)->launches++;                                                                      \
     }                                                                                       \
@@ -206,11 +211,22 @@ void free_ws(batotp_ctx *h) {
   h->wsAllocs.clear();
   h->capB = 0;
 }
+void free_out(batotp_ctx *h) {
+  for (void *p : h->outAllocs) g_free(p);
+  h->outAllocs.clear();
+  h->capBo = 0;
+}
 
 template <class T>
 T *ws_alloc(batotp_ctx *h, size_t count) {
   void *p = g_alloc(count * sizeof(T));
   h->wsAllocs.push_back(p);
+  return (T *)p;
+}
+template <class T>
+T *out_alloc(batotp_ctx *h, size_t count) {
+  void *p = g_alloc(count * sizeof(T));
+  h->outAllocs.push_back(p);
   return (T *)p;
 }
 
@@ -265,17 +281,16 @@ int final_cap(const batotp_ctx *h, int Sc, int Os) {
   return std::max(std::max(n, 16), Os);
 }
 
+// chunk-resident arrays (input phase + sweeps)
 void ensure_ws(batotp_ctx *h, int B, int Nc, int Sc) {
   const DevCfg &c = h->cfg;
-  const int Oc = oversample_cap(h, Sc);
   const bool trq = c.trqOn != 0;
-  int Os = Oc;
-  if (!trq && smooth_uniform_on(h)) Os = (int)(Oc / c.c.out_smooth_fact) + 16;
-  const int OutC = final_cap(h, Sc, Os);
-  if (B <= h->capB && Nc <= h->capNc && Sc <= h->capSc && Oc <= h->capOc && Os <= h->capOs &&
-      OutC <= h->capOutC && c.R == h->capR && c.RT == h->capRT && trq == h->capTrq && h->keepF64 == h->capKeep)
+  if (B <= h->capB && Nc <= h->capNc && Sc <= h->capSc && c.R == h->capR && c.RT == h->capRT && trq == h->capTrq) {
+    h->w.B = B;
     return;
+  }
   free_ws(h);
+  free_out(h);
   Ws &w = h->w;
   memset(&w, 0, sizeof(w));
   const size_t b = (size_t)B;
@@ -283,9 +298,6 @@ void ensure_ws(batotp_ctx *h, int B, int Nc, int Sc) {
   w.B = B;
   w.Nc = Nc;
   w.Sc = Sc;
-  w.Oc = Oc;
-  w.Os = Os;
-  w.OutC = OutC;
   w.R = R;
   w.RT = RT;
   w.P = ws_alloc<double>(h, b * R * Nc);
@@ -297,42 +309,82 @@ void ensure_ws(batotp_ctx *h, int B, int Nc, int Sc) {
   w.hist = ws_alloc<double>(h, b * 4 * Sc);
   w.flags = ws_alloc<unsigned char>(h, b * 2 * Sc);
   w.st = ws_alloc<TrajState>(h, b);
-  w.mS = ws_alloc<double>(h, b * Sc);
-  w.sOut = ws_alloc<double>(h, b * Oc);
-  w.segO = ws_alloc<int>(h, b * Oc);
-  w.tauO = ws_alloc<double>(h, b * Oc);
-  w.O5 = ws_alloc<double>(h, b * R * Oc);
-  w.OA = ws_alloc<double>(h, b * R * Os);
-  w.OM = ws_alloc<double>(h, b * R * Os);
   if (trq) {
-    w.OD = ws_alloc<double>(h, b * R * Oc);
-    w.OD2 = ws_alloc<double>(h, b * R * Oc);
-    w.Trq = ws_alloc<double>(h, b * MAXD * Oc);
-    w.Trq2 = ws_alloc<double>(h, b * MAXD * Oc);
-    w.TrqM = ws_alloc<double>(h, b * MAXD * Oc);
     w.A = ws_alloc<double>(h, b * 4 * MAXD * Nc);
     w.AM = ws_alloc<double>(h, b * 4 * MAXD * Nc);
     w.GD = ws_alloc<double>(h, b * R * Nc);
     w.GD2 = ws_alloc<double>(h, b * R * Nc);
+    g_zero(w.A, b * 4 * MAXD * Nc * sizeof(double), h->stream);
   }
   w.queue = ws_alloc<int>(h, 4);
-  h->d_thetaOut = ws_alloc<float>(h, b * c.J * OutC);
-  h->d_cartOut = ws_alloc<float>(h, b * std::max(c.Cin, 1) * OutC);
-  h->d_trqOut = trq ? ws_alloc<float>(h, b * c.J * OutC) : nullptr;
-  h->d_cartOutD = (c.C == 7) ? ws_alloc<double>(h, b * 7 * OutC) : nullptr;
-  h->d_histOut = ws_alloc<float>(h, b * 4 * Sc);
-  h->d_outD = h->keepF64 ? ws_alloc<double>(h, b * (R + c.J) * OutC) : nullptr;
-  h->capKeep = h->keepF64;
   h->capB = B;
   h->capNc = Nc;
   h->capSc = Sc;
-  h->capOc = Oc;
-  h->capOs = Os;
-  h->capOutC = OutC;
   h->capR = R;
   h->capRT = RT;
   h->capTrq = trq;
-  ensure_tabs(h, std::max(std::max(Nc, Sc), Oc) + 8);
+  ensure_tabs(h, std::max(Nc, Sc) + 8);
+}
+
+// output sub-chunk arrays, sized from the step capacity of the resident chunk
+void ensure_out(batotp_ctx *h, int Bo) {
+  const DevCfg &c = h->cfg;
+  Ws &w = h->w;
+  const int Sc = w.Sc;
+  const int Oc = oversample_cap(h, Sc);
+  const bool trq = c.trqOn != 0;
+  int Os = Oc;
+  if (!trq && smooth_uniform_on(h)) Os = (int)(Oc / c.c.out_smooth_fact) + 16;
+  const int OutC = final_cap(h, Sc, Os);
+  if (!(Bo <= h->capBo && Oc <= h->capOc && Os <= h->capOs && OutC <= h->capOutC && Sc == h->capOSc &&
+        h->keepF64 == h->capKeep)) {
+    free_out(h);
+    const size_t b = (size_t)Bo;
+    const int R = c.R;
+    h->o_mS = out_alloc<double>(h, b * Sc);
+    h->o_sOut = out_alloc<double>(h, b * Oc);
+    h->o_segO = out_alloc<int>(h, b * Oc);
+    h->o_tauO = out_alloc<double>(h, b * Oc);
+    h->o_O5 = out_alloc<double>(h, b * R * Oc);
+    h->o_OA = out_alloc<double>(h, b * R * Os);
+    h->o_OM = out_alloc<double>(h, b * R * Os);
+    h->o_OD = h->o_OD2 = h->o_Trq = h->o_Trq2 = h->o_TrqM = nullptr;
+    if (trq) {
+      h->o_OD = out_alloc<double>(h, b * R * Oc);
+      h->o_OD2 = out_alloc<double>(h, b * R * Oc);
+      h->o_Trq = out_alloc<double>(h, b * MAXD * Oc);
+      h->o_Trq2 = out_alloc<double>(h, b * MAXD * Oc);
+      h->o_TrqM = out_alloc<double>(h, b * MAXD * Oc);
+    }
+    h->d_thetaOut = out_alloc<float>(h, b * c.J * OutC);
+    h->d_cartOut = out_alloc<float>(h, b * std::max(c.Cin, 1) * OutC);
+    h->d_trqOut = trq ? out_alloc<float>(h, b * c.J * OutC) : nullptr;
+    h->d_cartOutD = (c.C == 7) ? out_alloc<double>(h, b * 7 * OutC) : nullptr;
+    h->d_histOut = out_alloc<float>(h, b * 4 * Sc);
+    h->d_outD = h->keepF64 ? out_alloc<double>(h, b * (R + c.J) * OutC) : nullptr;
+    h->capBo = Bo;
+    h->capOc = Oc;
+    h->capOs = Os;
+    h->capOutC = OutC;
+    h->capOSc = Sc;
+    h->capKeep = h->keepF64;
+    ensure_tabs(h, std::max(std::max(w.Nc, Sc), Oc) + 8);
+  }
+  w.Oc = h->capOc;
+  w.Os = h->capOs;
+  w.OutC = h->capOutC;
+  w.mS = h->o_mS;
+  w.sOut = h->o_sOut;
+  w.segO = h->o_segO;
+  w.tauO = h->o_tauO;
+  w.O5 = h->o_O5;
+  w.OA = h->o_OA;
+  w.OM = h->o_OM;
+  w.OD = h->o_OD;
+  w.OD2 = h->o_OD2;
+  w.Trq = h->o_Trq;
+  w.Trq2 = h->o_Trq2;
+  w.TrqM = h->o_TrqM;
 }
 
 void set_cfg(batotp_ctx *h, const batotp_cfg *cfg) {
@@ -392,54 +444,64 @@ int check_cfg(batotp_ctx *h) {
 
 // ---- strict-parity trig: the host evaluates the trig-bearing point functions with its libm,
 //      exactly as the reference does.  Rows travel D2H/H2D around the call.
-void host_rows_apply(batotp_ctx *h, double *base, int stride, bool over, int kind) {
+//      `base` is a point-major array [npts][nb][R]; b0 = chunk index of its first trajectory.
+void host_rows_apply(batotp_ctx *h, double *base, int npts, int nb, int b0, bool over, int kind) {
   // kind 1: fwdKin (theta rows -> cart rows); kind 2: aa2qVect on cart rows 3..6
   const DevCfg &c = h->cfg;
-  const int B = h->B, R = c.R, J = c.J;
-  std::vector<double> buf((size_t)B * R * stride);
+  const int R = c.R, J = c.J;
+  h->hst.resize(h->B);
+  g_d2h(h->hst.data(), h->w.st, (size_t)h->B * sizeof(TrajState), h->stream);
+  g_sync(h->stream);
+  int nmax = 0;
+  for (int bl = 0; bl < nb; ++bl) {
+    const TrajState &s = h->hst[b0 + bl];
+    if (s.status & ST_FATAL_MASK) continue;
+    nmax = std::max(nmax, over ? s.nOver : s.nPts);
+  }
+  nmax = std::min(nmax, npts);
+  if (nmax <= 0) return;
+  std::vector<double> buf((size_t)nmax * nb * R);
   g_d2h(buf.data(), base, buf.size() * sizeof(double), h->stream);
-  h->hst.resize(B);
-  g_d2h(h->hst.data(), h->w.st, (size_t)B * sizeof(TrajState), h->stream);
   g_sync(h->stream);
   const int nth = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+  const size_t pst = (size_t)nb * R;
   auto work = [&](int tid) {
-    for (int b = tid; b < B; b += nth) {
-      const TrajState &s = h->hst[b];
+    for (int bl = tid; bl < nb; bl += nth) {
+      const TrajState &s = h->hst[b0 + bl];
       if (s.status & ST_FATAL_MASK) continue;
-      const int n = over ? s.nOver : s.nPts;
-      double *r0 = buf.data() + (size_t)b * R * stride;
+      const int n = std::min(over ? s.nOver : s.nPts, nmax);
+      double *r0 = buf.data() + (size_t)bl * R;
       if (kind == 1) {
         for (int i = 0; i < n; ++i) {
-          double th[MAXD], xyz[3];
-          for (int j = 0; j < J; ++j) th[j] = r0[(size_t)j * stride + i];
+          double *p = r0 + (size_t)i * pst;
+          double xyz[3];
           if (c.c.robot_type == BATOTP_KUKA) {
-            fk_kuka_point(th, xyz);
-            for (int q = 0; q < 3; ++q) r0[(size_t)(J + q) * stride + i] = xyz[q];
+            fk_kuka_point(p, xyz);
+            for (int q = 0; q < 3; ++q) p[J + q] = xyz[q];
           } else if (c.c.robot_type == BATOTP_RR) {
-            fk_rr_point(th, xyz);
-            r0[(size_t)J * stride + i] = xyz[0];
-            r0[(size_t)(J + 1) * stride + i] = xyz[1];
+            fk_rr_point(p, xyz);
+            p[J] = xyz[0];
+            p[J + 1] = xyz[1];
           }
         }
       } else if (kind == 2) {
-        double *r3 = r0 + (size_t)(J + 3) * stride, *r4 = r0 + (size_t)(J + 4) * stride,
-               *r5 = r0 + (size_t)(J + 5) * stride, *r6 = r0 + (size_t)(J + 6) * stride;
-        double aa[3] = {r3[0], r4[0], r5[0]}, q[4], qprev[4];
+        double aa[3] = {r0[J + 3], r0[J + 4], r0[J + 5]}, q[4], qprev[4];
         aa2q_dev(aa, qprev);
         for (int i = 0; i < n; ++i) {
-          aa[0] = r3[i];
-          aa[1] = r4[i];
-          aa[2] = r5[i];
+          double *p = r0 + (size_t)i * pst;
+          aa[0] = p[J + 3];
+          aa[1] = p[J + 4];
+          aa[2] = p[J + 5];
           aa2q_dev(aa, q);
           double qdir = 0;
           for (int j = 0; j < 4; ++j) qdir += q[j] * qprev[j];
           if (qdir < 0.0)
             for (int j = 0; j < 4; ++j) q[j] = -q[j];
           for (int j = 0; j < 4; ++j) qprev[j] = q[j];
-          r3[i] = q[0];
-          r4[i] = q[1];
-          r5[i] = q[2];
-          r6[i] = q[3];
+          p[J + 3] = q[0];
+          p[J + 4] = q[1];
+          p[J + 5] = q[2];
+          p[J + 6] = q[3];
         }
       }
     }
@@ -448,9 +510,7 @@ void host_rows_apply(batotp_ctx *h, double *base, int stride, bool over, int kin
   for (int t = 1; t < nth; ++t) th.emplace_back(work, t);
   work(0);
   for (auto &x : th) x.join();
-  // only the Cartesian rows changed
-  g_h2d_2d(base + (size_t)J * stride, (size_t)R * stride * sizeof(double), buf.data() + (size_t)J * stride,
-           (size_t)R * stride * sizeof(double), (size_t)c.C * stride * sizeof(double), (size_t)B, h->stream);
+  g_h2d(base, buf.data(), buf.size() * sizeof(double), h->stream);
   g_sync(h->stream);
 }
 
@@ -460,7 +520,9 @@ void apply_kinematics(batotp_ctx *h, int where) {
   const int pt = c.c.path_type;
   const bool over = (where == 2);
   double *base = over ? h->w.O5 : h->w.P;
-  const int stride = over ? h->w.Oc : h->w.Nc;
+  const int npts = over ? h->w.Oc : h->w.Nc;
+  const int nb = over ? h->w.Bo : h->w.B;
+  const int b0 = over ? h->w.b0 : 0;
   int mode = 0;
   if (pt == BATOTP_JOINT) {
     if (where == 0)
@@ -477,16 +539,16 @@ void apply_kinematics(batotp_ctx *h, int where) {
   }
   if (mode == 0) return;
   if (mode == 1 && c.c.trig_mode == 1) {
-    host_rows_apply(h, base, stride, over, 1);
+    host_rows_apply(h, base, npts, nb, b0, over, 1);
     return;
   }
-  LAUNCH_TP(h, k_pointfn, stride, h->w, base, stride, mode, over ? 1 : 0, h->pm);
+  LAUNCH_TP(h, k_pointfn, npts, nb, h->w, base, b0, mode, over ? 1 : 0, h->pm);
 }
 
-void thomas_rows(batotp_ctx *h, const double *src, double *dst, int stride, int rows, int rowsPerTraj, int nsel,
+void thomas_rows(batotp_ctx *h, double *src, double *dst, int nb, int b0, int rows, int rowsPerTraj, int nsel,
                  int clamped) {
   ThomasTabs t{h->d_cN, h->d_cC};
-  LAUNCH_T(h, k_thomas_rows, h->B * rows, h->w, src, dst, stride, rows, rowsPerTraj, nsel, clamped, t);
+  LAUNCH_T(h, k_thomas_rows, nb * rows, h->w, src, dst, nb, b0, rows, rowsPerTraj, nsel, clamped, t);
 }
 
 template <int J, bool CART, bool TRQ>
@@ -596,15 +658,15 @@ void run_load_prepare(batotp_ctx *h, bool haveN0) {
   w.B = h->B;
   const int *n0 = haveN0 ? h->d_n0 : nullptr;
   if (h->inF64)
-    LAUNCH_TP(h, (k_in_load<double>), h->n0max, w, (const double *)h->in_theta, (const double *)h->in_cart, n0,
-              h->d_tres, h->n0max);
+    LAUNCH_TP(h, (k_in_load<double>), h->n0max, h->B, w, (const double *)h->in_theta, (const double *)h->in_cart, n0,
+              h->d_tres);
   else
-    LAUNCH_TP(h, (k_in_load<float>), h->n0max, w, (const float *)h->in_theta, (const float *)h->in_cart, n0,
-              h->d_tres, h->n0max);
+    LAUNCH_TP(h, (k_in_load<float>), h->n0max, h->B, w, (const float *)h->in_theta, (const float *)h->in_cart, n0,
+              h->d_tres);
   LAUNCH_T(h, k_in_prepare, h->B, w, h->in_ts, h->n0max, h->hasTheta ? 1 : 0, h->hasCart ? 1 : 0);
 }
 
-// returns max over trajectories of (nNew) after the special-pass plan, for capacity planning
+// returns max over trajectories of (nNew, nPts) for capacity planning
 int read_plan_max(batotp_ctx *h, int *anyGridCap) {
   h->hst.resize(h->B);
   g_d2h(h->hst.data(), h->w.st, (size_t)h->B * sizeof(TrajState), h->stream);
@@ -623,50 +685,51 @@ int read_plan_max(batotp_ctx *h, int *anyGridCap) {
 int do_interp_input(batotp_ctx *h, bool haveN0, bool planSync) {
   const DevCfg &c = h->cfg;
   Ws &w = h->w;
+  const int B = h->B;
   const bool adjust = !(c.c.s_weights[1] + c.c.s_weights[2] < 1e-8);  // ba.cpp:416
   run_load_prepare(h, haveN0);
   const int pt = c.c.path_type;
   if ((pt == BATOTP_CART || pt == BATOTP_BOTH) && c.Cin == 6) {  // ba.cpp:185-192
     if (c.c.trig_mode == 1)
-      host_rows_apply(h, w.P, w.Nc, false, 2);
+      host_rows_apply(h, w.P, w.Nc, B, 0, false, 2);
     else
-      LAUNCH_T(h, k_aa2q, h->B, w);
+      LAUNCH_T(h, k_aa2q, B, w);
   }
   if (c.c.input_decim_fact > 1 || c.c.smooth_window > 1) {
-    LAUNCH_T(h, k_in_smooth_decimate, h->B * c.R, w);
-    LAUNCH_T(h, k_in_decim_fix, h->B, w);
+    LAUNCH_T(h, k_in_smooth_decimate, B * c.R, w);
+    LAUNCH_T(h, k_in_decim_fix, B, w);
   }
   apply_kinematics(h, 0);
   if (adjust) {
-    LAUNCH_T(h, k_adjust_s, h->B, w, 1);
+    LAUNCH_T(h, k_adjust_s, B, w, 1);
     if (planSync) {
       const int mx = read_plan_max(h, nullptr);
       const int need = (int)(mx * 1.125) + 64;
       if (need > w.Nc) return need;  // caller grows the workspace and restarts the chunk
     }
-    thomas_rows(h, w.P, w.M, w.Nc, c.R, c.R, 0, 0);
-    LAUNCH_T(h, k_march, h->B, w);
+    thomas_rows(h, w.P, w.M, B, 0, c.R, c.R, 0, 0);
+    LAUNCH_T(h, k_march, B, w);
     std::swap(w.P, w.Q);
     apply_kinematics(h, 1);
-    LAUNCH_T(h, k_adjust_s, h->B, w, 0);
-    thomas_rows(h, w.P, w.M, w.Nc, c.R, c.R, 0, 0);
-    LAUNCH_TP(h, k_resample, w.Nc, w);
-    LAUNCH_T(h, k_resample_commit, h->B, w);
+    LAUNCH_T(h, k_adjust_s, B, w, 0);
+    thomas_rows(h, w.P, w.M, B, 0, c.R, c.R, 0, 0);
+    LAUNCH_TP(h, k_resample, w.Nc, B, w);
+    LAUNCH_T(h, k_resample_commit, B, w);
     std::swap(w.P, w.Q);
     apply_kinematics(h, 1);
   }
   // ba.cpp:297-305: final splines on the uniform grid, then the dynamic model
-  thomas_rows(h, w.P, w.M, w.Nc, c.R, c.R, 0, 0);
-  LAUNCH_T(h, k_final_plan, h->B, w);
+  thomas_rows(h, w.P, w.M, B, 0, c.R, c.R, 0, 0);
+  LAUNCH_T(h, k_final_plan, B, w);
   if (c.trqOn) {
-    LAUNCH_TP(h, k_eval_grid, w.Nc, w, w.GD, w.GD2);
+    LAUNCH_TP(h, k_eval_grid, w.Nc, B, w);
     if (!c.c.is_parallel && c.c.trig_mode == 1)
       host_dyn_rr_grid(h);
     else
-      LAUNCH_TP(h, k_dyn_grid, w.Nc, w, h->pm);
-    thomas_rows(h, w.A, w.AM, w.Nc, 4 * MAXD, 4 * MAXD, 0, 0);
+      LAUNCH_TP(h, k_dyn_grid, w.Nc, B, w, h->pm);
+    thomas_rows(h, w.A, w.AM, B, 0, 4 * MAXD, 4 * MAXD, 0, 0);
   }
-  LAUNCH_TP(h, k_build_table, w.Nc, w, w.A, w.AM);
+  LAUNCH_TP(h, k_build_table, w.Nc, B, w);
   h->phase = 2;
   return 0;
 }
@@ -677,53 +740,53 @@ int do_sweeps(batotp_ctx *h) {
   return 0;
 }
 
-void do_interp_output(batotp_ctx *h) {
+// interpOutputData for the sub-chunk [b0, b0+Bo) of the resident chunk
+void do_interp_output(batotp_ctx *h, int b0, int Bo) {
   const DevCfg &c = h->cfg;
+  ensure_out(h, std::max(Bo, h->capBo));
   Ws &w = h->w;
+  w.b0 = b0;
+  w.Bo = Bo;
   ThomasTabs t{h->d_cN, h->d_cC};
-  LAUNCH_T(h, k_out_plan, h->B, w, t);
-  LAUNCH_TP(h, k_out_s, w.Oc, w);
-  LAUNCH_T(h, k_out_segs, h->B, w);
-  LAUNCH_TP(h, k_out_eval, w.Oc, w);
+  LAUNCH_T(h, k_out_plan, Bo, w, t);
+  LAUNCH_TP(h, k_out_s, w.Oc, Bo, w);
+  LAUNCH_T(h, k_out_segs, Bo, w);
+  LAUNCH_TP(h, k_out_eval, w.Oc, Bo, w);
   apply_kinematics(h, 2);
-  const double *cur = w.O5;
-  int curStride = w.Oc;
+  double *cur = w.O5;
+  int curCap = w.Oc;
   if (c.trqOn) {
     // re-spline theta(t) (and cart(t) for the parallel robot) to get time derivatives
-    thomas_rows(h, w.O5, w.OM, w.Oc, c.c.is_parallel ? c.R : c.J, c.R, 1, c.c.is_parallel ? 0 : 1);
-    LAUNCH_TP(h, k_out_knot_eval, w.Oc, w);
+    thomas_rows(h, w.O5, w.OM, Bo, b0, c.c.is_parallel ? c.R : c.J, c.R, 1, c.c.is_parallel ? 0 : 1);
+    LAUNCH_TP(h, k_out_knot_eval, w.Oc, Bo, w);
     if (!c.c.is_parallel && c.c.trig_mode == 1)
       host_dyn_rr_out(h);
     else
-      LAUNCH_TP(h, k_out_trq, w.Oc, w, h->pm);
+      LAUNCH_TP(h, k_out_trq, w.Oc, Bo, w, h->pm);
     cur = w.OA;
   }
-  LAUNCH_T(h, k_out_smooth_plan, h->B, w);
-  const double *trqCur = w.Trq;
+  LAUNCH_T(h, k_out_smooth_plan, Bo, w);
+  double *trqCur = w.Trq;
   if (smooth_uniform_on(h) || c.c.is_auto_integ_res) {
     double *dst = (cur == w.O5) ? w.OA : w.O5;
-    const int dstStride = (cur == w.O5) ? w.Os : w.Oc;
-    LAUNCH_TP(h, k_out_smooth, std::min(curStride, dstStride), w, cur, curStride, dst, dstStride);
+    const int dstCap = (cur == w.O5) ? w.Os : w.Oc;
+    LAUNCH_TP(h, k_out_smooth, std::min(curCap, dstCap), Bo, w, cur, dst);
     cur = dst;
-    curStride = dstStride;
+    curCap = dstCap;
     trqCur = w.Trq2;
   }
-  LAUNCH_T(h, k_out_final_plan, h->B, w);
+  LAUNCH_T(h, k_out_final_plan, Bo, w);
   // natural splines of the rows for the final resample (ba.cpp:1889-1915; used where isReinterp).
-  // OM shares the pitch of `cur` by construction (Os == Oc whenever cur can be O5 here).
+  // OM has at least the capacity of `cur` by construction (Os == Oc whenever cur can be O5 here).
   const bool needRe = (c.c.out_res < c.c.integ_res) || c.c.is_auto_integ_res;
   if (needRe) {
-    thomas_rows(h, cur, w.OM, curStride, c.R, c.R, 2, 0);
-    if (c.trqOn) thomas_rows(h, trqCur, w.TrqM, w.Oc, c.J, MAXD, 2, 0);
+    thomas_rows(h, cur, w.OM, Bo, b0, c.R, c.R, 2, 0);
+    if (c.trqOn) thomas_rows(h, trqCur, w.TrqM, Bo, b0, c.J, MAXD, 2, 0);
   }
-  h->finSrc = cur;
-  h->finM = w.OM;
-  h->finTrq = trqCur;
-  h->finTrqM = w.TrqM;
   const bool strictQuat = (c.C == 7 && c.c.trig_mode == 1);
-  LAUNCH_TP(h, k_out_pack, w.OutC, w, cur, (const double *)w.OM, curStride, trqCur, (const double *)w.TrqM,
-            h->d_thetaOut, h->d_cartOut, h->d_trqOut, strictQuat ? h->d_cartOutD : (double *)nullptr, h->d_outD);
-  LAUNCH_TP(h, k_pack_hist, w.Sc, w, h->d_histOut);
+  LAUNCH_TP(h, k_out_pack, w.OutC, Bo, w, cur, w.OM, trqCur, w.TrqM, h->d_thetaOut, h->d_cartOut, h->d_trqOut,
+            strictQuat ? h->d_cartOutD : (double *)nullptr, h->d_outD);
+  LAUNCH_TP(h, k_pack_hist, w.Sc, Bo, w, h->d_histOut);
   h->phase = 4;
 }
 
@@ -849,6 +912,7 @@ int batotp_cuda_create(int device, batotp_handle *out) {
 int batotp_cuda_destroy(batotp_handle h) {
   if (!h) return -1;
   free_ws(h);
+  free_out(h);
   g_free(h->d_cN);
   g_free(h->d_cC);
   g_free(h->d_theta);
@@ -1028,7 +1092,7 @@ static int load_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_batch
 // one chunk through interpInputData with capacity planning / retry
 static int chunk_interp_input(batotp_handle h, bool haveN0) {
   int Nc = std::max(h->hwNc, h->n0max + 8);
-  int Sc = std::max(h->hwSc, 1024);
+  int Sc = std::max(h->hwSc, std::max(1024, 2 * Nc));
   bool plan = (h->hwNc == 0);
   for (int attempt = 0; attempt < 8; ++attempt) {
     ensure_ws(h, std::max(h->B, h->capB), Nc, Sc);
@@ -1128,7 +1192,8 @@ int batotp_cuda_sweeps(batotp_handle h) {
 int batotp_cuda_interp_output(batotp_handle h) {
   if (!h || h->phase < 3) return -1;
   try {
-    do_interp_output(h);
+    if (h->B > h->outChunk) h->outChunk = h->B;  // the phase-wise API keeps one sub-chunk resident
+    do_interp_output(h, 0, h->B);
     g_sync(h->stream);
     return 0;
   } catch (const Err &e) {
@@ -1137,17 +1202,19 @@ int batotp_cuda_interp_output(batotp_handle h) {
   }
 }
 
-static void fetch_chunk(batotp_handle h, batotp_batch_out *out, int first) {
+// copy the results of the current output sub-chunk [w.b0, w.b0+w.Bo) to the caller's buffers;
+// `first` = index of the resident chunk's first trajectory in the caller's batch
+static void fetch_sub(batotp_handle h, batotp_batch_out *out, int first) {
   const DevCfg &c = h->cfg;
   const Ws &w = h->w;
-  const int B = h->B;
-  h->hst.resize(B);
-  g_d2h(h->hst.data(), w.st, (size_t)B * sizeof(TrajState), h->stream);
+  const int Bo = w.Bo, g0 = first + w.b0;
+  h->hst.resize(h->B);
+  g_d2h(h->hst.data() + w.b0, w.st + w.b0, (size_t)Bo * sizeof(TrajState), h->stream);
   g_sync(h->stream);
   if (out->on_device) throw Err{"batotp_batch_out.on_device is not implemented yet"};
-  for (int b = 0; b < B; ++b) {
-    const TrajState &s = h->hst[b];
-    const int g = first + b;
+  for (int bl = 0; bl < Bo; ++bl) {
+    const TrajState &s = h->hst[w.b0 + bl];
+    const int g = g0 + bl;
     if (out->status) out->status[g] = s.status;
     if (out->n_rev) out->n_rev[g] = s.nRev;
     if (out->n_fwd) out->n_fwd[g] = s.nFwd;
@@ -1161,33 +1228,33 @@ static void fetch_chunk(batotp_handle h, batotp_batch_out *out, int first) {
   }
   const int oc = out->out_cap, wc = std::min(out->out_cap, w.OutC);
   if (out->theta_out && oc > 0)
-    g_d2h_2d(out->theta_out + (size_t)first * c.J * oc, (size_t)oc * 4, h->d_thetaOut, (size_t)w.OutC * 4,
-             (size_t)wc * 4, (size_t)B * c.J, h->stream);
+    g_d2h_2d(out->theta_out + (size_t)g0 * c.J * oc, (size_t)oc * 4, h->d_thetaOut, (size_t)w.OutC * 4,
+             (size_t)wc * 4, (size_t)Bo * c.J, h->stream);
   if (out->trq_out && oc > 0 && c.trqOn)
-    g_d2h_2d(out->trq_out + (size_t)first * c.J * oc, (size_t)oc * 4, h->d_trqOut, (size_t)w.OutC * 4,
-             (size_t)wc * 4, (size_t)B * c.J, h->stream);
+    g_d2h_2d(out->trq_out + (size_t)g0 * c.J * oc, (size_t)oc * 4, h->d_trqOut, (size_t)w.OutC * 4,
+             (size_t)wc * 4, (size_t)Bo * c.J, h->stream);
   if (out->cart_out && oc > 0 && c.Cin > 0) {
     if (c.C == 7 && c.c.trig_mode == 1) {
-      host_q2aa_out(h, out, first);
+      host_q2aa_out(h, out, g0);
     } else {
-      g_d2h_2d(out->cart_out + (size_t)first * c.Cin * oc, (size_t)oc * 4, h->d_cartOut, (size_t)w.OutC * 4,
-               (size_t)wc * 4, (size_t)B * c.Cin, h->stream);
+      g_d2h_2d(out->cart_out + (size_t)g0 * c.Cin * oc, (size_t)oc * 4, h->d_cartOut, (size_t)w.OutC * 4,
+               (size_t)wc * 4, (size_t)Bo * c.Cin, h->stream);
     }
   }
   const int hc = out->hist_cap, hw = std::min(out->hist_cap, w.Sc);
   if (out->hist && hc > 0)
-    g_d2h_2d(out->hist + (size_t)first * 4 * hc, (size_t)hc * 4, h->d_histOut, (size_t)w.Sc * 4, (size_t)hw * 4,
-             (size_t)B * 4, h->stream);
+    g_d2h_2d(out->hist + (size_t)g0 * 4 * hc, (size_t)hc * 4, h->d_histOut, (size_t)w.Sc * 4, (size_t)hw * 4,
+             (size_t)Bo * 4, h->stream);
   if (out->flags && hc > 0)
-    g_d2h_2d(out->flags + (size_t)first * 2 * hc, (size_t)hc, w.flags, (size_t)w.Sc, (size_t)hw, (size_t)B * 2,
-             h->stream);
+    g_d2h_2d(out->flags + (size_t)g0 * 2 * hc, (size_t)hc, w.flags + (size_t)w.b0 * 2 * w.Sc, (size_t)w.Sc,
+             (size_t)hw, (size_t)Bo * 2, h->stream);
   g_sync(h->stream);
 }
 
 int batotp_cuda_fetch(batotp_handle h, batotp_batch_out *out) {
   if (!h || !out || h->phase < 4) return -1;
   try {
-    fetch_chunk(h, out, 0);
+    fetch_sub(h, out, 0);
     return 0;
   } catch (const Err &e) {
     h->err = e.msg;
@@ -1207,8 +1274,10 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
       h->lastHaveN0 = in->n0 != nullptr;
       if (chunk_interp_input(h, h->lastHaveN0) != 0) return -1;
       if (chunk_sweeps_output(h, h->lastHaveN0) != 0) return -1;
-      do_interp_output(h);
-      fetch_chunk(h, out, at);
+      for (int b0 = 0; b0 < B; b0 += h->outChunk) {
+        do_interp_output(h, b0, std::min(h->outChunk, B - b0));
+        fetch_sub(h, out, at);
+      }
     }
     return 0;
   } catch (const Err &e) {
@@ -1237,24 +1306,27 @@ int batotp_cuda_get_f64(batotp_handle h, const char *name, int traj, int row, do
     g_sync(h->stream);
     const std::string n(name);
     const double *src = nullptr;
+    size_t stride = 1;  // in doubles
     int len = 0;
-    auto prow = [&](const double *base, int r) { return base + ((size_t)traj * c.R + r) * w.Nc; };
-    auto arow = [&](const double *base, int k, int r) { return base + (((size_t)traj * 4 + k) * MAXD + r) * w.Nc; };
-    if (n == "thetaC_y") { src = prow(w.P, row); len = s.nPtsC; }
-    else if (n == "thetaC_m") { src = prow(w.M, row); len = s.nPtsC; }
-    else if (n == "cartC_y") { src = prow(w.P, c.J + row); len = s.nPtsC; }
-    else if (n == "cartC_m") { src = prow(w.M, c.J + row); len = s.nPtsC; }
-    else if (n == "theta" && c.trqOn) { src = prow(w.Q, row); len = s.nPts; }
-    else if (n == "cart" && c.trqOn) { src = prow(w.Q, c.J + row); len = s.nPts; }
-    else if (n.size() == 2 && n[0] == 'a' && n[1] >= '1' && n[1] <= '4' && c.trqOn) { src = arow(w.A, n[1] - '1', row); len = s.nPts; }
-    else if (n.size() == 5 && n[0] == 'a' && n.substr(2) == "C_m" && c.trqOn) { src = arow(w.AM, n[1] - '1', row); len = s.nPts; }
+    const size_t pst = (size_t)w.B * c.R, ast = (size_t)w.B * 4 * MAXD;
+    auto prow = [&](const double *base, int r) { return base + (size_t)traj * c.R + r; };
+    auto arow = [&](const double *base, int k, int r) { return base + (size_t)traj * 4 * MAXD + (size_t)k * MAXD + r; };
+    if (n == "thetaC_y") { src = prow(w.P, row); stride = pst; len = s.nPtsC; }
+    else if (n == "thetaC_m") { src = prow(w.M, row); stride = pst; len = s.nPtsC; }
+    else if (n == "cartC_y") { src = prow(w.P, c.J + row); stride = pst; len = s.nPtsC; }
+    else if (n == "cartC_m") { src = prow(w.M, c.J + row); stride = pst; len = s.nPtsC; }
+    else if (n == "theta" && c.trqOn) { src = prow(w.Q, row); stride = pst; len = s.nPts; }
+    else if (n == "cart" && c.trqOn) { src = prow(w.Q, c.J + row); stride = pst; len = s.nPts; }
+    else if (n.size() == 2 && n[0] == 'a' && n[1] >= '1' && n[1] <= '4' && c.trqOn) { src = arow(w.A, n[1] - '1', row); stride = ast; len = s.nPts; }
+    else if (n.size() == 5 && n[0] == 'a' && n.substr(2) == "C_m" && c.trqOn) { src = arow(w.AM, n[1] - '1', row); stride = ast; len = s.nPts; }
     else if (h->phase >= 3 && n == "s_rev") { src = w.hist + (size_t)traj * 4 * w.Sc + (w.Sc - s.nRev); len = s.nRev; }
     else if (h->phase >= 3 && n == "sdot_rev") { src = w.hist + (size_t)traj * 4 * w.Sc + w.Sc + (w.Sc - s.nRev); len = s.nRev; }
     else if (h->phase >= 3 && n == "s_fwd") { src = w.hist + (size_t)traj * 4 * w.Sc + 2 * (size_t)w.Sc; len = s.nFwd; }
     else if (h->phase >= 3 && n == "sdot_fwd") { src = w.hist + (size_t)traj * 4 * w.Sc + 3 * (size_t)w.Sc; len = s.nFwd; }
-    else if (h->phase >= 4 && h->d_outD && (n == "theta_out" || n == "cart_out" || n == "trq_out")) {
-      const int rows = c.R + c.J;
-      auto orow_ = [&](int r) { return h->d_outD + ((size_t)traj * rows + r) * w.OutC; };
+    else if (h->phase >= 4 && h->d_outD && traj >= w.b0 && traj < w.b0 + w.Bo &&
+             (n == "theta_out" || n == "cart_out" || n == "trq_out")) {
+      const int rows = c.R + c.J, bl = traj - w.b0;
+      auto orow_ = [&](int r) { return h->d_outD + ((size_t)bl * rows + r) * w.OutC; };
       if (n == "theta_out") { src = orow_(row); len = s.nOut; }
       else if (n == "trq_out") { src = orow_(c.R + row); len = s.nOut; }
       else {
@@ -1279,7 +1351,10 @@ int batotp_cuda_get_f64(batotp_handle h, const char *name, int traj, int row, do
     if (s.status & ST_FATAL_MASK) return 0;
     const int m = std::min(len, cap);
     if (buf && m > 0) {
-      g_d2h(buf, src, (size_t)m * sizeof(double), h->stream);
+      if (stride == 1)
+        g_d2h(buf, src, (size_t)m * sizeof(double), h->stream);
+      else
+        g_d2h_2d(buf, sizeof(double), src, stride * sizeof(double), sizeof(double), (size_t)m, h->stream);
       g_sync(h->stream);
     }
     return len;
@@ -1287,6 +1362,12 @@ int batotp_cuda_get_f64(batotp_handle h, const char *name, int traj, int row, do
     h->err = e.msg;
     return -1;
   }
+}
+
+int batotp_cuda_set_out_chunk(batotp_handle h, int n) {
+  if (!h || n < 1) return -1;
+  h->outChunk = n;
+  return 0;
 }
 
 }  // extern "C"

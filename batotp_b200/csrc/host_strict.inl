@@ -9,62 +9,67 @@
 // device.  trig_mode == 0 keeps these on the device (CUDA sincos) for throughput.
 namespace {
 
-// dynRR on the final grid (findDynModel, ba.cpp:905-914): Q/GD/GD2 rows -> A rows
+// dynRR on the final grid (findDynModel, ba.cpp:905-914): Q/GD/GD2 rows -> A rows (point-major)
 void host_dyn_rr_grid(batotp_ctx *h) {
   const DevCfg &c = h->cfg;
   const Ws &w = h->w;
-  const int B = h->B, R = c.R, Nc = w.Nc;
-  std::vector<double> q((size_t)B * R * Nc), d1(q.size()), d2(q.size()), A((size_t)B * 4 * MAXD * Nc, 0.0);
-  g_d2h(q.data(), w.Q, q.size() * 8, h->stream);
-  g_d2h(d1.data(), w.GD, q.size() * 8, h->stream);
-  g_d2h(d2.data(), w.GD2, q.size() * 8, h->stream);
+  const int B = h->B, R = c.R;
   h->hst.resize(B);
   g_d2h(h->hst.data(), w.st, (size_t)B * sizeof(TrajState), h->stream);
+  g_sync(h->stream);
+  int nmax = 0;
+  for (int b = 0; b < B; ++b)
+    if (!(h->hst[b].status & ST_FATAL_MASK)) nmax = std::max(nmax, h->hst[b].nPts);
+  if (nmax <= 0) return;
+  const size_t cnt = (size_t)nmax * B * R;
+  std::vector<double> q(cnt), d1(cnt), d2(cnt), A((size_t)nmax * B * 4 * MAXD, 0.0);
+  g_d2h(q.data(), w.Q, cnt * 8, h->stream);
+  g_d2h(d1.data(), w.GD, cnt * 8, h->stream);
+  g_d2h(d2.data(), w.GD2, cnt * 8, h->stream);
   g_sync(h->stream);
   for (int b = 0; b < B; ++b) {
     const TrajState &s = h->hst[b];
     if (s.status & ST_FATAL_MASK) continue;
     for (int i = 0; i < s.nPts; ++i) {
-      double th[2], v1[2], v2[2], a1[2], a2[2], a3[2], a4[2];
-      for (int k = 0; k < 2; ++k) {
-        th[k] = q[((size_t)b * R + k) * Nc + i];
-        v1[k] = d1[((size_t)b * R + k) * Nc + i];
-        v2[k] = d2[((size_t)b * R + k) * Nc + i];
-      }
-      dyn_rr_point(th, v1, v2, a1, a2, a3, a4);
+      const size_t off = ((size_t)i * B + b) * R;
+      double a1[2], a2[2], a3[2], a4[2];
+      dyn_rr_point(&q[off], &d1[off], &d2[off], a1, a2, a3, a4);
       const double *aa[4] = {a1, a2, a3, a4};
+      double *Ab = &A[((size_t)i * B + b) * 4 * MAXD];
       for (int k = 0; k < 4; ++k)
-        for (int j = 0; j < 2; ++j) A[(((size_t)b * 4 + k) * MAXD + j) * Nc + i] = aa[k][j];
+        for (int j = 0; j < 2; ++j) Ab[k * MAXD + j] = aa[k][j];
     }
   }
   g_h2d(w.A, A.data(), A.size() * 8, h->stream);
   g_sync(h->stream);
 }
 
-// dynRR at the output sites (ba.cpp:1815-1825): OA/OD/OD2 rows -> Trq rows
+// dynRR at the output sites (ba.cpp:1815-1825): OA/OD/OD2 rows -> Trq rows (sub-chunk, point-major)
 void host_dyn_rr_out(batotp_ctx *h) {
   const DevCfg &c = h->cfg;
   const Ws &w = h->w;
-  const int B = h->B, R = c.R, Oc = w.Oc;
-  std::vector<double> q((size_t)B * R * Oc), d1(q.size()), d2(q.size()), T((size_t)B * MAXD * Oc, 0.0);
-  g_d2h(q.data(), w.OA, q.size() * 8, h->stream);
-  g_d2h(d1.data(), w.OD, q.size() * 8, h->stream);
-  g_d2h(d2.data(), w.OD2, q.size() * 8, h->stream);
-  h->hst.resize(B);
-  g_d2h(h->hst.data(), w.st, (size_t)B * sizeof(TrajState), h->stream);
+  const int Bo = w.Bo, b0 = w.b0, R = c.R;
+  h->hst.resize(h->B);
+  g_d2h(h->hst.data(), w.st, (size_t)h->B * sizeof(TrajState), h->stream);
   g_sync(h->stream);
-  for (int b = 0; b < B; ++b) {
-    const TrajState &s = h->hst[b];
+  int nmax = 0;
+  for (int bl = 0; bl < Bo; ++bl)
+    if (!(h->hst[b0 + bl].status & ST_FATAL_MASK)) nmax = std::max(nmax, h->hst[b0 + bl].nOver);
+  if (nmax <= 0) return;
+  const size_t cnt = (size_t)nmax * Bo * R;
+  std::vector<double> q(cnt), d1(cnt), d2(cnt), T((size_t)nmax * Bo * MAXD, 0.0);
+  g_d2h(q.data(), w.OA, cnt * 8, h->stream);
+  g_d2h(d1.data(), w.OD, cnt * 8, h->stream);
+  g_d2h(d2.data(), w.OD2, cnt * 8, h->stream);
+  g_sync(h->stream);
+  for (int bl = 0; bl < Bo; ++bl) {
+    const TrajState &s = h->hst[b0 + bl];
     if (s.status & ST_FATAL_MASK) continue;
     for (int i = 0; i < s.nOver; ++i) {
-      double th[2], v1[2], v2[2], a1[2], a2[2], a3[2], a4[2];
-      for (int k = 0; k < 2; ++k) {
-        th[k] = q[((size_t)b * R + k) * Oc + i];
-        v1[k] = d1[((size_t)b * R + k) * Oc + i];
-        v2[k] = d2[((size_t)b * R + k) * Oc + i];
-      }
-      dyn_rr_point(th, v1, v2, a1, a2, a3, a4);
-      for (int j = 0; j < 2; ++j) T[((size_t)b * MAXD + j) * Oc + i] = a2[j] + a3[j] + a4[j];
+      const size_t off = ((size_t)i * Bo + bl) * R;
+      double a1[2], a2[2], a3[2], a4[2];
+      dyn_rr_point(&q[off], &d1[off], &d2[off], a1, a2, a3, a4);
+      for (int j = 0; j < 2; ++j) T[((size_t)i * Bo + bl) * MAXD + j] = a2[j] + a3[j] + a4[j];
     }
   }
   g_h2d(w.Trq, T.data(), T.size() * 8, h->stream);
@@ -73,13 +78,14 @@ void host_dyn_rr_out(batotp_ctx *h) {
 
 // q2aaVect on the final Cartesian rows (ba.cpp:382-403, 1922-1929) and the float cast
 void host_q2aa_out(batotp_ctx *h, batotp_batch_out *out, int first) {
+  // `first` = global index of the sub-chunk's first trajectory; h->hst holds the chunk's states
   const Ws &w = h->w;
-  const int B = h->B, OutC = w.OutC, oc = out->out_cap;
+  const int B = w.Bo, OutC = w.OutC, oc = out->out_cap;
   std::vector<double> q((size_t)B * 7 * OutC);
   g_d2h(q.data(), h->d_cartOutD, q.size() * 8, h->stream);
   g_sync(h->stream);
   for (int b = 0; b < B; ++b) {
-    const TrajState &s = h->hst[b];
+    const TrajState &s = h->hst[w.b0 + b];
     if (s.status & ST_FATAL_MASK) continue;
     float *o = out->cart_out + (size_t)(first + b) * 6 * oc;
     for (int i = 0; i < s.nCartOut && i < oc; ++i) {
@@ -94,7 +100,7 @@ void host_q2aa_out(batotp_ctx *h, batotp_batch_out *out, int first) {
 
 template <int J, bool CART, bool TRQ>
 void launch_mvc(batotp_ctx *h, double sdotStart, double *d_out, int cap) {
-  LAUNCH_TP(h, (k_mvc<J, CART, TRQ>), h->w.Nc, h->w, sdotStart, d_out, cap);
+  LAUNCH_TP(h, (k_mvc<J, CART, TRQ>), h->w.Nc, h->B, h->w, sdotStart, d_out, cap);
 }
 
 int run_mvc_per_sample(batotp_ctx *h, double sdotStart, double *sdot_out, int cap) {

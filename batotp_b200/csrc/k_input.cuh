@@ -3,7 +3,8 @@
 //
 // Kernel shapes:  T  = one thread per trajectory (strictly sequential walkers)
 //                 TR = one thread per (trajectory, coordinate row) (Thomas recurrences)
-//                 TP = one thread per (trajectory, point) (pointwise evaluation, coalesced)
+//                 TP = one thread per (trajectory, point), trajectories fastest (pointwise evaluation)
+// All row arrays are point-major [point][trajectory][row] (ba_dev.cuh), accessed through RV views.
 #pragma once
 #include "ba_dev.cuh"
 
@@ -17,43 +18,74 @@ struct ThomasTabs {
 };
 
 // spline.cpp:168-211 + 252-276: y[n] -> second-derivative solution m[n] ("natural", quirk Q4)
-__host__ __device__ inline void thomas_natural(const double *y, double *m, int npts, const double *cN) {
+template <class VY, class VM>
+__host__ __device__ inline void thomas_natural(const VY &y, const VM &m, int npts, const double *cN) {
   const int n = npts - 1;
   m[0] = 0.0;
   m[npts - 1] = 0.0;
-  for (int i = 1; i < npts - 1; ++i) m[i] = 6 * (y[i - 1] - 2 * y[i] + y[i + 1]);
   const double a = 1.0, b = 4.0;
-  m[1] /= b;
-  for (int i = 2; i < n; ++i) m[i] = (m[i] - a * m[i - 1]) / (b - a * cN[i - 1]);
-  m[n] = (m[n] - a * m[n - 1]) / (b - a * cN[n - 1]);
-  for (int i = n; i > 1; --i) m[i - 1] -= cN[i - 1] * m[i];
+  // rhs and forward elimination in one pass (each m[i] depends on y[i-1..i+1] and m[i-1] only)
+  double ym = y[0], yc = y[1], prev = 0.0;
+  for (int i = 1; i < npts - 1; ++i) {
+    const double yp = y[i + 1];
+    double v = 6 * (ym - 2 * yc + yp);
+    if (i == 1)
+      v /= b;
+    else
+      v = (v - a * prev) / (b - a * cN[i - 1]);
+    m[i] = v;
+    prev = v;
+    ym = yc;
+    yc = yp;
+  }
+  double last = (0.0 - a * prev) / (b - a * cN[n - 1]);  // the last unknown is an ordinary row with rhs 0
+  m[n] = last;
+  for (int i = n; i > 1; --i) {
+    const double v = m[i - 1] - cN[i - 1] * last;
+    m[i - 1] = v;
+    last = v;
+  }
 }
 
 // spline.cpp:225-243 ("clamped": b0=b_{n-1}=2, back-substitution starts at n-3, quirk Q4)
-__host__ __device__ inline void thomas_clamped(const double *y, double *m, int n, const double *cC) {
-  m[0] = 0.0;
-  m[n - 1] = 0.0;
-  for (int i = 1; i < n - 1; ++i) m[i] = 6 * (y[i - 1] - 2 * y[i] + y[i + 1]);
+template <class VY, class VM>
+__host__ __device__ inline void thomas_clamped(const VY &y, const VM &m, int n, const double *cC) {
   const double a = 1.0;
-  m[0] /= 2.0;
+  double prev = 0.0 / 2.0;
+  m[0] = prev;
+  double ym = y[0], yc = y[1];
   for (int i = 1; i < n; ++i) {
+    double rhs = 0.0;
+    if (i < n - 1) {
+      const double yp = y[i + 1];
+      rhs = 6 * (ym - 2 * yc + yp);
+      ym = yc;
+      yc = yp;
+    }
     const double bi = (i == n - 1) ? 2.0 : 4.0;
-    m[i] = (m[i] - a * m[i - 1]) / (bi - a * cC[i - 1]);
+    const double v = (rhs - a * prev) / (bi - a * cC[i - 1]);
+    m[i] = v;
+    prev = v;
   }
-  for (int i = n - 2; i-- > 0;) m[i] -= cC[i] * m[i + 1];
+  for (int i = n - 2; i-- > 0;) m[i] = m[i] - cC[i] * m[i + 1];
 }
 
 // spline.cpp:203-209: coefficients of segment k from knot values and the solution
 struct Seg4 {
   double c0, c1, c2, c3;
 };
-__host__ __device__ __forceinline__ Seg4 seg_coef(const double *y, const double *m, int k) {
+template <class VY, class VM>
+__host__ __device__ __forceinline__ Seg4 seg_coef(const VY &y, const VM &m, int k) {
   Seg4 s;
-  s.c3 = (m[k + 1] - m[k]) / 6.0;
-  s.c2 = m[k] / 2.0;
-  s.c1 = y[k + 1] - y[k] - (m[k + 1] + 2 * m[k]) / 6.0;
-  s.c0 = y[k];
+  const double y0 = y[k], y1 = y[k + 1], m0 = m[k], m1 = m[k + 1];
+  s.c3 = (m1 - m0) / 6.0;
+  s.c2 = m0 / 2.0;
+  s.c1 = y1 - y0 - (m1 + 2 * m0) / 6.0;
+  s.c0 = y0;
   return s;
+}
+__host__ __device__ __forceinline__ double seg_value(const Seg4 &c, double tau, double tau2, double tau3) {
+  return c.c3 * tau3 + c.c2 * tau2 + c.c1 * tau + c.c0;
 }
 
 // spline.cpp:64-75 for one output site when the sites are non-decreasing: the monotone cursor
@@ -75,22 +107,25 @@ struct UniformSites {  // a[k] = res * k   (util.h:101-107 applied to an iota, e
   double res;
   __host__ __device__ __forceinline__ double operator()(int k) const { return res * (double)k; }
 };
-struct ArraySites {
-  const double *a;
+struct ViewSites {
+  RV a;
   __host__ __device__ __forceinline__ double operator()(int k) const { return a[k]; }
 };
 
-#define TP_DECOMP(nblk)                                 \
-  const int b = (int)(blockIdx.x / (unsigned)(nblk));   \
-  const int i = (int)((blockIdx.x % (unsigned)(nblk)) * blockDim.x + threadIdx.x)
+// (trajectory, point) decomposition with trajectories fastest: nb trajectories per point
+#define TP_DECOMP(nb)                                                                      \
+  const long long t_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;                   \
+  const int bl = (int)(t_ % (nb));                                                         \
+  const int i = (int)(t_ / (nb))
 
 // ----------------------------------------------------------------------------- load (TP)
 // trajReadBIN / trajReadCSV payload -> FP64 rows (ba.cpp:2283-2299, 2417-2437)
 template <typename T>
 __global__ void k_in_load(Ws w, const T *theta, const T *cart, const int *n0, const double *tres,
-                          int n0max, int nblk) {
-  TP_DECOMP(nblk);
-  if (b >= w.B) return;
+                          int n0max, int nb) {
+  TP_DECOMP(nb);
+  const int b = bl;
+  if (i >= n0max) return;
   const int n = n0 ? n0[b] : n0max;
   if (i == 0) {
     TrajState &s = w.st[b];
@@ -106,15 +141,15 @@ __global__ void k_in_load(Ws w, const T *theta, const T *cart, const int *n0, co
     s.sLastSec = 0.0;
     s.nRev = s.nFwd = s.nOver = s.nSm = s.nOut = 0;
     s.tRev = s.tFwd = 0.0;
+    s.nVerify = 0;
   }
   if (i >= n) return;
-  if (theta)
-    for (int j = 0; j < CFG.J; ++j)
-      rowp(w.P, w, b, j)[i] = (double)theta[((size_t)b * CFG.J + j) * n0max + i];
+  double *dst = w.P + ((size_t)i * w.B + b) * w.R;
+  for (int j = 0; j < CFG.J; ++j) dst[j] = theta ? (double)theta[((size_t)b * CFG.J + j) * n0max + i] : 0.0;
   for (int j = 0; j < CFG.C; ++j) {
     double v = 0.0;
     if (cart && j < CFG.Cin) v = (double)cart[((size_t)b * CFG.Cin + j) * n0max + i];
-    rowp(w.P, w, b, CFG.J + j)[i] = v;
+    dst[CFG.J + j] = v;
   }
 }
 
@@ -131,7 +166,7 @@ __host__ __device__ inline void traj_linear_to4(const Ws &w, double *base, int b
     tau[i] = (a - so(seg[i])) / (so(seg[i] + 1) - so(seg[i]));
   }
   for (int r = 0; r < rows; ++r) {
-    double *x = rowp(base, w, b, r);
+    const RV x = rowv(base, w, b, r);
     double o[4];
     for (int i = 0; i < nNew; ++i) o[i] = x[seg[i]] + (x[seg[i] + 1] - x[seg[i]]) * tau[i];
     for (int i = 0; i < nNew; ++i) x[i] = o[i];
@@ -142,27 +177,27 @@ __host__ __device__ inline void traj_linear_to4(const Ws &w, double *base, int b
 
 // ----------------------------------------------------------------------------- prepare (T)
 // ba.cpp:98-183: timestamp de-duplication, length guards, remClosePts (util.cpp:452-524).
-// `ts` (optional) [B][n0max] timestamps of a CSV path; isRem scratch lives in w.nrm.
+// `ts` (optional) [B][n0max] timestamps of a CSV path; scratch lives in w.sC / w.nrm.
 __global__ void k_in_prepare(Ws w, const double *ts, int n0max, int hasTheta, int hasCart) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= w.B) return;
   TrajState &s = w.st[b];
-  const int J = CFG.J, C = CFG.C, R = CFG.R;
+  const int J = CFG.J, R = CFG.R;
   int nPts = s.nPts;
+  const RV scr = RV{w.nrm + (size_t)b * 2, (size_t)w.B * 2};  // per-trajectory scratch vector
   if (ts) {  // ba.cpp:98-127 — the index list is a vector<uint8_t>, so indices wrap at 256
     const double *t = ts + (size_t)b * n0max;
-    double *tt = w.sC + (size_t)b * w.Nc;  // working copy of the timestamps
+    const RV tt = vecv(w.sC, w, b);  // working copy of the timestamps
     for (int i = 0; i < nPts; ++i) tt[i] = t[i];
-    double *rem = w.nrm + (size_t)b * 2 * w.Nc;  // index list (values wrap like the uint8_t vector)
     int nRem = 0;
     for (int i = 1; i < nPts; ++i)
-      if (tt[i] == tt[i - 1]) rem[nRem++] = (double)(unsigned char)i;
+      if (tt[i] == tt[i - 1]) scr[nRem++] = (double)(unsigned char)i;
     int n = nPts;
     for (int r = nRem - 1; r >= 0; --r) {
-      const int k = (int)rem[r];
+      const int k = (int)scr[r];
       for (int i = k; i < n - 1; ++i) tt[i] = tt[i + 1];
       for (int row = 0; row < R; ++row) {
-        double *x = rowp(w.P, w, b, row);
+        const RV x = rowv(w.P, w, b, row);
         for (int i = k; i < n - 1; ++i) x[i] = x[i + 1];
       }
       n--;
@@ -186,15 +221,17 @@ __global__ void k_in_prepare(Ws w, const double *ts, int n0max, int hasTheta, in
   const int x0 = cartDriven ? J : 0, nx = cartDriven ? (hasCart ? CFG.Cin : 0) : (hasTheta ? J : 0);
   const double thr = cartDriven ? CFG.c.cart_thresh : CFG.c.jnt_thresh;
   const double thrSQ = thr * thr;
-  double *isRem = w.nrm + (size_t)b * 2 * w.Nc;
+  const RV isRem = scr;
   for (int i = 0; i < nPts; ++i) isRem[i] = 0.0;
+  const size_t pst = (size_t)w.B * w.R;
+  double *p0 = w.P + (size_t)b * w.R;
   for (;;) {
     bool any = false;
     for (int i = 1; i < nPts; ++i) {
       double sum = 0;
+      const double *a = p0 + (size_t)i * pst + x0, *a1 = p0 + (size_t)(i - 1) * pst + x0;
       for (int j = 0; j < nx; ++j) {
-        const double *x = rowp(w.P, w, b, x0 + j);
-        const double d = x[i] - x[i - 1];
+        const double d = a[j] - a1[j];
         sum += d * d;
       }
       if (sum < thrSQ && !(isRem[i - 1] != 0.0)) {
@@ -211,10 +248,9 @@ __global__ void k_in_prepare(Ws w, const double *ts, int n0max, int hasTheta, in
     int cur = 0;
     for (int i = 0; i < nPts; ++i) {
       if (!(isRem[i] != 0.0)) {
-        for (int row = 0; row < R; ++row) {
-          double *x = rowp(w.P, w, b, row);
-          x[cur] = x[i];
-        }
+        double *d = p0 + (size_t)cur * pst;
+        const double *a = p0 + (size_t)i * pst;
+        for (int row = 0; row < R; ++row) d[row] = a[row];
         cur++;
       }
     }
@@ -227,13 +263,12 @@ __global__ void k_in_prepare(Ws w, const double *ts, int n0max, int hasTheta, in
     return;
   }
   if (nPts < 4) traj_linear_to4(w, w.P, b, s, R);
-  (void)C;
 }
 
 // ----------------------------------------------------------------------------- smooth/decimate (TR)
 // util.cpp:254-288 (smooth), 343-352 (decimate) as used by ba.cpp:195-242 (quirk Q6: the
 // smoothWindow branch smooths with inputDecimFact as the window).  tmp row = Q.
-__host__ __device__ inline void smooth_row(double *x, double *x2, int n, int w) {
+__host__ __device__ inline void smooth_row(const RV &x, const RV &x2, int n, int w) {
   w = imin_(w, n);
   const int wMid = w / 2 + w % 2 - 1;
   w = 2 * wMid + 1;
@@ -267,7 +302,7 @@ __global__ void k_in_smooth_decimate(Ws w) {
   const bool isJ = row < CFG.J;
   const bool active = isJ ? (pt == BATOTP_JOINT || pt == BATOTP_BOTH) : (pt == BATOTP_CART || pt == BATOTP_BOTH);
   if (!active) return;
-  double *x = rowp(w.P, w, b, row), *tmp = rowp(w.Q, w, b, row);
+  const RV x = rowv(w.P, w, b, row), tmp = rowv(w.Q, w, b, row);
   int n = s.nPts;
   const int df = CFG.c.input_decim_fact;
   if (df > 1) {
@@ -295,7 +330,8 @@ __global__ void k_in_decim_fix(Ws w) {
 
 // ----------------------------------------------------------------------------- Robot point functions (TP)
 // mode: 1 = fwdKin (theta rows -> cart rows), 2 = invKin (cart -> theta), 3 = zero cart rows,
-//       4 = zero theta rows.  Evaluated on `base` rows for i < st.nPts (or nOver for the output).
+//       4 = zero theta rows.  `base` is a point-major array of nb trajectories (b0 = first trajectory
+//       of the chunk it holds); evaluated for i < st.nPts (or nOver for the output).
 // robot.cpp:105-176 (KUKA; 3x3 products accumulated left to right as in oracle/eigen_standin),
 // 185-202 (RR), 243-278 + 291-322 (CSPR inverse kinematics / attachment points).
 struct Pmat {
@@ -306,12 +342,8 @@ __host__ __device__ inline void fk_kuka_point(const double *th, double *xyz) {
   double c[7], s[7];
   for (int k = 0; k < 7; ++k) {
     const double tk = D2R * th[k];
-#ifdef BATOTP_HOST_EMU
     c[k] = cos(tk);
     s[k] = sin(tk);
-#else
-    sincos(tk, &s[k], &c[k]);
-#endif
   }
   const double c1 = c[0], c2 = c[1], c3 = c[2], c4 = c[3], c5 = c[4], c6 = c[5], c7 = c[6];
   const double s1 = s[0], s2 = s[1], s3 = s[2], s4 = s[3], s5 = s[4], s6 = s[5], s7 = s[6];
@@ -351,35 +383,35 @@ __host__ __device__ inline void ik_cspr_point(const Pmat &pm, const double *xyz,
   }
 }
 
-__global__ void k_pointfn(Ws w, double *base, int stride, int mode, int useOver, Pmat pm, int nblk) {
-  TP_DECOMP(nblk);
-  if (b >= w.B) return;
-  const TrajState &s = w.st[b];
+__global__ void k_pointfn(Ws w, double *base, int b0, int mode, int useOver, Pmat pm, int npts, int nb) {
+  TP_DECOMP(nb);
+  if (i >= npts) return;
+  const TrajState &s = w.st[b0 + bl];
   if (s.status & ST_FATAL_MASK) return;
   const int n = useOver ? s.nOver : s.nPts;
   if (i >= n) return;
   const int J = CFG.J, C = CFG.C;
-  double *r0 = base + (size_t)b * CFG.R * stride;
+  double *r0 = base + ((size_t)i * nb + bl) * CFG.R;
   if (mode == 1) {
     double th[MAXD], xyz[3];
-    for (int j = 0; j < J; ++j) th[j] = r0[(size_t)j * stride + i];
+    for (int j = 0; j < J; ++j) th[j] = r0[j];
     if (CFG.c.robot_type == BATOTP_KUKA) {
       fk_kuka_point(th, xyz);
-      for (int q = 0; q < 3; ++q) r0[(size_t)(J + q) * stride + i] = xyz[q];
+      for (int q = 0; q < 3; ++q) r0[J + q] = xyz[q];
     } else if (CFG.c.robot_type == BATOTP_RR) {
       fk_rr_point(th, xyz);
-      r0[(size_t)(J + 0) * stride + i] = xyz[0];
-      r0[(size_t)(J + 1) * stride + i] = xyz[1];
+      r0[J + 0] = xyz[0];
+      r0[J + 1] = xyz[1];
     }
   } else if (mode == 2) {
     double xyz[3], rho[3];
-    for (int q = 0; q < 3; ++q) xyz[q] = r0[(size_t)(J + q) * stride + i];
+    for (int q = 0; q < 3; ++q) xyz[q] = r0[J + q];
     ik_cspr_point(pm, xyz, rho);
-    for (int q = 0; q < 3; ++q) r0[(size_t)q * stride + i] = rho[q];
+    for (int q = 0; q < 3; ++q) r0[q] = rho[q];
   } else if (mode == 3) {
-    for (int q = 0; q < C; ++q) r0[(size_t)(J + q) * stride + i] = 0.0;
+    for (int q = 0; q < C; ++q) r0[J + q] = 0.0;
   } else if (mode == 4) {
-    for (int q = 0; q < J; ++q) r0[(size_t)q * stride + i] = 0.0;
+    for (int q = 0; q < J; ++q) r0[q] = 0.0;
   }
 }
 
@@ -401,8 +433,8 @@ __global__ void k_aa2q(Ws w) {
   TrajState &s = w.st[b];
   if (s.status & ST_FATAL_MASK) return;
   const int J = CFG.J;
-  double *r3 = rowp(w.P, w, b, J + 3), *r4 = rowp(w.P, w, b, J + 4), *r5 = rowp(w.P, w, b, J + 5),
-         *r6 = rowp(w.P, w, b, J + 6);
+  const RV r3 = rowv(w.P, w, b, J + 3), r4 = rowv(w.P, w, b, J + 4), r5 = rowv(w.P, w, b, J + 5),
+           r6 = rowv(w.P, w, b, J + 6);
   double aa[3] = {r3[0], r4[0], r5[0]}, q[4], qprev[4];
   aa2q_dev(aa, qprev);
   for (int i = 0; i < s.nPts; ++i) {
@@ -436,57 +468,67 @@ __global__ void k_adjust_s(Ws w, int special) {
   double cartNormRes = special ? CFG.c.cart_norm_res : CFG.c.cart_norm_res2;
   const double thetaNormRes = special ? CFG.c.theta_norm_res : CFG.c.theta_norm_res2;
   const int nPts = s.nPts;
-  double *thetaNorm = w.nrm + (size_t)b * 2 * w.Nc, *cartPosNorm = thetaNorm + w.Nc;
-  double *sC = w.sC + (size_t)b * w.Nc;
+  const RV thetaNorm = RV{w.nrm + (size_t)b * 2, (size_t)w.B * 2}, cartPosNorm = RV{w.nrm + (size_t)b * 2 + 1, (size_t)w.B * 2};
+  const RV sC = vecv(w.sC, w, b);
   const double sResi = s.sres;
   double MinRatio = 1.0 / CFG.quadThresh;
   double thetaWindow = 5;
   double thetaNormLast = 0, cartPosNormLast = 0;
   const double DEG2RAD = 3.14159265358979323846 / 180.0, RAD2DEG = 180.0 / 3.14159265358979323846;
   if (!CFG.c.are_jnt_deg) thetaWindow *= DEG2RAD;
-  const double *cx = rowp(w.P, w, b, J), *cy = rowp(w.P, w, b, J + 1), *cz = rowp(w.P, w, b, J + 2);
+  const size_t pst = (size_t)w.B * w.R;
+  const double *p0 = w.P + (size_t)b * w.R;
+  double tn = 0.0, cn = 0.0;
   thetaNorm[0] = 0.0;
   cartPosNorm[0] = 0.0;
+  double cur[MAXD + 3];
+  for (int j = 0; j < J; ++j) cur[j] = p0[j];
+  for (int j = 0; j < 3; ++j) cur[MAXD + j] = p0[J + j];
   for (int i = 0; i < nPts - 1; ++i) {
+    const double *nx = p0 + (size_t)(i + 1) * pst;
     double dthetaSQ = 0;
     for (int j = 0; j < J; ++j) {
-      const double *x = rowp(w.P, w, b, j);
-      const double d = x[i + 1] - x[i];
+      const double v = nx[j];
+      const double d = v - cur[j];
       dthetaSQ += d * d;
+      cur[j] = v;
     }
-    thetaNorm[i + 1] = thetaNorm[i] + sqrt(dthetaSQ);
+    tn = tn + sqrt(dthetaSQ);
+    thetaNorm[i + 1] = tn;
     double dcartSQ = 0;
-    double d = cx[i + 1] - cx[i];
-    dcartSQ += d * d;
-    d = cy[i + 1] - cy[i];
-    dcartSQ += d * d;
-    d = cz[i + 1] - cz[i];
-    dcartSQ += d * d;
-    cartPosNorm[i + 1] = cartPosNorm[i] + sqrt(dcartSQ);
+    for (int j = 0; j < 3; ++j) {
+      const double v = nx[J + j];
+      const double d = v - cur[MAXD + j];
+      dcartSQ += d * d;
+      cur[MAXD + j] = v;
+    }
+    cn = cn + sqrt(dcartSQ);
+    cartPosNorm[i + 1] = cn;
     if (CFG.c.is_auto_integ_res) {
-      const double thetaChange = thetaNorm[i + 1] - thetaNormLast;
-      const double cartChange = cartPosNorm[i + 1] - cartPosNormLast;
+      const double thetaChange = tn - thetaNormLast;
+      const double cartChange = cn - cartPosNormLast;
       if (thetaChange > thetaWindow) {
         MinRatio = dmin_(MinRatio, 3.0 * cartChange / thetaChange);
-        thetaNormLast = thetaNorm[i + 1];
-        cartPosNormLast = cartPosNorm[i + 1];
+        thetaNormLast = tn;
+        cartPosNormLast = cn;
       }
     }
   }
-  if (thetaNorm[nPts - 1] < thetaNormRes) {
+  const double tnLast = tn, cnLast = cn;
+  if (tnLast < thetaNormRes) {
     s.status |= ST_IDENTICAL;
     return;
   }
   double sLast = 0, sResNew = 0;
   if (CFG.c.is_auto_integ_res) {  // ba.cpp:493-556
-    if ((cartPosNorm[nPts - 1] < cartNormRes) && s.scaleType == 2) {
+    if ((cnLast < cartNormRes) && s.scaleType == 2) {
       s.sWeights[1] = s.sWeights[1] + s.sWeights[2];
       s.sWeights[2] = 0;
       s.scaleType = 1;
     }
     const double sW12in = s.sWeights[1] + s.sWeights[2];
-    double cartRat = 500.0 * cartPosNorm[nPts - 1];
-    double thetaRat = thetaNorm[nPts - 1];
+    double cartRat = 500.0 * cnLast;
+    double thetaRat = tnLast;
     if (!CFG.c.are_jnt_deg) thetaRat *= RAD2DEG;
     const double minIntegRes = 0.004, maxIntegRes = 0.2, K = 0.0003;
     double newIntegRes = K * CFG.c.cart_acc_max / CFG.c.cart_vel_max;
@@ -513,19 +555,25 @@ __global__ void k_adjust_s(Ws w, int special) {
   const double ptsLast = (double)(nPts - 1);
   switch (s.scaleType) {
     case 0: sLast = sResi * ptsLast; sResNew = sResi; break;
-    case 1: sLast = thetaNorm[nPts - 1]; sResNew = thetaNormRes; break;
-    case 2: sLast = cartPosNorm[nPts - 1]; sResNew = cartNormRes; break;
+    case 1: sLast = tnLast; sResNew = thetaNormRes; break;
+    case 2: sLast = cnLast; sResNew = cartNormRes; break;
   }
   double cartPosNormFact;
-  if (cartPosNorm[nPts - 1] >= cartNormRes)
-    cartPosNormFact = s.sWeights[2] * sLast / cartPosNorm[nPts - 1];
+  if (cnLast >= cartNormRes)
+    cartPosNormFact = s.sWeights[2] * sLast / cnLast;
   else
     cartPosNormFact = 0;
   const double tTeachFact = s.sWeights[0] * sLast / (sResi * ptsLast);
-  const double thetaNormFact = s.sWeights[1] * sLast / thetaNorm[nPts - 1];
+  const double thetaNormFact = s.sWeights[1] * sLast / tnLast;
   s.sres = sLast / (nPts - 1);
-  for (int i = 0; i < nPts; ++i)
-    sC[i] = tTeachFact * sResi * (double)i + thetaNormFact * thetaNorm[i] + cartPosNormFact * cartPosNorm[i];
+  double prevSC = 0.0;
+  bool tooSmall = false;
+  for (int i = 0; i < nPts; ++i) {
+    const double v = tTeachFact * sResi * (double)i + thetaNormFact * thetaNorm[i] + cartPosNormFact * cartPosNorm[i];
+    sC[i] = v;
+    if (!special && i > 0 && !tooSmall && (v - prevSC < 1e-12 * s.sres)) tooSmall = true;
+    prevSC = v;
+  }
   s.sLast = sLast;
   s.sResNew = sResNew;
   s.sResi = sResi;
@@ -536,17 +584,16 @@ __global__ void k_adjust_s(Ws w, int special) {
     int nPts2 = (int)ceil(sLast / sResNew) + 1;  // ba.cpp:666-667, capacity estimate for the march
     s.nNew = imax_(nPts2, 4);
   } else {
-    for (int i = 1; i < nPts; ++i)
-      if (sC[i] - sC[i - 1] < 1e-12 * s.sres) {
-        s.status |= ST_SRES_SMALL;
-        return;
-      }
+    if (tooSmall) {  // ba.cpp:605-612
+      s.status |= ST_SRES_SMALL;
+      return;
+    }
     // evalSplineFullTraj(traj, traj.sres, sResNew) plan: ba.cpp:794-819
     const double oldRes = s.sres;
     int nNew = (int)ceil(oldRes / sResNew * (nPts - 1)) + 1;
     nNew = imax_(nNew, 4);
     const double newRes = oldRes * (nPts - 1) / (nNew - 1);
-    s.sScale = sC[nPts - 1] / (double)(nNew - 1);
+    s.sScale = prevSC / (double)(nNew - 1);  // sC[nPts-1] / sMVC[nNew-1]
     s.nNew = nNew;
     s.sresC = s.sres;
     s.vFact = 1 / s.sresC;
@@ -557,18 +604,19 @@ __global__ void k_adjust_s(Ws w, int special) {
 }
 
 // ----------------------------------------------------------------------------- Thomas (TR)
-// Spline::getSplineCoeffs on every coordinate row of `src` -> solution rows in `dst`.
+// Spline::getSplineCoeffs on `rows` of the `rowsPerTraj` rows each of nb trajectories holds in the
+// point-major array `src` -> solution rows in `dst`.  b0 = chunk index of the first trajectory.
 // n source: 0 = st.nPts, 1 = st.nOver, 2 = st.nSm
-__global__ void k_thomas_rows(Ws w, const double *src, double *dst, int stride, int rows, int rowsPerTraj,
+__global__ void k_thomas_rows(Ws w, double *src, double *dst, int nb, int b0, int rows, int rowsPerTraj,
                               int nsel, int clamped, ThomasTabs tabs) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = t / rows, row = t % rows;
-  if (b >= w.B) return;
-  const TrajState &s = w.st[b];
+  const int bl = t / rows, row = t % rows;
+  if (bl >= nb) return;
+  const TrajState &s = w.st[b0 + bl];
   if (s.status & ST_FATAL_MASK) return;
   const int n = nsel == 0 ? s.nPts : (nsel == 1 ? s.nOver : s.nSm);
-  const double *y = src + ((size_t)b * rowsPerTraj + row) * stride;
-  double *m = dst + ((size_t)b * rowsPerTraj + row) * stride;
+  const size_t st = (size_t)nb * rowsPerTraj, off = (size_t)bl * rowsPerTraj + row;
+  const RV y{src + off, st}, m{dst + off, st};
   if (clamped)
     thomas_clamped(y, m, n, tabs.cC);
   else
@@ -586,11 +634,15 @@ __global__ void k_march(Ws w) {
   if (s.status & ST_FATAL_MASK) return;
   const int J = CFG.J, C = CFG.C, R = CFG.R;
   const int nPts = s.nPts;
-  const double *sC = w.sC + (size_t)b * w.Nc;
-  const double *P = rowp(w.P, w, b, 0), *M = rowp(w.M, w, b, 0);
-  double *Q = rowp(w.Q, w, b, 0);
+  const RV sC = vecv(w.sC, w, b);
+  const size_t pst = (size_t)w.B * w.R;
+  const double *P = w.P + (size_t)b * w.R, *M = w.M + (size_t)b * w.R;
+  double *Q = w.Q + (size_t)b * w.R;
   const int Nc = w.Nc;
-  for (int r = 0; r < R; ++r) Q[(size_t)r * Nc] = P[(size_t)r * Nc];
+  double last[MAXD + 3];  // the previously emitted point (theta rows, cart xyz)
+  for (int r = 0; r < R; ++r) Q[r] = P[r];
+  for (int j = 0; j < J; ++j) last[j] = P[j];
+  for (int j = 0; j < 3; ++j) last[MAXD + j] = P[J + j];
   double sPrv = 0, prv_ds = 0;
   int CurNewPt = 1, CurOldPt = 1;
   int seg = 0;
@@ -599,15 +651,17 @@ __global__ void k_march(Ws w) {
   const bool cartEval = CFG.cartOn != 0;
   double cartpt[MAXD];
   for (int q = 0; q < MAXD; ++q) cartpt[q] = s.cartpt[q];
+  const double sCend = sC[nPts - 1];
   while (!isDone) {
+    const double *po = P + (size_t)CurOldPt * pst;
     double dthetaSQ = 0;
     for (int j = 0; j < J; ++j) {
-      const double d = P[(size_t)j * Nc + CurOldPt] - Q[(size_t)j * Nc + CurNewPt - 1];
+      const double d = po[j] - last[j];
       dthetaSQ += d * d;
     }
     double dcartSQ = 0;
     for (int j = 0; j < 3; ++j) {
-      const double d = P[(size_t)(J + j) * Nc + CurOldPt] - Q[(size_t)(J + j) * Nc + CurNewPt - 1];
+      const double d = po[J + j] - last[MAXD + j];
       dcartSQ += d * d;
     }
     const double cur_ds = s.tTeachFact * s.sResi * (double)CurOldPt + s.thetaNormFact * sqrt(dthetaSQ) +
@@ -617,14 +671,15 @@ __global__ void k_march(Ws w) {
       prv_ds = 0;
       sPrv = sNew;
       const double sCur = sPrv;
-      if (sCur > sC[nPts - 1]) isDone = true;
+      if (sCur > sCend) isDone = true;
       if (!isDone) {
         // updateCurSeg (ba.cpp:1617-1652) on the non-uniform sites
-        double sSeg;
+        double sSeg, sNext;
         int guard = 0;
         for (;;) {
           sSeg = sC[seg];
-          if (sCur >= sSeg && sCur <= sC[seg + 1]) break;
+          sNext = sC[seg + 1];
+          if (sCur >= sSeg && sCur <= sNext) break;
           if (sCur > sSeg) {
             if (seg >= lastSeg) {
               seg = lastSeg;
@@ -650,16 +705,30 @@ __global__ void k_march(Ws w) {
           s.status |= ST_GRID_CAP;
           return;
         }
+        const double *y0 = P + (size_t)seg * pst, *y1 = y0 + pst, *m0 = M + (size_t)seg * pst, *m1 = m0 + pst;
+        double *qo = Q + (size_t)CurNewPt * pst;
         for (int j = 0; j < J; ++j) {
-          const Seg4 c = seg_coef(P + (size_t)j * Nc, M + (size_t)j * Nc, seg);
-          Q[(size_t)j * Nc + CurNewPt] = c.c3 * tau3 + c.c2 * tau2 + c.c1 * tau + c.c0;
+          Seg4 c;
+          c.c3 = (m1[j] - m0[j]) / 6.0;
+          c.c2 = m0[j] / 2.0;
+          c.c1 = y1[j] - y0[j] - (m1[j] + 2 * m0[j]) / 6.0;
+          c.c0 = y0[j];
+          const double v = seg_value(c, tau, tau2, tau3);
+          qo[j] = v;
+          last[j] = v;
         }
         if (cartEval)
           for (int j = 0; j < C; ++j) {
-            const Seg4 c = seg_coef(P + (size_t)(J + j) * Nc, M + (size_t)(J + j) * Nc, seg);
-            cartpt[j] = c.c3 * tau3 + c.c2 * tau2 + c.c1 * tau + c.c0;
+            const int r = J + j;
+            Seg4 c;
+            c.c3 = (m1[r] - m0[r]) / 6.0;
+            c.c2 = m0[r] / 2.0;
+            c.c1 = y1[r] - y0[r] - (m1[r] + 2 * m0[r]) / 6.0;
+            c.c0 = y0[r];
+            cartpt[j] = seg_value(c, tau, tau2, tau3);
           }
-        for (int j = 0; j < C; ++j) Q[(size_t)(J + j) * Nc + CurNewPt] = cartpt[j];
+        for (int j = 0; j < C; ++j) qo[J + j] = cartpt[j];
+        for (int j = 0; j < 3; ++j) last[MAXD + j] = cartpt[j];
         CurOldPt = seg + 1;
         CurNewPt++;
       }
@@ -673,7 +742,11 @@ __global__ void k_march(Ws w) {
       }
     }
   }
-  for (int r = 0; r < R; ++r) Q[(size_t)r * Nc + CurNewPt] = P[(size_t)r * Nc + nPts - 1];
+  {
+    const double *pe = P + (size_t)(nPts - 1) * pst;
+    double *qo = Q + (size_t)CurNewPt * pst;
+    for (int r = 0; r < R; ++r) qo[r] = pe[r];
+  }
   for (int q = 0; q < MAXD; ++q) s.cartpt[q] = cartpt[q];
   s.nPts = CurNewPt + 1;
   s.sres = s.sResNew;
@@ -683,23 +756,33 @@ __global__ void k_march(Ws w) {
 // ----------------------------------------------------------------------------- resample (TP)
 // evalSplineFullTraj, regular pass (ba.cpp:835-859): sites sMVC[i] = sScale*i located in the
 // non-uniform sC by findInterpSegs, values by interp1spline.  Source P/M/sC -> Q.
-__global__ void k_resample(Ws w, int nblk) {
-  TP_DECOMP(nblk);
-  if (b >= w.B) return;
+__global__ void k_resample(Ws w, int npts, int nb) {
+  TP_DECOMP(nb);
+  if (i >= npts) return;
+  const int b = bl;
   const TrajState &s = w.st[b];
   if (s.status & ST_FATAL_MASK) return;
   if (i >= s.nNew) return;
-  const double *sC = w.sC + (size_t)b * w.Nc;
+  const RV sC = vecv(w.sC, w, b);
   const int nOld = s.nPts;
   const double aOut = s.sScale * (double)i;
-  ArraySites in{sC};
+  ViewSites in{sC};
   const int seg = find_seg(in, nOld, aOut);
-  const double den = sC[seg + 1] - sC[seg];
-  const double tau = (aOut - sC[seg]) / den;
+  const double lo = sC[seg];
+  const double den = sC[seg + 1] - lo;
+  const double tau = (aOut - lo) / den;
   const double tau2 = tau * tau, tau3 = tau2 * tau;
+  const size_t pst = (size_t)w.B * w.R;
+  const double *y0 = w.P + (size_t)seg * pst + (size_t)b * w.R, *y1 = y0 + pst;
+  const double *m0 = w.M + (size_t)seg * pst + (size_t)b * w.R, *m1 = m0 + pst;
+  double *qo = w.Q + (size_t)i * pst + (size_t)b * w.R;
   for (int r = 0; r < CFG.R; ++r) {
-    const Seg4 c = seg_coef(rowp(w.P, w, b, r), rowp(w.M, w, b, r), seg);
-    rowp(w.Q, w, b, r)[i] = c.c3 * tau3 + c.c2 * tau2 + c.c1 * tau + c.c0;
+    Seg4 c;
+    c.c3 = (m1[r] - m0[r]) / 6.0;
+    c.c2 = m0[r] / 2.0;
+    c.c1 = y1[r] - y0[r] - (m1[r] + 2 * m0[r]) / 6.0;
+    c.c0 = y0[r];
+    qo[r] = seg_value(c, tau, tau2, tau3);
   }
 }
 // spline.cpp:78-87: a zero-length input segment aborts findInterpSegs (status only) (T)
@@ -708,12 +791,16 @@ __global__ void k_resample_commit(Ws w) {
   if (b >= w.B) return;
   TrajState &s = w.st[b];
   if (s.status & ST_FATAL_MASK) return;
-  const double *sC = w.sC + (size_t)b * w.Nc;
-  for (int i = 0; i < s.nPts - 1; ++i)
-    if (sC[i + 1] - sC[i] < 1e-20) {
+  const RV sC = vecv(w.sC, w, b);
+  double prev = sC[0];
+  for (int i = 0; i < s.nPts - 1; ++i) {
+    const double nx = sC[i + 1];
+    if (nx - prev < 1e-20) {
       s.status |= ST_DIV0;
       return;
     }
+    prev = nx;
+  }
   s.nPts = s.nNew;
 }
 
@@ -745,9 +832,10 @@ __global__ void k_final_plan(Ws w) {
 //   kinematic rows (joints, then Cartesian xyz when a Cartesian constraint is on):
 //       {3*c3, 2*c2, c1, 6*c3}  — the products evalSplinePartials forms first (ba.cpp:1359-1360)
 //   dynamics rows a1..a4 (torque on): {c3, c2, c1, c0}  (ba.cpp:1387-1405)
-__global__ void k_build_table(Ws w, const double *A, const double *AM, int nblk) {
-  TP_DECOMP(nblk);
-  if (b >= w.B) return;
+__global__ void k_build_table(Ws w, int npts, int nb) {
+  TP_DECOMP(nb);
+  if (i >= npts) return;
+  const int b = bl;
   const TrajState &s = w.st[b];
   if (s.status & ST_FATAL_MASK) return;
   if (i >= s.nPtsC - 1) return;
@@ -756,7 +844,7 @@ __global__ void k_build_table(Ws w, const double *A, const double *AM, int nblk)
   int rt = 0;
   const int nKin = J + (CFG.cartOn ? 3 : 0);
   for (int r = 0; r < nKin; ++r, ++rt) {
-    const Seg4 c = seg_coef(rowp(w.P, w, b, r), rowp(w.M, w, b, r), i);
+    const Seg4 c = seg_coef(rowv(w.P, w, b, r), rowv(w.M, w, b, r), i);
     t[rt * 4 + 0] = 3 * c.c3;
     t[rt * 4 + 1] = 2 * c.c2;
     t[rt * 4 + 2] = c.c1;
@@ -765,8 +853,7 @@ __global__ void k_build_table(Ws w, const double *A, const double *AM, int nblk)
   if (CFG.trqOn) {
     for (int a = 0; a < 4; ++a)
       for (int j = 0; j < J; ++j, ++rt) {
-        const size_t off = (((size_t)b * 4 + a) * MAXD + j) * w.Nc;
-        const Seg4 c = seg_coef(A + off, AM + off, i);
+        const Seg4 c = seg_coef(arowv(w.A, w, b, a, j), arowv(w.AM, w, b, a, j), i);
         t[rt * 4 + 0] = c.c3;
         t[rt * 4 + 1] = c.c2;
         t[rt * 4 + 2] = c.c1;
@@ -776,10 +863,11 @@ __global__ void k_build_table(Ws w, const double *A, const double *AM, int nblk)
 }
 
 // Values and s-derivatives on the final grid (ba.cpp:840-855), needed by the dynamic model
-// (findDynModel, ba.cpp:905-938).  Source P/M -> Q (values), D, D2.   (TP)
-__global__ void k_eval_grid(Ws w, double *D, double *D2, int nblk) {
-  TP_DECOMP(nblk);
-  if (b >= w.B) return;
+// (findDynModel, ba.cpp:905-938).  Source P/M -> Q (values), GD, GD2.   (TP)
+__global__ void k_eval_grid(Ws w, int npts, int nb) {
+  TP_DECOMP(nb);
+  if (i >= npts) return;
+  const int b = bl;
   const TrajState &s = w.st[b];
   if (s.status & ST_FATAL_MASK) return;
   if (i >= s.nNew) return;
@@ -792,9 +880,9 @@ __global__ void k_eval_grid(Ws w, double *D, double *D2, int nblk) {
   const double vfact = 1.0 / s.sresC;  // interp1spline's own 1/tfact with tfact = oldRes (spline.cpp:142-143)
   const double afact = vfact * vfact;
   for (int r = 0; r < CFG.R; ++r) {
-    const Seg4 c = seg_coef(rowp(w.P, w, b, r), rowp(w.M, w, b, r), seg);
-    rowp(w.Q, w, b, r)[i] = c.c3 * tau3 + c.c2 * tau2 + c.c1 * tau + c.c0;
-    rowp(D, w, b, r)[i] = (3 * c.c3 * tau2 + 2 * c.c2 * tau + c.c1) * vfact;
-    rowp(D2, w, b, r)[i] = (6 * c.c3 * tau + 2 * c.c2) * afact;
+    const Seg4 c = seg_coef(rowv(w.P, w, b, r), rowv(w.M, w, b, r), seg);
+    rowv(w.Q, w, b, r)[i] = seg_value(c, tau, tau2, tau3);
+    rowv(w.GD, w, b, r)[i] = (3 * c.c3 * tau2 + 2 * c.c2 * tau + c.c1) * vfact;
+    rowv(w.GD2, w, b, r)[i] = (6 * c.c3 * tau + 2 * c.c2) * afact;
   }
 }

@@ -8,9 +8,10 @@
 #include "k_sweep.cuh"
 
 template <int J, bool CART, bool TRQ>
-__global__ void k_mvc(Ws w, double sdotStart, double *out, int cap, int nblk) {
-  TP_DECOMP(nblk);
-  if (b >= w.B) return;
+__global__ void k_mvc(Ws w, double sdotStart, double *out, int cap, int npts, int nb) {
+  TP_DECOMP(nb);
+  if (i >= npts) return;
+  const int b = bl;
   const TrajState &s = w.st[b];
   if (s.status & ST_FATAL_MASK) return;
   if (i >= s.nPtsC || i >= cap) return;

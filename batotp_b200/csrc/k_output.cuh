@@ -75,29 +75,30 @@ __host__ __device__ inline void dyn_rr_point(const double th[2], const double th
 }
 
 // findDynModel on the grid (TP): values in Q, s-derivatives in GD/GD2 -> A rows (+Par2Ser)
-__global__ void k_dyn_grid(Ws w, Pmat pm, int nblk) {
-  TP_DECOMP(nblk);
-  if (b >= w.B) return;
+__global__ void k_dyn_grid(Ws w, Pmat pm, int npts, int nb) {
+  TP_DECOMP(nb);
+  if (i >= npts) return;
+  const int b = bl;
   TrajState &s = w.st[b];
   if (s.status & ST_FATAL_MASK) return;
   if (i >= s.nPts) return;
   const int J = CFG.J;
-  const size_t aStride = (size_t)MAXD * w.Nc;
-  double *Ab = w.A + (size_t)b * 4 * aStride;
   double a[4][MAXD];
   for (int k = 0; k < 4; ++k)
     for (int q = 0; q < MAXD; ++q) a[k][q] = 0.0;
+  const size_t off = ((size_t)i * w.B + b) * w.R;
+  const double *q0 = w.Q + off, *g1 = w.GD + off, *g2 = w.GD2 + off;
   if (CFG.c.is_parallel) {  // dynCSPR3DOF (robot.cpp:487-517)
     for (int q = 0; q < 3; ++q) {
-      a[0][q] = -rowp(w.GD, w, b, J + q)[i];
-      a[1][q] = -rowp(w.GD2, w, b, J + q)[i];
+      a[0][q] = -g1[J + q];
+      a[1][q] = -g2[J + q];
     }
     a[3][2] = 9.81;
     if (CFG.c.is_par2ser) {  // ba.cpp:916-938: a_k <- A^-1 a_k with A from setA
       double Am[3][3], cart[3], th[3];
       for (int q = 0; q < 3; ++q) {
-        cart[q] = rowp(w.Q, w, b, J + q)[i];
-        th[q] = rowp(w.Q, w, b, q)[i];
+        cart[q] = q0[J + q];
+        th[q] = q0[q];
       }
       for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) Am[r][c] = (cart[r] - pm.p[r][c]) / th[c];
@@ -110,21 +111,24 @@ __global__ void k_dyn_grid(Ws w, Pmat pm, int nblk) {
   } else {  // dynRR
     double th[2], d1[2], d2[2];
     for (int q = 0; q < 2; ++q) {
-      th[q] = rowp(w.Q, w, b, q)[i];
-      d1[q] = rowp(w.GD, w, b, q)[i];
-      d2[q] = rowp(w.GD2, w, b, q)[i];
+      th[q] = q0[q];
+      d1[q] = g1[q];
+      d2[q] = g2[q];
     }
     dyn_rr_point(th, d1, d2, a[0], a[1], a[2], a[3]);
   }
+  double *Ab = w.A + ((size_t)i * w.B + b) * 4 * MAXD;
   for (int k = 0; k < 4; ++k)
-    for (int q = 0; q < J; ++q) Ab[(size_t)k * aStride + (size_t)q * w.Nc + i] = a[k][q];
+    for (int q = 0; q < MAXD; ++q) Ab[k * MAXD + q] = a[k][q];
 }
 
 // ----------------------------------------------------------------------------- output plan (T)
 // ba.cpp:1664-1706: output resolution bookkeeping, oversampled size, natural spline of sMVC(t).
+// Output kernels work on the sub-chunk [w.b0, w.b0 + w.Bo) of the resident chunk.
 __global__ void k_out_plan(Ws w, ThomasTabs tabs) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= w.B) return;
+  const int bl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bl >= w.Bo) return;
+  const int b = w.b0 + bl;
   TrajState &s = w.st[b];
   if (s.status & ST_FATAL_MASK) return;
   const double outResT = CFG.c.out_res;
@@ -147,8 +151,9 @@ __global__ void k_out_plan(Ws w, ThomasTabs tabs) {
     s.status |= ST_STEP_CAP;
     return;
   }
-  const double *sF = w.hist + (size_t)b * 4 * w.Sc + 2 * (size_t)w.Sc;
-  thomas_natural(sF, w.mS + (size_t)b * w.Sc, s.nFwd, tabs.cN);
+  double *sF = w.hist + (size_t)b * 4 * w.Sc + 2 * (size_t)w.Sc;
+  const RV y{sF, 1}, m{w.mS + (size_t)bl * w.Sc, 1};
+  thomas_natural(y, m, s.nFwd, tabs.cN);
 }
 
 // tMVCout[i] (ba.cpp:1693-1699) -> s at that time (TP)
@@ -165,13 +170,13 @@ __host__ __device__ __forceinline__ double tmvc_out(int i, int n, double tLast) 
     v = last - 1.0 / 3.0;
   else
     v = (double)(i - 1);
-  if (n == 4 && i == 2) v = last - 1.0 / 3.0;
   return (tLast / last) * v;
 }
 
-__global__ void k_out_s(Ws w, int nblk) {
-  TP_DECOMP(nblk);
-  if (b >= w.B) return;
+__global__ void k_out_s(Ws w, int npts, int nb) {
+  TP_DECOMP(nb);
+  if (i >= npts) return;
+  const int b = w.b0 + bl;
   const TrajState &s = w.st[b];
   if (s.status & ST_FATAL_MASK) return;
   if (i >= s.nOver) return;
@@ -180,67 +185,77 @@ __global__ void k_out_s(Ws w, int nblk) {
   UniformSites in{s.tStep};
   const int seg = find_seg(in, s.nFwd, t);
   const double tau = (t - in(seg)) / (in(seg + 1) - in(seg));
-  const double *sF = w.hist + (size_t)b * 4 * w.Sc + 2 * (size_t)w.Sc;
-  const Seg4 c = seg_coef(sF, w.mS + (size_t)b * w.Sc, seg);
+  double *sF = w.hist + (size_t)b * 4 * w.Sc + 2 * (size_t)w.Sc;
+  const Seg4 c = seg_coef(RV{sF, 1}, RV{w.mS + (size_t)bl * w.Sc, 1}, seg);
   const double tau2 = tau * tau, tau3 = tau2 * tau;
-  w.sOut[(size_t)b * w.Oc + i] = c.c3 * tau3 + c.c2 * tau2 + c.c1 * tau + c.c0;
+  w.sOut[(size_t)i * w.Bo + bl] = seg_value(c, tau, tau2, tau3);
 }
 
 // findInterpSegs(traj.sC, sMVCout) (ba.cpp:1708, spline.cpp:56-99): the interpolated s(t) need not
 // be monotone, so the reference's forward-only cursor is kept as a sequential walk (T).
 __global__ void k_out_segs(Ws w) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= w.B) return;
-  const TrajState &s = w.st[b];
+  const int bl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bl >= w.Bo) return;
+  const TrajState &s = w.st[w.b0 + bl];
   if (s.status & ST_FATAL_MASK) return;
-  const double *sOut = w.sOut + (size_t)b * w.Oc;
-  int *seg = w.segO + (size_t)b * w.Oc;
-  double *tau = w.tauO + (size_t)b * w.Oc;
   const int nIn = s.nPtsC;
   const double res = s.sresC;
   int cur = 0;
+  double hiEdge = res * (double)(cur + 1);
   for (int i = 0; i < s.nOver; ++i) {
-    const double a = sOut[i];
-    for (;;) {
-      if (a < res * (double)(cur + 1) || cur == nIn - 2) break;
+    const size_t at = (size_t)i * w.Bo + bl;
+    const double a = w.sOut[at];
+    while (!(a < hiEdge || cur == nIn - 2)) {
       cur++;
+      hiEdge = res * (double)(cur + 1);
     }
-    seg[i] = cur;
+    w.segO[at] = cur;
     const double lo = res * (double)cur;
-    tau[i] = (a - lo) / (res * (double)(cur + 1) - lo);
+    w.tauO[at] = (a - lo) / (hiEdge - lo);
   }
 }
 
 // theta(t) / cart(t) at the oversampled sites (ba.cpp:1713-1742) (TP).  Rows that are not
 // path-driven are filled by the kinematics kernel afterwards (or are the generic robot's zeros).
-__global__ void k_out_eval(Ws w, int nblk) {
-  TP_DECOMP(nblk);
-  if (b >= w.B) return;
+__global__ void k_out_eval(Ws w, int npts, int nb) {
+  TP_DECOMP(nb);
+  if (i >= npts) return;
+  const int b = w.b0 + bl;
   const TrajState &s = w.st[b];
   if (s.status & ST_FATAL_MASK) return;
   if (i >= s.nOver) return;
-  const int seg = w.segO[(size_t)b * w.Oc + i];
-  const double tau = w.tauO[(size_t)b * w.Oc + i];
+  const size_t at = (size_t)i * w.Bo + bl;
+  const int seg = w.segO[at];
+  const double tau = w.tauO[at];
   const double tau2 = tau * tau, tau3 = tau2 * tau;
   const int pt = CFG.c.path_type, J = CFG.J;
+  const size_t pst = (size_t)w.B * w.R;
+  const double *y0 = w.P + (size_t)seg * pst + (size_t)b * w.R, *y1 = y0 + pst;
+  const double *m0 = w.M + (size_t)seg * pst + (size_t)b * w.R, *m1 = m0 + pst;
+  double *o = w.O5 + at * w.R;
   for (int r = 0; r < CFG.R; ++r) {
     const bool isJ = r < J;
     const bool driven = isJ ? (pt == BATOTP_JOINT || pt == BATOTP_BOTH) : (pt == BATOTP_CART || pt == BATOTP_BOTH);
     double v = 0.0;
     if (driven) {
-      const Seg4 c = seg_coef(rowp(w.P, w, b, r), rowp(w.M, w, b, r), seg);
-      v = c.c3 * tau3 + c.c2 * tau2 + c.c1 * tau + c.c0;
+      Seg4 c;
+      c.c3 = (m1[r] - m0[r]) / 6.0;
+      c.c2 = m0[r] / 2.0;
+      c.c1 = y1[r] - y0[r] - (m1[r] + 2 * m0[r]) / 6.0;
+      c.c0 = y0[r];
+      v = seg_value(c, tau, tau2, tau3);
     }  // non-driven rows: filled by the kinematics kernel; the generic robot's Cartesian rows are zeros
-    orow(w.O5, w, b, r)[i] = v;
+    o[r] = v;
   }
 }
 
 // Torque branch, part 1 (ba.cpp:1746-1765 / 1807-1812): values and time derivatives of the
 // re-splined rows at their own knots (seg=i-1, tau=1; i=0: seg=0, tau=0).  O5/OM -> OA, OD, OD2.  (TP)
-__global__ void k_out_knot_eval(Ws w, int nblk) {
-  TP_DECOMP(nblk);
-  if (b >= w.B) return;
-  const TrajState &s = w.st[b];
+// (torque runs use Os == Oc, so OA/OM share O5's pitch)
+__global__ void k_out_knot_eval(Ws w, int npts, int nb) {
+  TP_DECOMP(nb);
+  if (i >= npts) return;
+  const TrajState &s = w.st[w.b0 + bl];
   if (s.status & ST_FATAL_MASK) return;
   if (i >= s.nOver) return;
   const int J = CFG.J;
@@ -252,52 +267,55 @@ __global__ void k_out_knot_eval(Ws w, int nblk) {
   for (int r = 0; r < CFG.R; ++r) {
     const bool resplined = (r < J) || CFG.c.is_parallel;
     if (resplined) {
-      const Seg4 c = seg_coef(orow(w.O5, w, b, r), orow(w.OM, w, b, r), seg);
-      orow(w.OA, w, b, r)[i] = c.c3 * tau3 + c.c2 * tau2 + c.c1 * tau + c.c0;
-      orow(w.OD, w, b, r)[i] = (3 * c.c3 * tau2 + 2 * c.c2 * tau + c.c1) * vfact;
-      orow(w.OD2, w, b, r)[i] = (6 * c.c3 * tau + 2 * c.c2) * afact;
+      const Seg4 c = seg_coef(orowv(w.O5, w, bl, r), orowv(w.OM, w, bl, r), seg);
+      orowv(w.OA, w, bl, r)[i] = seg_value(c, tau, tau2, tau3);
+      orowv(w.OD, w, bl, r)[i] = (3 * c.c3 * tau2 + 2 * c.c2 * tau + c.c1) * vfact;
+      orowv(w.OD2, w, bl, r)[i] = (6 * c.c3 * tau + 2 * c.c2) * afact;
     } else {
-      orow(w.OA, w, b, r)[i] = orow(w.O5, w, b, r)[i];
+      orowv(w.OA, w, bl, r)[i] = orowv(w.O5, w, bl, r)[i];
     }
   }
 }
 
 // Torque branch, part 2 (ba.cpp:1770-1803 / 1815-1825): generalized forces at the output sites (TP)
-__global__ void k_out_trq(Ws w, Pmat pm, int nblk) {
-  TP_DECOMP(nblk);
-  if (b >= w.B) return;
-  const TrajState &s = w.st[b];
+__global__ void k_out_trq(Ws w, Pmat pm, int npts, int nb) {
+  TP_DECOMP(nb);
+  if (i >= npts) return;
+  const TrajState &s = w.st[w.b0 + bl];
   if (s.status & ST_FATAL_MASK) return;
   if (i >= s.nOver) return;
   const int J = CFG.J;
-  double *trq = w.Trq + (size_t)b * MAXD * w.Oc;
+  const size_t off = ((size_t)i * w.Bo + bl) * w.R;
+  const double *oa = w.OA + off, *od = w.OD + off, *od2 = w.OD2 + off;
+  double *trq = w.Trq + ((size_t)i * w.Bo + bl) * MAXD;
   if (CFG.c.is_parallel) {
     double a2[3], a3[3] = {0, 0, 0}, a4[3] = {0, 0, 9.81}, cart[3], th[3], bStar[3], x[3], Am[3][3];
     for (int q = 0; q < 3; ++q) {
-      a2[q] = -orow(w.OD2, w, b, J + q)[i];
-      cart[q] = orow(w.OA, w, b, J + q)[i];
-      th[q] = orow(w.OA, w, b, q)[i];
+      a2[q] = -od2[J + q];
+      cart[q] = oa[J + q];
+      th[q] = oa[q];
     }
     for (int q = 0; q < 3; ++q) bStar[q] = a2[q] + a3[q] + a4[q];
     for (int r = 0; r < 3; ++r)
       for (int c = 0; c < 3; ++c) Am[r][c] = (cart[r] - pm.p[r][c]) / th[c];
     lu3_solve(Am, bStar, x);
-    for (int q = 0; q < J; ++q) trq[(size_t)q * w.Oc + i] = x[q];
+    for (int q = 0; q < J; ++q) trq[q] = x[q];
   } else {
     double th[2], d1[2], d2[2], a1[2], a2[2], a3[2], a4[2];
     for (int q = 0; q < 2; ++q) {
-      th[q] = orow(w.OA, w, b, q)[i];
-      d1[q] = orow(w.OD, w, b, q)[i];
-      d2[q] = orow(w.OD2, w, b, q)[i];
+      th[q] = oa[q];
+      d1[q] = od[q];
+      d2[q] = od2[q];
     }
     dyn_rr_point(th, d1, d2, a1, a2, a3, a4);
-    for (int q = 0; q < 2; ++q) trq[(size_t)q * w.Oc + i] = a2[q] + a3[q] + a4[q];
+    for (int q = 0; q < 2; ++q) trq[q] = a2[q] + a3[q] + a4[q];
   }
 }
 
 // ----------------------------------------------------------------------------- smoothing (TP)
 // util.cpp:254-288 evaluated pointwise: x2[p] for a row of length n, window w (valid for n >= 2*wMid).
-__host__ __device__ __forceinline__ double smooth_at(const double *x, int n, int wIn, int p) {
+template <class V>
+__host__ __device__ __forceinline__ double smooth_at(const V &x, int n, int wIn, int p) {
   int w = imin_(wIn, n);
   const int wMid = w / 2 + w % 2 - 1;
   w = 2 * wMid + 1;
@@ -323,9 +341,9 @@ __host__ __device__ __forceinline__ double smooth_at(const double *x, int n, int
 
 // ba.cpp:1838-1871 plan (T): nSm
 __global__ void k_out_smooth_plan(Ws w) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= w.B) return;
-  TrajState &s = w.st[b];
+  const int bl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bl >= w.Bo) return;
+  TrajState &s = w.st[w.b0 + bl];
   if (s.status & ST_FATAL_MASK) return;
   if (s.outSmooth > 1.5) {
     const int nIn = s.nOver;
@@ -339,10 +357,11 @@ __global__ void k_out_smooth_plan(Ws w) {
 
 // smooth + linear decimation of every row (src -> dst) and of the torque rows (TP over nSm).
 // Trajectories whose smoothing factor is <= 1.5 (ba.cpp:1838) are copied through unchanged.
-__global__ void k_out_smooth(Ws w, const double *src, int srcStride, double *dst, int dstStride, int nblk) {
-  TP_DECOMP(nblk);
-  if (b >= w.B) return;
-  const TrajState &s = w.st[b];
+// src/dst are point-major sub-chunk arrays [.][Bo][R].
+__global__ void k_out_smooth(Ws w, double *src, double *dst, int npts, int nb) {
+  TP_DECOMP(nb);
+  if (i >= npts) return;
+  const TrajState &s = w.st[w.b0 + bl];
   if (s.status & ST_FATAL_MASK) return;
   if (i >= s.nSm) return;
   const bool sm = s.outSmooth > 1.5;
@@ -357,34 +376,34 @@ __global__ void k_out_smooth(Ws w, const double *src, int srcStride, double *dst
   }
   const int wv = (int)s.outSmooth;
   for (int r = 0; r < CFG.R; ++r) {
-    const double *x = src + ((size_t)b * CFG.R + r) * srcStride;
+    const RV x = orowv(src, w, bl, r);
     double v;
     if (sm) {
       const double v0 = smooth_at(x, nIn, wv, seg), v1 = smooth_at(x, nIn, wv, seg + 1);
       v = v0 + (v1 - v0) * tau;
     } else
       v = x[i];
-    dst[((size_t)b * CFG.R + r) * dstStride + i] = v;
+    orowv(dst, w, bl, r)[i] = v;
   }
   if (CFG.trqOn)
     for (int r = 0; r < CFG.J; ++r) {
-      const double *x = w.Trq + ((size_t)b * MAXD + r) * w.Oc;
+      const RV x = trqv(w.Trq, w, bl, r);
       double v;
       if (sm) {
         const double v0 = smooth_at(x, nIn, wv, seg), v1 = smooth_at(x, nIn, wv, seg + 1);
         v = v0 + (v1 - v0) * tau;
       } else
         v = x[i];
-      w.Trq2[((size_t)b * MAXD + r) * w.Oc + i] = v;
+      trqv(w.Trq2, w, bl, r)[i] = v;
     }
 }
 
 // ----------------------------------------------------------------------------- final (T + TP)
 // ba.cpp:1873-1921: final sizes
 __global__ void k_out_final_plan(Ws w) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= w.B) return;
-  TrajState &s = w.st[b];
+  const int bl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bl >= w.Bo) return;
+  TrajState &s = w.st[w.b0 + bl];
   if (s.status & ST_FATAL_MASK) return;
   const double tLast = s.tStep * (double)(s.nFwd - 1);
   if (s.isReinterp) {
@@ -411,28 +430,30 @@ __host__ __device__ inline void q2aa_dev(const double q[4], double aa[3]) {
 }
 
 // Final resample (when outRes < integRes, ba.cpp:1880-1915) and float32 packing in trajWriteBIN
-// row order.  src rows hold nSm points, srcM their natural-spline solutions.   (TP over OutC)
-// Output rows are stored as FP64 too (outD) when requested, for the strict-parity trig path.
-__global__ void k_out_pack(Ws w, const double *src, const double *srcM, int sStride, const double *trqSrc,
-                           const double *trqM, float *thetaOut, float *cartOut, float *trqOut,
-                           double *cartOutD, double *outD, int nblk) {
-  TP_DECOMP(nblk);
-  if (b >= w.B) return;
-  const TrajState &s = w.st[b];
+// row order.  src rows hold nSm points, srcM their natural-spline solutions (point-major sub-chunk
+// arrays); outputs are trajectory-major [Bo][row][OutC] as the caller's buffers.  (TP over OutC,
+// points fastest so that the float rows are written coalesced)
+__global__ void k_out_pack(Ws w, double *src, double *srcM, double *trqSrc, double *trqM, float *thetaOut,
+                           float *cartOut, float *trqOut, double *cartOutD, double *outD, int npts, int nb) {
+  const long long t_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)(t_ % npts);
+  const int bl = (int)(t_ / npts);
+  if (bl >= nb) return;
+  const TrajState &s = w.st[w.b0 + bl];
   const int J = CFG.J, C = CFG.C, Cin = CFG.Cin;
   if (i >= w.OutC) return;
   const bool fatal = (s.status & ST_FATAL_MASK) != 0;
   // rows are zero beyond their length (and for trajectories that were not optimised)
   if (fatal || i >= s.nOut) {
-    for (int r = 0; r < J; ++r) thetaOut[((size_t)b * J + r) * w.OutC + i] = 0.f;
+    for (int r = 0; r < J; ++r) thetaOut[((size_t)bl * J + r) * w.OutC + i] = 0.f;
     if (trqOut && CFG.trqOn)
-      for (int r = 0; r < J; ++r) trqOut[((size_t)b * J + r) * w.OutC + i] = 0.f;
+      for (int r = 0; r < J; ++r) trqOut[((size_t)bl * J + r) * w.OutC + i] = 0.f;
   }
   if (fatal || i >= s.nCartOut) {
     if (cartOut)
-      for (int r = 0; r < Cin; ++r) cartOut[((size_t)b * Cin + r) * w.OutC + i] = 0.f;
+      for (int r = 0; r < Cin; ++r) cartOut[((size_t)bl * Cin + r) * w.OutC + i] = 0.f;
     if (cartOutD && C == 7)
-      for (int r = 0; r < 7; ++r) cartOutD[((size_t)b * 7 + r) * w.OutC + i] = 0.0;
+      for (int r = 0; r < 7; ++r) cartOutD[((size_t)bl * 7 + r) * w.OutC + i] = 0.0;
   }
   if (fatal) return;
   const bool generic = CFG.c.robot_type == BATOTP_GENJNT;
@@ -450,40 +471,37 @@ __global__ void k_out_pack(Ws w, const double *src, const double *srcM, int sStr
   if (i < s.nOut) {
     for (int r = 0; r < J; ++r) {
       double v;
-      if (re) {
-        const Seg4 c = seg_coef(src + ((size_t)b * CFG.R + r) * sStride, srcM + ((size_t)b * CFG.R + r) * sStride, seg);
-        v = c.c3 * tau3 + c.c2 * tau2 + c.c1 * tau + c.c0;
-      } else
-        v = src[((size_t)b * CFG.R + r) * sStride + i];
-      thetaOut[((size_t)b * J + r) * w.OutC + i] = (float)v;
-      if (outD) outD[((size_t)b * (CFG.R + J) + r) * w.OutC + i] = v;
+      if (re)
+        v = seg_value(seg_coef(orowv(src, w, bl, r), orowv(srcM, w, bl, r), seg), tau, tau2, tau3);
+      else
+        v = orowv(src, w, bl, r)[i];
+      thetaOut[((size_t)bl * J + r) * w.OutC + i] = (float)v;
+      if (outD) outD[((size_t)bl * (CFG.R + J) + r) * w.OutC + i] = v;
     }
     if (trqOut && CFG.trqOn)
       for (int r = 0; r < J; ++r) {
         double v;
-        if (re) {
-          const Seg4 c = seg_coef(trqSrc + ((size_t)b * MAXD + r) * w.Oc, trqM + ((size_t)b * MAXD + r) * w.Oc, seg);
-          v = c.c3 * tau3 + c.c2 * tau2 + c.c1 * tau + c.c0;
-        } else
-          v = trqSrc[((size_t)b * MAXD + r) * w.Oc + i];
-        trqOut[((size_t)b * J + r) * w.OutC + i] = (float)v;
-        if (outD) outD[((size_t)b * (CFG.R + J) + CFG.R + r) * w.OutC + i] = v;
+        if (re)
+          v = seg_value(seg_coef(trqv(trqSrc, w, bl, r), trqv(trqM, w, bl, r), seg), tau, tau2, tau3);
+        else
+          v = trqv(trqSrc, w, bl, r)[i];
+        trqOut[((size_t)bl * J + r) * w.OutC + i] = (float)v;
+        if (outD) outD[((size_t)bl * (CFG.R + J) + CFG.R + r) * w.OutC + i] = v;
       }
   }
   if (i < s.nCartOut && (cartOut || cartOutD || outD)) {
     double cv[MAXD];
     for (int r = 0; r < C; ++r) {
-      if (re && !generic) {
-        const Seg4 c = seg_coef(src + ((size_t)b * CFG.R + J + r) * sStride, srcM + ((size_t)b * CFG.R + J + r) * sStride, seg);
-        cv[r] = c.c3 * tau3 + c.c2 * tau2 + c.c1 * tau + c.c0;
-      } else
-        cv[r] = src[((size_t)b * CFG.R + J + r) * sStride + i];
+      if (re && !generic)
+        cv[r] = seg_value(seg_coef(orowv(src, w, bl, J + r), orowv(srcM, w, bl, J + r), seg), tau, tau2, tau3);
+      else
+        cv[r] = orowv(src, w, bl, J + r)[i];
     }
     if (outD)
-      for (int r = 0; r < C; ++r) outD[((size_t)b * (CFG.R + J) + J + r) * w.OutC + i] = cv[r];
+      for (int r = 0; r < C; ++r) outD[((size_t)bl * (CFG.R + J) + J + r) * w.OutC + i] = cv[r];
     if (C == 7) {
       if (cartOutD) {  // strict-parity path: the host applies q2aa with its own libm
-        for (int r = 0; r < 7; ++r) cartOutD[((size_t)b * 7 + r) * w.OutC + i] = cv[r];
+        for (int r = 0; r < 7; ++r) cartOutD[((size_t)bl * 7 + r) * w.OutC + i] = cv[r];
       } else {
         double aa[3];
         q2aa_dev(cv + 3, aa);
@@ -491,20 +509,24 @@ __global__ void k_out_pack(Ws w, const double *src, const double *srcM, int sStr
       }
     }
     if (cartOut && !(C == 7 && cartOutD))
-      for (int r = 0; r < Cin; ++r) cartOut[((size_t)b * Cin + r) * w.OutC + i] = (float)cv[r];
+      for (int r = 0; r < Cin; ++r) cartOut[((size_t)bl * Cin + r) * w.OutC + i] = (float)cv[r];
   }
 }
 
-// s-sdot histories in sdotWrite order (ascending s for the reverse sweep) as float32 (TP over Sc)
-__global__ void k_pack_hist(Ws w, float *histOut, int nblk) {
-  TP_DECOMP(nblk);
-  if (b >= w.B) return;
+// s-sdot histories in sdotWrite order (ascending s for the reverse sweep) as float32 (TP over Sc,
+// points fastest); also clears the switching flags beyond the recorded steps.
+__global__ void k_pack_hist(Ws w, float *histOut, int npts, int nb) {
+  const long long t_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)(t_ % npts);
+  const int bl = (int)(t_ / npts);
+  if (bl >= nb) return;
   if (i >= w.Sc) return;
+  const int b = w.b0 + bl;
   const TrajState &s = w.st[b];
   const bool fatal = (s.status & ST_FATAL_MASK) != 0;
   const int nRev = fatal ? 0 : s.nRev, nFwd = fatal ? 0 : s.nFwd;
   const double *hb = w.hist + (size_t)b * 4 * w.Sc;
-  float *o = histOut + (size_t)b * 4 * w.Sc;
+  float *o = histOut + (size_t)bl * 4 * w.Sc;
   unsigned char *fl = w.flags + (size_t)b * 2 * w.Sc;
   if (i < nRev) {
     o[i] = (float)hb[(w.Sc - nRev) + i];

@@ -62,6 +62,7 @@ def load(path: Optional[str] = None):
     L.batotp_cuda_last_error.argtypes = [C.c_void_p]
     L.batotp_cuda_last_error.restype = C.c_char_p
     L.batotp_cuda_set_chunk.argtypes = [C.c_void_p, C.c_int]
+    L.batotp_cuda_set_out_chunk.argtypes = [C.c_void_p, C.c_int]
     L.batotp_cuda_launch_count.argtypes = [C.c_void_p]
     L.batotp_cuda_launch_count.restype = C.c_long
     L.batotp_cuda_stats.argtypes = [C.c_void_p, _dp, C.c_int]
@@ -161,6 +162,9 @@ class Context:
 
     def set_chunk(self, n: int):
         self.L.batotp_cuda_set_chunk(self.h, n)
+
+    def set_out_chunk(self, n: int):
+        self.L.batotp_cuda_set_out_chunk(self.h, n)
 
     def set_keep_f64(self, on: bool):
         self.L.batotp_cuda_set_keep_f64(self.h, int(on))

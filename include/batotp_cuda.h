@@ -39,8 +39,11 @@ int batotp_cuda_device_count(void);
 int batotp_cuda_create(int device, batotp_handle *out);
 int batotp_cuda_destroy(batotp_handle h);
 const char *batotp_cuda_last_error(batotp_handle h);
-/* trajectories processed per device pass (workspace is sized for one chunk); default 16384 */
+/* trajectories resident per device pass (input interpolation + both sweeps run over the whole chunk;
+ * the tables and histories of one chunk live in HBM); default 16384 */
 int batotp_cuda_set_chunk(batotp_handle h, int chunk);
+/* trajectories per interpOutputData pass inside a chunk (bounds the oversampled-output buffers); default 8192 */
+int batotp_cuda_set_out_chunk(batotp_handle h, int n);
 /* number of kernels launched by this context since creation (for the benchmark's gpu_launches) */
 long batotp_cuda_launch_count(batotp_handle h);
 /* measurement hooks for bench.py.

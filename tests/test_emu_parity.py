@@ -49,9 +49,13 @@ def test_chunking_and_capacity_retries_do_not_change_results(ctx):
     ctx.set_chunk(4)  # 3 chunks: 4 + 4 + 2
     a = P.run_device(ctx, cfg, tres, th, None)
     ctx.set_chunk(16384)
+    ctx.set_out_chunk(3)  # 4 output passes over the single resident chunk: 3 + 3 + 3 + 1
     b = P.run_device(ctx, cfg, tres, th, None)
+    ctx.set_out_chunk(8192)
+    c = P.run_device(ctx, cfg, tres, th, None)
     for nm in ("status", "n_rev", "n_fwd", "n_out", "t_total", "theta_out", "hist", "flags"):
         assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
+        assert np.array_equal(getattr(a, nm), getattr(c, nm)), nm
 
 
 def test_ragged_short_and_degenerate_inputs(ctx):

@@ -54,7 +54,9 @@ def test_chunking_does_not_change_results(ctx):
     ctx.set_chunk(128)
     a = P.run_device(ctx, cfg, tres, th, None, out_cap=4096, hist_cap=4096)
     ctx.set_chunk(16384)
+    ctx.set_out_chunk(100)
     b = P.run_device(ctx, cfg, tres, th, None, out_cap=4096, hist_cap=4096)
+    ctx.set_out_chunk(8192)
     for nm in ("status", "n_rev", "n_fwd", "n_out", "t_total", "theta_out", "hist", "flags"):
         assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
 
