@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <thread>
 #include <vector>
@@ -23,6 +24,7 @@
 #include <cuda_runtime.h>
 #else
 thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+thread_local EmuCta *emu_cta = nullptr;
 #endif
 
 // ----------------------------------------------------------------------------- runtime shims
@@ -177,18 +179,52 @@ struct batotp_ctx {
   double sweepMs = 0;
   long sweepLaunches = 0;
   long long cntVerify = 0, cntSteps = 0, cntTraj = 0;
+  // optional per-kernel device timing (batotp_cuda_set_profile): serialises every launch
+  bool profile = false;
+  std::map<std::string, std::pair<double, long>> prof;
 #ifndef BATOTP_HOST_EMU
-  cudaEvent_t evS0 = nullptr, evS1 = nullptr, evT[2] = {nullptr, nullptr};
+  cudaEvent_t evS0 = nullptr, evS1 = nullptr, evT[2] = {nullptr, nullptr}, evP[2] = {nullptr, nullptr};
   bool sweepPending = false;
 #endif
 };
 
 namespace {
 
+// brackets one launch with events when profiling is on (and waits for it: measurement mode only)
+struct ProfScope {
+  batotp_ctx *h;
+  const char *name;
+  ProfScope(batotp_ctx *h_, const char *n) : h(h_), name(n) {
+#ifndef BATOTP_HOST_EMU
+    if (h->profile) {
+      if (!h->evP[0]) {
+        cudaEventCreate(&h->evP[0]);
+        cudaEventCreate(&h->evP[1]);
+      }
+      cudaEventRecord(h->evP[0], h->stream);
+    }
+#endif
+  }
+  ~ProfScope() {
+#ifndef BATOTP_HOST_EMU
+    if (h->profile) {
+      cudaEventRecord(h->evP[1], h->stream);
+      cudaEventSynchronize(h->evP[1]);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, h->evP[0], h->evP[1]);
+      auto &e = h->prof[name];
+      e.first += ms;
+      e.second++;
+    }
+#endif
+  }
+};
+
 #define LAUNCH_T(h, kern, nthreads, ...)                                                    \
   do {                                                                                      \
     const int nth_ = (nthreads);                                                            \
     if (nth_ > 0) {                                                                         \
+      ProfScope ps_((h), #kern);                                                            \
       BATOTP_LAUNCH(kern, dim3(cdiv(nth_, 128)), dim3(128), (h)->stream, __VA_ARGS__);      \
       g_check_launch();                                                                     \
       (h)->launches++;                                                                      \
@@ -199,6 +235,7 @@ namespace {
   do {                                                                                      \
     const long long tot_ = (long long)(npts) * (long long)(nb);                             \
     if (tot_ > 0) {                                                                         \
+      ProfScope ps_((h), #kern);                                                            \
       BATOTP_LAUNCH(kern, dim3((unsigned)((tot_ + 127) / 128)), dim3(128), (h)->stream,     \
                     __VA_ARGS__, (int)(npts), (int)(nb));                                   \
       g_check_launch();                                                                     \
@@ -554,8 +591,7 @@ void thomas_rows(batotp_ctx *h, double *src, double *dst, int nb, int b0, int ro
 template <int J, bool CART, bool TRQ>
 void launch_sweep(batotp_ctx *h) {
   g_zero(h->w.queue, sizeof(int) * 4, h->stream);
-  constexpr int RT = J + (CART ? 3 : 0) + (TRQ ? 4 * J : 0);
-  const size_t smem = (size_t)(36 + (RT * 4 + 14) * SW_NT) * sizeof(double);
+  const size_t smem = SweepLayout<J, CART, TRQ>::bytes;
 #ifndef BATOTP_HOST_EMU
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -574,8 +610,11 @@ void launch_sweep(batotp_ctx *h) {
 #else
   int blocks = 1;
 #endif
-  BATOTP_LAUNCH_SMEM((k_sweep<J, CART, TRQ>), dim3(blocks), dim3(SW_NT), smem, h->stream, h->w);
-  g_check_launch();
+  {
+    ProfScope ps_(h, "k_sweep");
+    BATOTP_LAUNCH_WARP((k_sweep<J, CART, TRQ>), dim3(blocks), dim3(SW_NT), smem, h->stream, h->w);
+    g_check_launch();
+  }
 #ifndef BATOTP_HOST_EMU
   CU_CHECK(cudaEventRecord(h->evS1, h->stream));
   h->sweepPending = true;
@@ -634,6 +673,7 @@ void stage_inputs(batotp_ctx *h, const batotp_batch_in *in, int first, int B) {
     h->d_n0 = (int *)g_alloc(capB * 4);
     h->capIn = capB * (size_t)std::max(c.J, c.Cin) * n0 * 8;
   }
+  ProfScope ps_(h, "copy_h2d(stage)");
   g_h2d(h->d_tres, tres.data(), (size_t)B * 8, h->stream);
   if (in->on_device) {
     h->in_theta = th ? (const char *)th + (size_t)first * c.J * n0 * es : nullptr;
@@ -1036,6 +1076,33 @@ int batotp_cuda_stats_reset(batotp_handle h) {
   h->launches = 0;
   return 0;
 }
+int batotp_cuda_set_profile(batotp_handle h, int on) {
+  if (!h) return -1;
+  h->profile = on != 0;
+  h->prof.clear();
+  return 0;
+}
+int batotp_cuda_profile_dump(batotp_handle h, char *buf, int cap) {
+  if (!h || !buf || cap < 1) return -1;
+  std::string o;
+  char line[256];
+  for (const auto &kv : h->prof) {
+    snprintf(line, sizeof line, "%s,%.4f,%ld\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    o += line;
+  }
+  const int n = (int)std::min(o.size(), (size_t)cap - 1);
+  memcpy(buf, o.data(), n);
+  buf[n] = 0;
+  return n;
+}
+#ifdef BATOTP_HOST_EMU
+// TEST-ONLY (host emulation build): counters of the sweep kernel's float filters, see k_sweep.cuh
+int batotp_emu_filter_stats(long long *out, int n, int reset) {
+  for (int i = 0; i < n && i < 8; ++i) out[i] = g_emu_filter[i];
+  if (reset) memset(g_emu_filter, 0, sizeof(g_emu_filter));
+  return 0;
+}
+#endif
 int batotp_cuda_timer(batotp_handle h, int which, double *elapsed_ms) {
 #ifndef BATOTP_HOST_EMU
   if (!h || which < 0 || which > 1) return -1;
@@ -1208,6 +1275,7 @@ static void fetch_sub(batotp_handle h, batotp_batch_out *out, int first) {
   const DevCfg &c = h->cfg;
   const Ws &w = h->w;
   const int Bo = w.Bo, g0 = first + w.b0;
+  ProfScope ps_(h, "copy_d2h(fetch)");
   h->hst.resize(h->B);
   g_d2h(h->hst.data() + w.b0, w.st + w.b0, (size_t)Bo * sizeof(TrajState), h->stream);
   g_sync(h->stream);

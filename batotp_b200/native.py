@@ -72,6 +72,8 @@ def load(path: Optional[str] = None):
                                            C.POINTER(C.c_longlong)]
     L.batotp_cuda_stats_reset.argtypes = [C.c_void_p]
     L.batotp_cuda_timer.argtypes = [C.c_void_p, C.c_int, _dp]
+    L.batotp_cuda_set_profile.argtypes = [C.c_void_p, C.c_int]
+    L.batotp_cuda_profile_dump.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.batotp_cuda_optimize_batch.argtypes = [C.c_void_p, C.POINTER(BatotpCfg), C.POINTER(BatchIn), C.POINTER(BatchOut)]
     L.batotp_cuda_load.argtypes = [C.c_void_p, C.POINTER(BatotpCfg), C.POINTER(BatchIn)]
     for f in ("batotp_cuda_interp_input", "batotp_cuda_sweeps", "batotp_cuda_interp_output"):
@@ -188,6 +190,19 @@ class Context:
         if self.L.batotp_cuda_selftest_div(self.h, seed, n, C.byref(bad), C.byref(fast)) != 0:
             self._err('batotp_cuda_selftest_div')
         return bad.value, fast.value
+
+    def set_profile(self, on: bool):
+        self.L.batotp_cuda_set_profile(self.h, int(on))
+
+    def profile(self) -> dict:
+        """{kernel: (total_ms, launches)} since set_profile(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        self.L.batotp_cuda_profile_dump(self.h, buf, len(buf))
+        out = {}
+        for ln in buf.value.decode().splitlines():
+            nm, ms, n = ln.rsplit(",", 2)
+            out[nm] = (float(ms), int(n))
+        return out
 
     def stats_reset(self):
         self.L.batotp_cuda_stats_reset(self.h)

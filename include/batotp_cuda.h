@@ -55,6 +55,11 @@ long batotp_cuda_launch_count(batotp_handle h);
 int batotp_cuda_stats(batotp_handle h, double *out, int n);
 int batotp_cuda_stats_reset(batotp_handle h);
 int batotp_cuda_timer(batotp_handle h, int which, double *elapsed_ms);
+/* per-kernel device timing for tuning runs: when on, every launch is bracketed by CUDA events and waited
+ * for (so the pipeline is serialised: never combine with a throughput measurement).
+ * _profile_dump writes "kernel,total_ms,launches" lines into buf and returns the length. */
+int batotp_cuda_set_profile(batotp_handle h, int on);
+int batotp_cuda_profile_dump(batotp_handle h, char *buf, int cap);
 /* measured FP64-pipe peak of the device in TFLOP/s: fused multiply-add chains, and separate
  * multiply + add chains (the ceiling of this library's -fmad=false kernels) */
 int batotp_cuda_fp64_peak(batotp_handle h, double *tflops_fma, double *tflops_nofma);
