@@ -790,8 +790,9 @@ void do_interp_output(batotp_ctx *h, int b0, int Bo) {
   ThomasTabs t{h->d_cN, h->d_cC};
   LAUNCH_T(h, k_out_plan, Bo, w, t);
   LAUNCH_TP(h, k_out_s, w.Oc, Bo, w);
+  LAUNCH_TP(h, k_out_segs_par, w.Oc, Bo, w);
   LAUNCH_T(h, k_out_segs, Bo, w);
-  LAUNCH_TP(h, k_out_eval, w.Oc, Bo, w);
+  LAUNCH_TP(h, k_out_eval, (long long)w.Oc * c.R, Bo, w);
   apply_kinematics(h, 2);
   double *cur = w.O5;
   int curCap = w.Oc;
@@ -903,6 +904,9 @@ __global__ void k_selftest_div(unsigned long long seed, int perThread, unsigned 
       const double q0 = __dmul_rn(a, rc.r);
       const double q = __fma_rn(rc.r, __fma_rn(-b, q0, a), q0);
       if (rc.ok && sdiv::exp_ok(a) && sdiv::exp_ok(q)) fast++;
+      // the constant-divisor form used by the spline coefficients
+      const double s1 = sdiv::div6(a), s2 = a / 6.0;
+      if (__double_as_longlong(s1) != __double_as_longlong(s2) && !(s1 != s1 && s2 != s2)) bad++;
     }
   }
   atomicAdd(mismatch, bad);

@@ -78,9 +78,9 @@ template <class VY, class VM>
 __host__ __device__ __forceinline__ Seg4 seg_coef(const VY &y, const VM &m, int k) {
   Seg4 s;
   const double y0 = y[k], y1 = y[k + 1], m0 = m[k], m1 = m[k + 1];
-  s.c3 = (m1 - m0) / 6.0;
+  s.c3 = sdiv::div6(m1 - m0);
   s.c2 = m0 / 2.0;
-  s.c1 = y1 - y0 - (m1 + 2 * m0) / 6.0;
+  s.c1 = y1 - y0 - sdiv::div6(m1 + 2 * m0);
   s.c0 = y0;
   return s;
 }

@@ -147,6 +147,7 @@ __global__ void k_out_plan(Ws w, ThomasTabs tabs) {
   s.outSmooth = outSmooth;
   s.outResT = outResT;
   s.nOver = nOver;
+  s.segWalk = 0;
   if (nOver > w.Oc) {
     s.status |= ST_STEP_CAP;
     return;
@@ -191,13 +192,45 @@ __global__ void k_out_s(Ws w, int npts, int nb) {
   w.sOut[(size_t)i * w.Bo + bl] = seg_value(c, tau, tau2, tau3);
 }
 
-// findInterpSegs(traj.sC, sMVCout) (ba.cpp:1708, spline.cpp:56-99): the interpolated s(t) need not
-// be monotone, so the reference's forward-only cursor is kept as a sequential walk (T).
+// findInterpSegs(traj.sC, sMVCout) (ba.cpp:1708, spline.cpp:56-99).  The reference walks a forward-only
+// cursor: seg[i] = min(nIn-2, max_{i' <= i} f(a[i'])) with f(a) = the first k with a < sC[k+1].  s(t) is
+// monotone in practice, so k_out_segs_par (TP) evaluates f(a[i]) directly from the uniform sites and flags
+// a trajectory when f decreases anywhere; only flagged trajectories take the sequential walk (T) after it.
+__host__ __device__ __forceinline__ int first_seg_uniform(double res, int nIn, double a) {
+  const int last = nIn - 2;
+  int k = 0;
+  const double g = a / res;  // estimate only: corrected against the products the reference compares with
+  if (g > 0.0) k = (g < (double)last) ? (int)g : last;
+  while (k > 0 && a < res * (double)k) k--;
+  while (k < last && !(a < res * (double)(k + 1))) k++;
+  return k;
+}
+__global__ void k_out_segs_par(Ws w, int npts, int nb) {
+  TP_DECOMP(nb);
+  if (i >= npts) return;
+  TrajState &s = w.st[w.b0 + bl];
+  if (s.status & ST_FATAL_MASK) return;
+  if (i >= s.nOver) return;
+  const size_t at = (size_t)i * w.Bo + bl;
+  const double a = w.sOut[at];
+  const int nIn = s.nPtsC;
+  const double res = s.sresC;
+  const int k = first_seg_uniform(res, nIn, a);
+  if (i > 0) {
+    const int kp = first_seg_uniform(res, nIn, w.sOut[at - w.Bo]);
+    if (kp > k) s.segWalk = 1;  // the running maximum differs from f here: sequential walk needed
+  }
+  w.segO[at] = k;
+  const double lo = res * (double)k, hiEdge = res * (double)(k + 1);
+  w.tauO[at] = (a - lo) / (hiEdge - lo);
+}
 __global__ void k_out_segs(Ws w) {
   const int bl = blockIdx.x * blockDim.x + threadIdx.x;
   if (bl >= w.Bo) return;
-  const TrajState &s = w.st[w.b0 + bl];
+  TrajState &s = w.st[w.b0 + bl];
   if (s.status & ST_FATAL_MASK) return;
+  if (!s.segWalk) return;  // k_out_segs_par's result stands
+  s.segWalk = 0;
   const int nIn = s.nPtsC;
   const double res = s.sresC;
   int cur = 0;
@@ -215,38 +248,41 @@ __global__ void k_out_segs(Ws w) {
   }
 }
 
-// theta(t) / cart(t) at the oversampled sites (ba.cpp:1713-1742) (TP).  Rows that are not
-// path-driven are filled by the kinematics kernel afterwards (or are the generic robot's zeros).
+// theta(t) / cart(t) at the oversampled sites (ba.cpp:1713-1742).  One thread per (point, trajectory, row),
+// rows fastest: the four knot gathers and the store of a point are contiguous R*8-byte runs.  Rows that are
+// not path-driven are filled by the kinematics kernel afterwards (or are the generic robot's zeros).
 __global__ void k_out_eval(Ws w, int npts, int nb) {
-  TP_DECOMP(nb);
-  if (i >= npts) return;
+  const long long t_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int R = w.R;
+  const int r = (int)(t_ % R);
+  const long long pb = t_ / R;
+  const int bl = (int)(pb % nb);
+  const int i = (int)(pb / nb);
+  if (i >= w.Oc) return;  // (npts counts rows as well here)
   const int b = w.b0 + bl;
   const TrajState &s = w.st[b];
   if (s.status & ST_FATAL_MASK) return;
   if (i >= s.nOver) return;
   const size_t at = (size_t)i * w.Bo + bl;
-  const int seg = w.segO[at];
-  const double tau = w.tauO[at];
-  const double tau2 = tau * tau, tau3 = tau2 * tau;
-  const int pt = CFG.c.path_type, J = CFG.J;
-  const size_t pst = (size_t)w.B * w.R;
-  const double *y0 = w.P + (size_t)seg * pst + (size_t)b * w.R, *y1 = y0 + pst;
-  const double *m0 = w.M + (size_t)seg * pst + (size_t)b * w.R, *m1 = m0 + pst;
-  double *o = w.O5 + at * w.R;
-  for (int r = 0; r < CFG.R; ++r) {
-    const bool isJ = r < J;
-    const bool driven = isJ ? (pt == BATOTP_JOINT || pt == BATOTP_BOTH) : (pt == BATOTP_CART || pt == BATOTP_BOTH);
-    double v = 0.0;
-    if (driven) {
-      Seg4 c;
-      c.c3 = (m1[r] - m0[r]) / 6.0;
-      c.c2 = m0[r] / 2.0;
-      c.c1 = y1[r] - y0[r] - (m1[r] + 2 * m0[r]) / 6.0;
-      c.c0 = y0[r];
-      v = seg_value(c, tau, tau2, tau3);
-    }  // non-driven rows: filled by the kinematics kernel; the generic robot's Cartesian rows are zeros
-    o[r] = v;
+  const int pt = CFG.c.path_type;
+  const bool isJ = r < CFG.J;
+  const bool driven = isJ ? (pt == BATOTP_JOINT || pt == BATOTP_BOTH) : (pt == BATOTP_CART || pt == BATOTP_BOTH);
+  double v = 0.0;
+  if (driven) {
+    const int seg = w.segO[at];
+    const double tau = w.tauO[at];
+    const double tau2 = tau * tau, tau3 = tau2 * tau;
+    const size_t pst = (size_t)w.B * R;
+    const size_t k0 = (size_t)seg * pst + (size_t)b * R + r;
+    const double y0 = w.P[k0], y1 = w.P[k0 + pst], m0 = w.M[k0], m1 = w.M[k0 + pst];
+    Seg4 c;
+    c.c3 = sdiv::div6(m1 - m0);
+    c.c2 = m0 / 2.0;
+    c.c1 = y1 - y0 - sdiv::div6(m1 + 2 * m0);
+    c.c0 = y0;
+    v = seg_value(c, tau, tau2, tau3);
   }
+  w.O5[at * R + r] = v;
 }
 
 // Torque branch, part 1 (ba.cpp:1746-1765 / 1807-1812): values and time derivatives of the
