@@ -230,14 +230,42 @@ struct ProfScope {
       (h)->launches++;                                                                      \
     }                                                                                       \
   } while (0)
-// (trajectory, point) kernels: npts x nb threads; the kernel receives (..., npts, nb) last
+// (trajectory, point) kernels: a 3-D grid, x over the nb trajectories (fastest), y/z over the points; the
+// kernel receives (..., npts, nb) last and decomposes with TP_DECOMP
+inline void tp_dims(long long fast, long long slow, dim3 &grid, dim3 &block) {
+  int bdx = 128;
+  if (fast < 128) {
+    bdx = 32;
+    while (bdx < fast) bdx <<= 1;
+  }
+  const int bdy = 128 / bdx;
+  const long long rows = (slow + bdy - 1) / bdy;
+  const long long gy = std::min<long long>(rows, 32768);
+  const long long gz = (rows + gy - 1) / gy;
+  grid = dim3((unsigned)((fast + bdx - 1) / bdx), (unsigned)gy, (unsigned)gz);
+  block = dim3(bdx, bdy, 1);
+}
 #define LAUNCH_TP(h, kern, npts, nb, ...)                                                   \
   do {                                                                                      \
-    const long long tot_ = (long long)(npts) * (long long)(nb);                             \
-    if (tot_ > 0) {                                                                         \
+    const long long np_ = (long long)(npts), nb_ = (long long)(nb);                         \
+    if (np_ > 0 && nb_ > 0) {                                                               \
+      dim3 g_, b_;                                                                          \
+      tp_dims(nb_, np_, g_, b_);                                                            \
       ProfScope ps_((h), #kern);                                                            \
-      BATOTP_LAUNCH(kern, dim3((unsigned)((tot_ + 127) / 128)), dim3(128), (h)->stream,     \
-                    __VA_ARGS__, (int)(npts), (int)(nb));                                   \
+      BATOTP_LAUNCH(kern, g_, b_, (h)->stream, __VA_ARGS__, (int)np_, (int)nb_);            \
+      g_check_launch();                                                                     \
+      (h)->launches++;                                                                      \
+    }                                                                                       \
+  } while (0)
+// (point, trajectory) kernels with points fastest (PT_DECOMP)
+#define LAUNCH_PT(h, kern, npts, nb, ...)                                                   \
+  do {                                                                                      \
+    const long long np_ = (long long)(npts), nb_ = (long long)(nb);                         \
+    if (np_ > 0 && nb_ > 0) {                                                               \
+      dim3 g_, b_;                                                                          \
+      tp_dims(np_, nb_, g_, b_);                                                            \
+      ProfScope ps_((h), #kern);                                                            \
+      BATOTP_LAUNCH(kern, g_, b_, (h)->stream, __VA_ARGS__, (int)np_, (int)nb_);            \
       g_check_launch();                                                                     \
       (h)->launches++;                                                                      \
     }                                                                                       \
@@ -445,6 +473,10 @@ void set_cfg(batotp_ctx *h, const batotp_cfg *cfg) {
                            {0, 0, 0, 0, -5103. / 18656, -2187. / 6784},
                            {0, 0, 0, 0, 0, 11. / 84}};  // ba.cpp:58-63, literals as written there
   memcpy(d.B, Bt, sizeof(Bt));
+  for (int i = 0; i < MAXD; ++i) {
+    d.accMaxF[i] = (float)cfg->jnt_acc_max[i];
+    d.velMaxF[i] = (float)std::fabs(cfg->jnt_vel_max[i]);
+  }
   if (!h->haveCfg || memcmp(&h->cfg.c, cfg, sizeof(batotp_cfg)) != 0) {
     h->hwNc = 0;  // capacity high-water marks belong to one configuration
     h->hwSc = 0;
@@ -792,7 +824,7 @@ void do_interp_output(batotp_ctx *h, int b0, int Bo) {
   LAUNCH_TP(h, k_out_s, w.Oc, Bo, w);
   LAUNCH_TP(h, k_out_segs_par, w.Oc, Bo, w);
   LAUNCH_T(h, k_out_segs, Bo, w);
-  LAUNCH_TP(h, k_out_eval, (long long)w.Oc * c.R, Bo, w);
+  LAUNCH_TP(h, k_out_eval, w.Oc, (long long)Bo * c.R, w);
   apply_kinematics(h, 2);
   double *cur = w.O5;
   int curCap = w.Oc;
@@ -825,9 +857,9 @@ void do_interp_output(batotp_ctx *h, int b0, int Bo) {
     if (c.trqOn) thomas_rows(h, trqCur, w.TrqM, Bo, b0, c.J, MAXD, 2, 0);
   }
   const bool strictQuat = (c.C == 7 && c.c.trig_mode == 1);
-  LAUNCH_TP(h, k_out_pack, w.OutC, Bo, w, cur, w.OM, trqCur, w.TrqM, h->d_thetaOut, h->d_cartOut, h->d_trqOut,
+  LAUNCH_PT(h, k_out_pack, w.OutC, Bo, w, cur, w.OM, trqCur, w.TrqM, h->d_thetaOut, h->d_cartOut, h->d_trqOut,
             strictQuat ? h->d_cartOutD : (double *)nullptr, h->d_outD);
-  LAUNCH_TP(h, k_pack_hist, w.Sc, Bo, w, h->d_histOut);
+  LAUNCH_PT(h, k_pack_hist, w.Sc, Bo, w, h->d_histOut);
   h->phase = 4;
 }
 

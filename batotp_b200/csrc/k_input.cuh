@@ -112,11 +112,18 @@ struct ViewSites {
   __host__ __device__ __forceinline__ double operator()(int k) const { return a[k]; }
 };
 
-// (trajectory, point) decomposition with trajectories fastest: nb trajectories per point
+// (trajectory, point) decomposition with trajectories fastest.  The launch (LAUNCH_TP) uses a 3-D grid:
+// x covers the nb trajectories of a point (blockDim.x lanes), y/z the points (blockDim.y per block), so no
+// thread pays a 64-bit division to find its indices.
 #define TP_DECOMP(nb)                                                                      \
-  const long long t_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;                   \
-  const int bl = (int)(t_ % (nb));                                                         \
-  const int i = (int)(t_ / (nb))
+  const int bl = (int)(blockIdx.x * blockDim.x + threadIdx.x);                             \
+  const int i = (int)((blockIdx.z * gridDim.y + blockIdx.y) * blockDim.y + threadIdx.y);   \
+  if (bl >= (nb)) return
+// (point, trajectory) decomposition with points fastest (row-contiguous float outputs)
+#define PT_DECOMP(npts)                                                                    \
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);                              \
+  const int bl = (int)((blockIdx.z * gridDim.y + blockIdx.y) * blockDim.y + threadIdx.y);  \
+  if (i >= (npts)) return
 
 // ----------------------------------------------------------------------------- load (TP)
 // trajReadBIN / trajReadCSV payload -> FP64 rows (ba.cpp:2283-2299, 2417-2437)

@@ -252,13 +252,13 @@ __global__ void k_out_segs(Ws w) {
 // rows fastest: the four knot gathers and the store of a point are contiguous R*8-byte runs.  Rows that are
 // not path-driven are filled by the kinematics kernel afterwards (or are the generic robot's zeros).
 __global__ void k_out_eval(Ws w, int npts, int nb) {
-  const long long t_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // x covers (trajectory, row) pairs, rows fastest; nb = Bo * R
   const int R = w.R;
-  const int r = (int)(t_ % R);
-  const long long pb = t_ / R;
-  const int bl = (int)(pb % nb);
-  const int i = (int)(pb / nb);
-  if (i >= w.Oc) return;  // (npts counts rows as well here)
+  const int xr = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  const int i = (int)((blockIdx.z * gridDim.y + blockIdx.y) * blockDim.y + threadIdx.y);
+  if (xr >= nb) return;
+  const int bl = xr / R, r = xr - bl * R;
+  if (i >= npts) return;
   const int b = w.b0 + bl;
   const TrajState &s = w.st[b];
   if (s.status & ST_FATAL_MASK) return;
@@ -471,9 +471,7 @@ __host__ __device__ inline void q2aa_dev(const double q[4], double aa[3]) {
 // points fastest so that the float rows are written coalesced)
 __global__ void k_out_pack(Ws w, double *src, double *srcM, double *trqSrc, double *trqM, float *thetaOut,
                            float *cartOut, float *trqOut, double *cartOutD, double *outD, int npts, int nb) {
-  const long long t_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = (int)(t_ % npts);
-  const int bl = (int)(t_ / npts);
+  PT_DECOMP(npts);
   if (bl >= nb) return;
   const TrajState &s = w.st[w.b0 + bl];
   const int J = CFG.J, C = CFG.C, Cin = CFG.Cin;
@@ -552,9 +550,7 @@ __global__ void k_out_pack(Ws w, double *src, double *srcM, double *trqSrc, doub
 // s-sdot histories in sdotWrite order (ascending s for the reverse sweep) as float32 (TP over Sc,
 // points fastest); also clears the switching flags beyond the recorded steps.
 __global__ void k_pack_hist(Ws w, float *histOut, int npts, int nb) {
-  const long long t_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = (int)(t_ % npts);
-  const int bl = (int)(t_ / npts);
+  PT_DECOMP(npts);
   if (bl >= nb) return;
   if (i >= w.Sc) return;
   const int b = w.b0 + bl;
