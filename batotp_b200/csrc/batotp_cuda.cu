@@ -168,7 +168,7 @@ struct batotp_ctx {
   double *o_mS = nullptr, *o_sOut = nullptr, *o_tauO = nullptr, *o_O5 = nullptr, *o_OA = nullptr, *o_OM = nullptr;
   double *o_OD = nullptr, *o_OD2 = nullptr, *o_Trq = nullptr, *o_Trq2 = nullptr, *o_TrqM = nullptr;
   int *o_segO = nullptr;
-  bool keepF64 = false, capKeep = false;
+  bool keepF64 = false, capKeep = false, capFused = false;
   // which buffers hold the final rows after interp_output
   // high-water marks so that steady-state chunks need no planning sync
   int hwNc = 0, hwSc = 0;
@@ -338,6 +338,12 @@ bool smooth_uniform_on(const batotp_ctx *h) {
   return sm > 1.5;
 }
 
+int kin_mode(const batotp_ctx *h, int where);
+// the oversampled output rows feed nothing but the smoothing stage (do_interp_output's fused path)
+bool fused_out(const batotp_ctx *h) {
+  return !h->cfg.trqOn && smooth_uniform_on(h) && kin_mode(h, 2) == 0 && (int)h->cfg.c.out_smooth_fact <= 11;
+}
+
 int final_cap(const batotp_ctx *h, int Sc, int Os) {
   const batotp_cfg &c = h->cfg.c;
   const double integMax = c.is_auto_integ_res ? 0.2 : c.integ_res;
@@ -402,7 +408,7 @@ void ensure_out(batotp_ctx *h, int Bo) {
   if (!trq && smooth_uniform_on(h)) Os = (int)(Oc / c.c.out_smooth_fact) + 16;
   const int OutC = final_cap(h, Sc, Os);
   if (!(Bo <= h->capBo && Oc <= h->capOc && Os <= h->capOs && OutC <= h->capOutC && Sc == h->capOSc &&
-        h->keepF64 == h->capKeep)) {
+        h->keepF64 == h->capKeep && fused_out(h) == h->capFused && c.R == h->capR && trq == h->capTrq)) {
     free_out(h);
     const size_t b = (size_t)Bo;
     const int R = c.R;
@@ -410,7 +416,7 @@ void ensure_out(batotp_ctx *h, int Bo) {
     h->o_sOut = out_alloc<double>(h, b * Oc);
     h->o_segO = out_alloc<int>(h, b * Oc);
     h->o_tauO = out_alloc<double>(h, b * Oc);
-    h->o_O5 = out_alloc<double>(h, b * R * Oc);
+    h->o_O5 = out_alloc<double>(h, fused_out(h) ? 8 : b * R * Oc);  // untouched on the fused path
     h->o_OA = out_alloc<double>(h, b * R * Os);
     h->o_OM = out_alloc<double>(h, b * R * Os);
     h->o_OD = h->o_OD2 = h->o_Trq = h->o_Trq2 = h->o_TrqM = nullptr;
@@ -433,6 +439,7 @@ void ensure_out(batotp_ctx *h, int Bo) {
     h->capOutC = OutC;
     h->capOSc = Sc;
     h->capKeep = h->keepF64;
+    h->capFused = fused_out(h);
     ensure_tabs(h, std::max(std::max(w.Nc, Sc), Oc) + 8);
   }
   w.Oc = h->capOc;
@@ -584,14 +591,9 @@ void host_rows_apply(batotp_ctx *h, double *base, int npts, int nb, int b0, bool
 }
 
 // kinematics after a resampling stage (ba.cpp:245-280 mode 0; ba.cpp:616-632 mode 1; ba.cpp:1723-1741 mode 2)
-void apply_kinematics(batotp_ctx *h, int where) {
+int kin_mode(const batotp_ctx *h, int where) {
   const DevCfg &c = h->cfg;
   const int pt = c.c.path_type;
-  const bool over = (where == 2);
-  double *base = over ? h->w.O5 : h->w.P;
-  const int npts = over ? h->w.Oc : h->w.Nc;
-  const int nb = over ? h->w.Bo : h->w.B;
-  const int b0 = over ? h->w.b0 : 0;
   int mode = 0;
   if (pt == BATOTP_JOINT) {
     if (where == 0)
@@ -606,6 +608,17 @@ void apply_kinematics(batotp_ctx *h, int where) {
       mode = 2;
     if (mode == 2 && c.c.robot_type != BATOTP_CSPR3DOF) mode = 0;
   }
+  return mode;
+}
+
+void apply_kinematics(batotp_ctx *h, int where) {
+  const DevCfg &c = h->cfg;
+  const bool over = (where == 2);
+  double *base = over ? h->w.O5 : h->w.P;
+  const int npts = over ? h->w.Oc : h->w.Nc;
+  const int nb = over ? h->w.Bo : h->w.B;
+  const int b0 = over ? h->w.b0 : 0;
+  const int mode = kin_mode(h, where);
   if (mode == 0) return;
   if (mode == 1 && c.c.trig_mode == 1) {
     host_rows_apply(h, base, npts, nb, b0, over, 1);
@@ -824,29 +837,37 @@ void do_interp_output(batotp_ctx *h, int b0, int Bo) {
   LAUNCH_TP(h, k_out_s, w.Oc, Bo, w);
   LAUNCH_TP(h, k_out_segs_par, w.Oc, Bo, w);
   LAUNCH_T(h, k_out_segs, Bo, w);
-  LAUNCH_TP(h, k_out_eval, w.Oc, (long long)Bo * c.R, w);
-  apply_kinematics(h, 2);
   double *cur = w.O5;
   int curCap = w.Oc;
-  if (c.trqOn) {
-    // re-spline theta(t) (and cart(t) for the parallel robot) to get time derivatives
-    thomas_rows(h, w.O5, w.OM, Bo, b0, c.c.is_parallel ? c.R : c.J, c.R, 1, c.c.is_parallel ? 0 : 1);
-    LAUNCH_TP(h, k_out_knot_eval, w.Oc, Bo, w);
-    if (!c.c.is_parallel && c.c.trig_mode == 1)
-      host_dyn_rr_out(h);
-    else
-      LAUNCH_TP(h, k_out_trq, w.Oc, Bo, w, h->pm);
-    cur = w.OA;
-  }
-  LAUNCH_T(h, k_out_smooth_plan, Bo, w);
   double *trqCur = w.Trq;
-  if (smooth_uniform_on(h) || c.c.is_auto_integ_res) {
-    double *dst = (cur == w.O5) ? w.OA : w.O5;
-    const int dstCap = (cur == w.O5) ? w.Os : w.Oc;
-    LAUNCH_TP(h, k_out_smooth, std::min(curCap, dstCap), Bo, w, cur, dst);
-    cur = dst;
-    curCap = dstCap;
-    trqCur = w.Trq2;
+  if (fused_out(h)) {
+    // the oversampled rows have no other consumer: evaluate, smooth and decimate in one pass (O5 is not touched)
+    LAUNCH_T(h, k_out_smooth_plan, Bo, w);
+    LAUNCH_TP(h, k_out_eval_smooth, w.Os, (long long)Bo * c.R, w, w.OA);
+    cur = w.OA;
+    curCap = w.Os;
+  } else {
+    LAUNCH_TP(h, k_out_eval, w.Oc, (long long)Bo * c.R, w);
+    apply_kinematics(h, 2);
+    if (c.trqOn) {
+      // re-spline theta(t) (and cart(t) for the parallel robot) to get time derivatives
+      thomas_rows(h, w.O5, w.OM, Bo, b0, c.c.is_parallel ? c.R : c.J, c.R, 1, c.c.is_parallel ? 0 : 1);
+      LAUNCH_TP(h, k_out_knot_eval, w.Oc, Bo, w);
+      if (!c.c.is_parallel && c.c.trig_mode == 1)
+        host_dyn_rr_out(h);
+      else
+        LAUNCH_TP(h, k_out_trq, w.Oc, Bo, w, h->pm);
+      cur = w.OA;
+    }
+    LAUNCH_T(h, k_out_smooth_plan, Bo, w);
+    if (smooth_uniform_on(h) || c.c.is_auto_integ_res) {
+      double *dst = (cur == w.O5) ? w.OA : w.O5;
+      const int dstCap = (cur == w.O5) ? w.Os : w.Oc;
+      LAUNCH_TP(h, k_out_smooth, std::min(curCap, dstCap), Bo, w, cur, dst);
+      cur = dst;
+      curCap = dstCap;
+      trqCur = w.Trq2;
+    }
   }
   LAUNCH_T(h, k_out_final_plan, Bo, w);
   // natural splines of the rows for the final resample (ba.cpp:1889-1915; used where isReinterp).

@@ -351,7 +351,7 @@ __global__ void k_out_trq(Ws w, Pmat pm, int npts, int nb) {
 // ----------------------------------------------------------------------------- smoothing (TP)
 // util.cpp:254-288 evaluated pointwise: x2[p] for a row of length n, window w (valid for n >= 2*wMid).
 template <class V>
-__host__ __device__ __forceinline__ double smooth_at(const V &x, int n, int wIn, int p) {
+__host__ __device__ __forceinline__ double smooth_at(V &&x, int n, int wIn, int p) {
   int w = imin_(wIn, n);
   const int wMid = w / 2 + w % 2 - 1;
   w = 2 * wMid + 1;
@@ -432,6 +432,85 @@ __global__ void k_out_smooth(Ws w, double *src, double *dst, int npts, int nb) {
         v = x[i];
       trqv(w.Trq2, w, bl, r)[i] = v;
     }
+}
+
+// Fused evaluation + smoothing + decimation (ba.cpp:1713-1742 then 1838-1871) for runs whose oversampled rows
+// have no other consumer (no torque branch, no kinematics at the output sites, smoothing on for the whole
+// batch): one thread per (decimated point, trajectory, row) evaluates the 2*wMid+2 oversampled values its
+// two smoothing windows need — the same seg_value expressions k_out_eval forms, summed in smooth()'s
+// order — so the oversampled rows (the largest array of the output phase) never travel through HBM.
+struct OverEval {  // x[j]: row r of trajectory b at oversampled site j; caches the segment coefficients
+  const Ws *w;
+  int bl, cseg;
+  size_t rowOff;  // b * R + r
+  Seg4 c;
+  int base, nval;
+  double vals[12];
+  __host__ __device__ __forceinline__ double eval(int j) {
+    const size_t at = (size_t)j * w->Bo + bl;
+    const int sg = w->segO[at];
+    const double ta = w->tauO[at];
+    if (sg != cseg) {
+      const size_t pst = (size_t)w->B * w->R;
+      const size_t k0 = (size_t)sg * pst + rowOff;
+      const double y0 = w->P[k0], y1 = w->P[k0 + pst], m0 = w->M[k0], m1 = w->M[k0 + pst];
+      c.c3 = sdiv::div6(m1 - m0);
+      c.c2 = m0 / 2.0;
+      c.c1 = y1 - y0 - sdiv::div6(m1 + 2 * m0);
+      c.c0 = y0;
+      cseg = sg;
+    }
+    const double ta2 = ta * ta, ta3 = ta2 * ta;
+    return seg_value(c, ta, ta2, ta3);
+  }
+  __host__ __device__ __forceinline__ double operator[](int j) {
+    if (j >= base && j < base + nval) return vals[j - base];
+    return eval(j);
+  }
+};
+__global__ void k_out_eval_smooth(Ws w, double *dst, int npts, int nb) {
+  // x covers (trajectory, row) pairs, rows fastest (nb = Bo * R); y/z the decimated points
+  const int R = w.R;
+  const int xr = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  const int i = (int)((blockIdx.z * gridDim.y + blockIdx.y) * blockDim.y + threadIdx.y);
+  if (xr >= nb) return;
+  const int bl = xr / R, r = xr - bl * R;
+  if (i >= npts) return;
+  const int b = w.b0 + bl;
+  const TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  if (i >= s.nSm) return;
+  const int pt = CFG.c.path_type;
+  const bool isJ = r < CFG.J;
+  const bool driven = isJ ? (pt == BATOTP_JOINT || pt == BATOTP_BOTH) : (pt == BATOTP_CART || pt == BATOTP_BOTH);
+  double v = 0.0;  // non-driven rows are zeros here (generic robot), and smoothing zeros gives zeros
+  if (driven) {
+    const int nIn = s.nOver, nOut = s.nSm;
+    const int wv = (int)s.outSmooth;
+    const double aOut = ((double)(nIn - 1) / (double)(nOut - 1)) * (double)i;
+    UniformSites in{1.0};
+    const int seg = find_seg(in, nIn, aOut);
+    const double tau = (aOut - (double)seg) / ((double)(seg + 1) - (double)seg);
+    OverEval X;
+    X.w = &w;
+    X.bl = bl;
+    X.cseg = -1;
+    X.rowOff = (size_t)b * R + r;
+    X.base = 0;
+    X.nval = 0;
+    // the two windows [seg-wMid, seg+wMid] and [seg+1-wMid, seg+1+wMid], evaluated once
+    int ww = imin_(wv, nIn);
+    const int wMid = ww / 2 + ww % 2 - 1;
+    const int lo = imax_(seg - wMid, 0), hi = imin_(seg + 1 + wMid, nIn - 1);
+    if (hi - lo + 1 <= 12) {
+      for (int j = lo; j <= hi; ++j) X.vals[j - lo] = X.eval(j);
+      X.base = lo;
+      X.nval = hi - lo + 1;
+    }
+    const double v0 = smooth_at(X, nIn, wv, seg), v1 = smooth_at(X, nIn, wv, seg + 1);
+    v = v0 + (v1 - v0) * tau;
+  }
+  dst[((size_t)i * w.Bo + bl) * R + r] = v;
 }
 
 // ----------------------------------------------------------------------------- final (T + TP)
