@@ -149,7 +149,7 @@ struct batotp_ctx {
   std::vector<void *> outAllocs;  // output sub-chunk arrays
   int outChunk = 8192;            // trajectories per output pass
   // Thomas factor tables
-  double *d_cN = nullptr, *d_cC = nullptr;
+  double *d_cN = nullptr;  // Thomas tables (ensure_tabs)
   int tabN = 0;
   Pmat pm;
   // staged inputs
@@ -298,21 +298,32 @@ T *out_alloc(batotp_ctx *h, size_t count) {
 void ensure_tabs(batotp_ctx *h, int n) {
   if (n <= h->tabN) return;
   g_free(h->d_cN);
-  g_free(h->d_cC);
   n = std::max(n + 64, 4096);
-  std::vector<double> cN(n, 1.0), cC(n, 1.0);
+  // [cN | dN | rN | cC | dC | rC], n doubles each
+  std::vector<double> t((size_t)6 * n, 1.0);
+  double *cN = t.data(), *dN = cN + n, *rN = dN + n, *cC = rN + n, *dC = cC + n, *rC = dC + n;
   // spline.cpp:259-268 (natural) and 229-237 (clamped): the same divisions, tabulated
   cN[0] = 1.0;
   if (n > 1) cN[1] = 1.0 / 4.0;
   for (int i = 2; i < n; ++i) cN[i] = 1.0 / (4.0 - 1.0 * cN[i - 1]);
   cC[0] = 1.0 / 2.0;
   for (int i = 1; i < n; ++i) cC[i] = 1.0 / (4.0 - 1.0 * cC[i - 1]);
-  h->d_cN = (double *)g_alloc(n * sizeof(double));
-  h->d_cC = (double *)g_alloc(n * sizeof(double));
-  g_h2d(h->d_cN, cN.data(), n * sizeof(double), h->stream);
-  g_h2d(h->d_cC, cC.data(), n * sizeof(double), h->stream);
+  // denominators of row i and their correctly rounded reciprocals (for sdiv::div)
+  for (int i = 1; i < n; ++i) {
+    dN[i] = 4.0 - 1.0 * cN[i - 1];
+    rN[i] = 1.0 / dN[i];
+    dC[i] = 4.0 - 1.0 * cC[i - 1];
+    rC[i] = 1.0 / dC[i];
+  }
+  h->d_cN = (double *)g_alloc((size_t)6 * n * sizeof(double));
+  g_h2d(h->d_cN, t.data(), (size_t)6 * n * sizeof(double), h->stream);
   g_sync(h->stream);
   h->tabN = n;
+}
+inline ThomasTabs thomas_tabs(const batotp_ctx *h) {
+  const double *p = h->d_cN;
+  const size_t n = (size_t)h->tabN;
+  return ThomasTabs{p, p + n, p + 2 * n, p + 3 * n, p + 4 * n, p + 5 * n};
 }
 
 int oversample_cap(const batotp_ctx *h, int Sc) {
@@ -629,7 +640,7 @@ void apply_kinematics(batotp_ctx *h, int where) {
 
 void thomas_rows(batotp_ctx *h, double *src, double *dst, int nb, int b0, int rows, int rowsPerTraj, int nsel,
                  int clamped) {
-  ThomasTabs t{h->d_cN, h->d_cC};
+  const ThomasTabs t = thomas_tabs(h);
   LAUNCH_T(h, k_thomas_rows, nb * rows, h->w, src, dst, nb, b0, rows, rowsPerTraj, nsel, clamped, t);
 }
 
@@ -832,7 +843,7 @@ void do_interp_output(batotp_ctx *h, int b0, int Bo) {
   Ws &w = h->w;
   w.b0 = b0;
   w.Bo = Bo;
-  ThomasTabs t{h->d_cN, h->d_cC};
+  const ThomasTabs t = thomas_tabs(h);
   LAUNCH_T(h, k_out_plan, Bo, w, t);
   LAUNCH_TP(h, k_out_s, w.Oc, Bo, w);
   LAUNCH_TP(h, k_out_segs_par, w.Oc, Bo, w);
@@ -843,7 +854,17 @@ void do_interp_output(batotp_ctx *h, int b0, int Bo) {
   if (fused_out(h)) {
     // the oversampled rows have no other consumer: evaluate, smooth and decimate in one pass (O5 is not touched)
     LAUNCH_T(h, k_out_smooth_plan, Bo, w);
-    LAUNCH_TP(h, k_out_eval_smooth, w.Os, (long long)Bo * c.R, w, w.OA);
+    {
+      const int wv = (int)c.c.out_smooth_fact;  // smooth()'s window half-width (util.cpp:261-263) when the row is long enough
+      const int wMid = wv / 2 + wv % 2 - 1;
+      switch (wMid) {
+        case 1: LAUNCH_TP(h, k_out_eval_smooth<1>, w.Os, (long long)Bo * c.R, w, w.OA); break;
+        case 2: LAUNCH_TP(h, k_out_eval_smooth<2>, w.Os, (long long)Bo * c.R, w, w.OA); break;
+        case 3: LAUNCH_TP(h, k_out_eval_smooth<3>, w.Os, (long long)Bo * c.R, w, w.OA); break;
+        case 4: LAUNCH_TP(h, k_out_eval_smooth<4>, w.Os, (long long)Bo * c.R, w, w.OA); break;
+        default: LAUNCH_TP(h, k_out_eval_smooth<5>, w.Os, (long long)Bo * c.R, w, w.OA); break;  // others: generic path
+      }
+    }
     cur = w.OA;
     curCap = w.Os;
   } else {
@@ -957,6 +978,10 @@ __global__ void k_selftest_div(unsigned long long seed, int perThread, unsigned 
       const double q0 = __dmul_rn(a, rc.r);
       const double q = __fma_rn(rc.r, __fma_rn(-b, q0, a), q0);
       if (rc.ok && sdiv::exp_ok(a) && sdiv::exp_ok(q)) fast++;
+      // the tabulated-reciprocal form of the Thomas recurrences: r = RN(1/b) formed by an IEEE division
+      const sdiv::Rcp rt = {1.0 / b, rc.ok};
+      const double q3 = sdiv::div(a, b, rt);
+      if (__double_as_longlong(q3) != __double_as_longlong(q2) && !(q3 != q3 && q2 != q2)) bad++;
       // the constant-divisor form used by the spline coefficients
       const double s1 = sdiv::div6(a), s2 = a / 6.0;
       if (__double_as_longlong(s1) != __double_as_longlong(s2) && !(s1 != s1 && s2 != s2)) bad++;
@@ -1011,7 +1036,6 @@ int batotp_cuda_destroy(batotp_handle h) {
   free_ws(h);
   free_out(h);
   g_free(h->d_cN);
-  g_free(h->d_cC);
   g_free(h->d_theta);
   g_free(h->d_cart);
   g_free(h->d_ts);

@@ -12,18 +12,22 @@
 // Thomas elimination factors depend only on the row index, so they are tabulated once on the
 // host with the very divisions spline.cpp performs:  natural (spline.cpp:259-268):
 // cN[1]=1/4, cN[i]=1/(4-cN[i-1]);  clamped (spline.cpp:229-237): cC[0]=1/2, cC[i]=1/(4-cC[i-1]).
+// The elimination denominators 4 - c[i-1] are tabulated with them, together with their correctly rounded
+// reciprocals, so that the recurrence divides through sdiv::div (the same quotient as '/', a third of the
+// dependent latency).
 struct ThomasTabs {
-  const double *cN;
-  const double *cC;
+  const double *cN, *dN, *rN;  // natural: factor, denominator of row i, RN(1/denominator)
+  const double *cC, *dC, *rC;  // clamped (rows with diagonal 4)
 };
 
 // spline.cpp:168-211 + 252-276: y[n] -> second-derivative solution m[n] ("natural", quirk Q4)
 template <class VY, class VM>
-__host__ __device__ inline void thomas_natural(const VY &y, const VM &m, int npts, const double *cN) {
+__host__ __device__ inline void thomas_natural(const VY &y, const VM &m, int npts, const ThomasTabs &tb) {
   const int n = npts - 1;
   m[0] = 0.0;
   m[npts - 1] = 0.0;
   const double a = 1.0, b = 4.0;
+  const double *cN = tb.cN;
   // rhs and forward elimination in one pass (each m[i] depends on y[i-1..i+1] and m[i-1] only)
   double ym = y[0], yc = y[1], prev = 0.0;
   for (int i = 1; i < npts - 1; ++i) {
@@ -32,7 +36,7 @@ __host__ __device__ inline void thomas_natural(const VY &y, const VM &m, int npt
     if (i == 1)
       v /= b;
     else
-      v = (v - a * prev) / (b - a * cN[i - 1]);
+      v = sdiv::div(v - a * prev, tb.dN[i], sdiv::Rcp{tb.rN[i], true});  // (v - a*prev) / (b - a*cN[i-1])
     m[i] = v;
     prev = v;
     ym = yc;
@@ -49,8 +53,9 @@ __host__ __device__ inline void thomas_natural(const VY &y, const VM &m, int npt
 
 // spline.cpp:225-243 ("clamped": b0=b_{n-1}=2, back-substitution starts at n-3, quirk Q4)
 template <class VY, class VM>
-__host__ __device__ inline void thomas_clamped(const VY &y, const VM &m, int n, const double *cC) {
+__host__ __device__ inline void thomas_clamped(const VY &y, const VM &m, int n, const ThomasTabs &tb) {
   const double a = 1.0;
+  const double *cC = tb.cC;
   double prev = 0.0 / 2.0;
   m[0] = prev;
   double ym = y[0], yc = y[1];
@@ -62,8 +67,11 @@ __host__ __device__ inline void thomas_clamped(const VY &y, const VM &m, int n, 
       ym = yc;
       yc = yp;
     }
-    const double bi = (i == n - 1) ? 2.0 : 4.0;
-    const double v = (rhs - a * prev) / (bi - a * cC[i - 1]);
+    double v;
+    if (i == n - 1)
+      v = (rhs - a * prev) / (2.0 - a * cC[i - 1]);
+    else
+      v = sdiv::div(rhs - a * prev, tb.dC[i], sdiv::Rcp{tb.rC[i], true});  // / (4.0 - a*cC[i-1])
     m[i] = v;
     prev = v;
   }
@@ -625,9 +633,9 @@ __global__ void k_thomas_rows(Ws w, double *src, double *dst, int nb, int b0, in
   const size_t st = (size_t)nb * rowsPerTraj, off = (size_t)bl * rowsPerTraj + row;
   const RV y{src + off, st}, m{dst + off, st};
   if (clamped)
-    thomas_clamped(y, m, n, tabs.cC);
+    thomas_clamped(y, m, n, tabs);
   else
-    thomas_natural(y, m, n, tabs.cN);
+    thomas_natural(y, m, n, tabs);
 }
 
 // ----------------------------------------------------------------------------- interpSpecial (T)
@@ -716,9 +724,9 @@ __global__ void k_march(Ws w) {
         double *qo = Q + (size_t)CurNewPt * pst;
         for (int j = 0; j < J; ++j) {
           Seg4 c;
-          c.c3 = (m1[j] - m0[j]) / 6.0;
+          c.c3 = sdiv::div6(m1[j] - m0[j]);
           c.c2 = m0[j] / 2.0;
-          c.c1 = y1[j] - y0[j] - (m1[j] + 2 * m0[j]) / 6.0;
+          c.c1 = y1[j] - y0[j] - sdiv::div6(m1[j] + 2 * m0[j]);
           c.c0 = y0[j];
           const double v = seg_value(c, tau, tau2, tau3);
           qo[j] = v;
@@ -728,9 +736,9 @@ __global__ void k_march(Ws w) {
           for (int j = 0; j < C; ++j) {
             const int r = J + j;
             Seg4 c;
-            c.c3 = (m1[r] - m0[r]) / 6.0;
+            c.c3 = sdiv::div6(m1[r] - m0[r]);
             c.c2 = m0[r] / 2.0;
-            c.c1 = y1[r] - y0[r] - (m1[r] + 2 * m0[r]) / 6.0;
+            c.c1 = y1[r] - y0[r] - sdiv::div6(m1[r] + 2 * m0[r]);
             c.c0 = y0[r];
             cartpt[j] = seg_value(c, tau, tau2, tau3);
           }

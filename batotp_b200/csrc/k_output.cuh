@@ -154,7 +154,7 @@ __global__ void k_out_plan(Ws w, ThomasTabs tabs) {
   }
   double *sF = w.hist + (size_t)b * 4 * w.Sc + 2 * (size_t)w.Sc;
   const RV y{sF, 1}, m{w.mS + (size_t)bl * w.Sc, 1};
-  thomas_natural(y, m, s.nFwd, tabs.cN);
+  thomas_natural(y, m, s.nFwd, tabs);
 }
 
 // tMVCout[i] (ba.cpp:1693-1699) -> s at that time (TP)
@@ -440,20 +440,18 @@ __global__ void k_out_smooth(Ws w, double *src, double *dst, int npts, int nb) {
 // two smoothing windows need — the same seg_value expressions k_out_eval forms, summed in smooth()'s
 // order — so the oversampled rows (the largest array of the output phase) never travel through HBM.
 struct OverEval {  // x[j]: row r of trajectory b at oversampled site j; caches the segment coefficients
-  const Ws *w;
-  int bl, cseg;
-  size_t rowOff;  // b * R + r
+  const double *P, *M, *tauO;
+  const int *segO;
+  size_t pst, rowOff;  // B * R;  b * R + r
+  int Bo, bl, cseg;
   Seg4 c;
-  int base, nval;
-  double vals[12];
-  __host__ __device__ __forceinline__ double eval(int j) {
-    const size_t at = (size_t)j * w->Bo + bl;
-    const int sg = w->segO[at];
-    const double ta = w->tauO[at];
+  __host__ __device__ __forceinline__ double operator[](int j) {
+    const size_t at = (size_t)j * Bo + bl;
+    const int sg = segO[at];
+    const double ta = tauO[at];
     if (sg != cseg) {
-      const size_t pst = (size_t)w->B * w->R;
       const size_t k0 = (size_t)sg * pst + rowOff;
-      const double y0 = w->P[k0], y1 = w->P[k0 + pst], m0 = w->M[k0], m1 = w->M[k0 + pst];
+      const double y0 = P[k0], y1 = P[k0 + pst], m0 = M[k0], m1 = M[k0 + pst];
       c.c3 = sdiv::div6(m1 - m0);
       c.c2 = m0 / 2.0;
       c.c1 = y1 - y0 - sdiv::div6(m1 + 2 * m0);
@@ -463,11 +461,9 @@ struct OverEval {  // x[j]: row r of trajectory b at oversampled site j; caches 
     const double ta2 = ta * ta, ta3 = ta2 * ta;
     return seg_value(c, ta, ta2, ta3);
   }
-  __host__ __device__ __forceinline__ double operator[](int j) {
-    if (j >= base && j < base + nval) return vals[j - base];
-    return eval(j);
-  }
 };
+// WM = wMid of smooth() (util.cpp:262): the window is 2*WM+1 points
+template <int WM>
 __global__ void k_out_eval_smooth(Ws w, double *dst, int npts, int nb) {
   // x covers (trajectory, row) pairs, rows fastest (nb = Bo * R); y/z the decimated points
   const int R = w.R;
@@ -491,23 +487,27 @@ __global__ void k_out_eval_smooth(Ws w, double *dst, int npts, int nb) {
     UniformSites in{1.0};
     const int seg = find_seg(in, nIn, aOut);
     const double tau = (aOut - (double)seg) / ((double)(seg + 1) - (double)seg);
-    OverEval X;
-    X.w = &w;
-    X.bl = bl;
-    X.cseg = -1;
-    X.rowOff = (size_t)b * R + r;
-    X.base = 0;
-    X.nval = 0;
-    // the two windows [seg-wMid, seg+wMid] and [seg+1-wMid, seg+1+wMid], evaluated once
+    OverEval X{w.P, w.M, w.tauO, w.segO, (size_t)w.B * R, (size_t)b * R + r, w.Bo, bl, -1, Seg4{0, 0, 0, 0}};
     int ww = imin_(wv, nIn);
     const int wMid = ww / 2 + ww % 2 - 1;
-    const int lo = imax_(seg - wMid, 0), hi = imin_(seg + 1 + wMid, nIn - 1);
-    if (hi - lo + 1 <= 12) {
-      for (int j = lo; j <= hi; ++j) X.vals[j - lo] = X.eval(j);
-      X.base = lo;
-      X.nval = hi - lo + 1;
+    double v0, v1;
+    if (wMid == WM && seg >= WM && seg + 1 < nIn - WM) {
+      // both windows are interior (util.cpp:268-273): their 2*WM+2 sites are evaluated once, in registers
+      double x[2 * WM + 2];
+#pragma unroll
+      for (int q = 0; q < 2 * WM + 2; ++q) x[q] = X[seg - WM + q];
+      double t0 = 0, t1 = 0;
+#pragma unroll
+      for (int q = 0; q < 2 * WM + 1; ++q) {
+        t0 += x[q];
+        t1 += x[q + 1];
+      }
+      v0 = t0 / (2 * WM + 1);
+      v1 = t1 / (2 * WM + 1);
+    } else {
+      v0 = smooth_at(X, nIn, wv, seg);
+      v1 = smooth_at(X, nIn, wv, seg + 1);
     }
-    const double v0 = smooth_at(X, nIn, wv, seg), v1 = smooth_at(X, nIn, wv, seg + 1);
     v = v0 + (v1 - v0) * tau;
   }
   dst[((size_t)i * w.Bo + bl) * R + r] = v;
