@@ -28,15 +28,40 @@ __host__ __device__ inline void thomas_natural(const VY &y, const VM &m, int npt
   m[npts - 1] = 0.0;
   const double a = 1.0, b = 4.0;
   const double *cN = tb.cN;
-  // rhs and forward elimination in one pass (each m[i] depends on y[i-1..i+1] and m[i-1] only)
+  // rhs and forward elimination in one pass (each m[i] depends on y[i-1..i+1] and m[i-1] only).  The loads
+  // do not depend on the recurrence: they are issued four rows ahead of it.
   double ym = y[0], yc = y[1], prev = 0.0;
-  for (int i = 1; i < npts - 1; ++i) {
+  int i = 1;
+  for (; i + 3 < npts - 1; i += 4) {
+    const double y1 = y[i + 1], y2 = y[i + 2], y3 = y[i + 3], y4 = y[i + 4];
+    const double d1 = tb.dN[i], d2 = tb.dN[i + 1], d3 = tb.dN[i + 2], d4 = tb.dN[i + 3];
+    const double r1 = tb.rN[i], r2 = tb.rN[i + 1], r3 = tb.rN[i + 2], r4 = tb.rN[i + 3];
+    double v = 6 * (ym - 2 * yc + y1);
+    if (i == 1)
+      v /= b;
+    else
+      v = sdiv::div(v - a * prev, d1, sdiv::Rcp{r1, true});  // (v - a*prev) / (b - a*cN[i-1])
+    m[i] = v;
+    prev = v;
+    v = sdiv::div(6 * (yc - 2 * y1 + y2) - a * prev, d2, sdiv::Rcp{r2, true});
+    m[i + 1] = v;
+    prev = v;
+    v = sdiv::div(6 * (y1 - 2 * y2 + y3) - a * prev, d3, sdiv::Rcp{r3, true});
+    m[i + 2] = v;
+    prev = v;
+    v = sdiv::div(6 * (y2 - 2 * y3 + y4) - a * prev, d4, sdiv::Rcp{r4, true});
+    m[i + 3] = v;
+    prev = v;
+    ym = y3;
+    yc = y4;
+  }
+  for (; i < npts - 1; ++i) {
     const double yp = y[i + 1];
     double v = 6 * (ym - 2 * yc + yp);
     if (i == 1)
       v /= b;
     else
-      v = sdiv::div(v - a * prev, tb.dN[i], sdiv::Rcp{tb.rN[i], true});  // (v - a*prev) / (b - a*cN[i-1])
+      v = sdiv::div(v - a * prev, tb.dN[i], sdiv::Rcp{tb.rN[i], true});
     m[i] = v;
     prev = v;
     ym = yc;
@@ -44,9 +69,26 @@ __host__ __device__ inline void thomas_natural(const VY &y, const VM &m, int npt
   }
   double last = (0.0 - a * prev) / (b - a * cN[n - 1]);  // the last unknown is an ordinary row with rhs 0
   m[n] = last;
-  for (int i = n; i > 1; --i) {
-    const double v = m[i - 1] - cN[i - 1] * last;
-    m[i - 1] = v;
+  int k = n;
+  for (; k - 4 >= 1; k -= 4) {  // rows k-1 .. k-4
+    const double m1 = m[k - 1], m2 = m[k - 2], m3 = m[k - 3], m4 = m[k - 4];
+    const double c1 = cN[k - 1], c2 = cN[k - 2], c3 = cN[k - 3], c4 = cN[k - 4];
+    double v = m1 - c1 * last;
+    m[k - 1] = v;
+    last = v;
+    v = m2 - c2 * last;
+    m[k - 2] = v;
+    last = v;
+    v = m3 - c3 * last;
+    m[k - 3] = v;
+    last = v;
+    v = m4 - c4 * last;
+    m[k - 4] = v;
+    last = v;
+  }
+  for (; k > 1; --k) {
+    const double v = m[k - 1] - cN[k - 1] * last;
+    m[k - 1] = v;
     last = v;
   }
 }

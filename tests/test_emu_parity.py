@@ -86,3 +86,20 @@ def test_per_sample_mvc_matches_oracle(ctx):
         want = o.mvc_per_sample(1.0e3)
         assert np.array_equal(got[b, :len(want)], want)
         assert want.min() > 0 and want.max() < 1.0e3
+
+
+def test_sweep_filters_decide_nearly_everything(ctx):
+    """The sweep kernel takes the bisection decisions from float enclosures and falls back to the exact code
+    when they do not separate.  Results are exact either way (checked above); this guards the speed path:
+    the fallbacks must stay rare, otherwise the kernel silently degenerates into the all-exact one."""
+    import ctypes as C
+    out = (C.c_longlong * 8)()
+    ctx.L.batotp_emu_filter_stats(out, 8, 1)
+    cfg, tres, th, ca = P.load_synth("GEN7DOF", 100, 8)
+    P.run_device(ctx, cfg, tres, th, ca)
+    ctx.L.batotp_emu_filter_stats(out, 8, 1)
+    certain, exact, b_joint, b_exact, v_skip, v_one, v_all = list(out)[:7]
+    assert certain > 100000
+    assert exact < 0.01 * certain        # decisions deferred to the exact verification
+    assert b_exact < 0.001 * b_joint     # bounds that needed all joints instead of the certified one
+    assert v_all < 0.001 * (v_skip + v_one + 1)

@@ -128,7 +128,9 @@ def test_device_trig_mode_is_within_tolerance(ctx):
     assert abs(int(fast.n_fwd[0]) - int(strict.n_fwd[0])) <= 8
     assert abs(fast.t_total[0] - strict.t_total[0]) / strict.t_total[0] < 2e-3
     n = min(int(fast.n_out[0]), int(strict.n_out[0]))
-    assert np.abs(fast.theta_out[0, :, :n] - strict.theta_out[0, :, :n]).max() < 0.5  # degrees, over a 20 s move
+    # degrees over a 20 s move: a timing shift of a few integration steps (allowed above) at joint speeds of
+    # some tens of deg/s moves theta(t) by up to ~1 degree at a fixed output index
+    assert np.abs(fast.theta_out[0, :, :n] - strict.theta_out[0, :, :n]).max() < 2.0
 
 
 def test_shared_reciprocal_division_is_ieee(ctx):
@@ -140,3 +142,36 @@ def test_shared_reciprocal_division_is_ieee(ctx):
         assert bad == 0
         total_fast += fast
     assert total_fast > 1_000_000_000  # the fast path really is what gets exercised
+
+
+def test_large_batch_matches_oracle_bit_for_bit(ctx):
+    """4096 GEN7DOF paths (BASELINE configs[2] size) through the C-ABI against the oracle restatement run on
+    the host cores: switching counts, total time and every float32 output sample.  The sweep kernel takes its
+    bisection decisions from certified float enclosures and forms only the binding quotients exactly; a wrong
+    certificate anywhere would change a step count here (the algorithm is chaotic at the last bit)."""
+    import ctypes as C
+    import os
+    from _oracle import orc_lib
+    from batotp_b200 import synth
+    from batotp_b200.config import read_config
+    cfg, _ = read_config(os.path.join(P.GOLD, "synthetic", "GEN7DOF_config.dat"))
+    B = 4096
+    tres, th = synth.gen7dof_paths(500000, B)
+    out_cap = 3200
+    res = native.BatchResult(B, cfg.n_joints, 0, out_cap, 0, False, want_rows=True, want_hist=False)
+    ctx.set_chunk(4096)
+    ctx.optimize_batch(cfg, ctx.make_in(theta=th, tres=tres), res)
+    ctx.set_chunk(16384)
+    L = orc_lib()
+    tt = np.zeros(B)
+    nr, nf, no, st = (np.zeros(B, np.int32) for _ in range(4))
+    rows = np.zeros((B, cfg.n_joints, out_cap), np.float32)
+    fp, dp, ip = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int)
+    L.orc_batch_run(C.byref(cfg), B, th.shape[2], tres, th.ctypes.data_as(fp), None, os.cpu_count() or 1,
+                    tt.ctypes.data_as(dp), nr.ctypes.data_as(ip), nf.ctypes.data_as(ip), no.ctypes.data_as(ip),
+                    st.ctypes.data_as(ip), rows.ctypes.data_as(fp), out_cap)
+    assert (res.status & native.ST_FATAL_MASK == 0).all() and (st == 0).all()
+    assert np.array_equal(res.n_rev, nr) and np.array_equal(res.n_fwd, nf) and np.array_equal(res.n_out, no)
+    assert np.array_equal(res.t_total, tt)
+    assert int(no.max()) <= out_cap
+    assert np.array_equal(res.theta_out, rows)
