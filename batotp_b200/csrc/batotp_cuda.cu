@@ -73,6 +73,8 @@ inline void g_d2d_2d(void *d, size_t dp, const void *s0, size_t sp, size_t width
   CU_CHECK(cudaMemcpy2DAsync(d, dp, s0, sp, width, rows, cudaMemcpyDeviceToDevice, s));
 }
 inline void g_sync(cudaStream_t s) { CU_CHECK(cudaStreamSynchronize(s)); }
+inline void g_event_record(cudaEvent_t e, cudaStream_t s) { CU_CHECK(cudaEventRecord(e, s)); }
+inline void g_stream_wait(cudaStream_t s, cudaEvent_t e) { CU_CHECK(cudaStreamWaitEvent(s, e, 0)); }
 inline void g_set_cfg(const DevCfg &c, cudaStream_t s) {
   CU_CHECK(cudaMemcpyToSymbolAsync(g_cfg, &c, sizeof(DevCfg), 0, cudaMemcpyHostToDevice, s));
 }
@@ -97,6 +99,9 @@ inline void g_d2d_2d(void *d, size_t dp, const void *s0, size_t sp, size_t width
   copy2d(d, dp, s0, sp, width, rows);
 }
 inline void g_sync(cudaStream_t) {}
+typedef int cudaEvent_t;
+inline void g_event_record(cudaEvent_t, cudaStream_t) {}
+inline void g_stream_wait(cudaStream_t, cudaEvent_t) {}
 inline void g_set_cfg(const DevCfg &c, cudaStream_t) { g_cfg = c; }
 inline void g_check_launch() {}
 #endif
@@ -137,7 +142,7 @@ struct batotp_ctx {
   int device = 0;
   cudaStream_t stream = 0;
   std::string err;
-  int chunk = 16384;
+  int chunk = 0;  // trajectories per resident chunk; 0 = automatic (auto_chunk)
   long launches = 0;
   DevCfg cfg;
   bool haveCfg = false;
@@ -156,13 +161,18 @@ struct batotp_ctx {
   void *d_theta = nullptr, *d_cart = nullptr;
   double *d_ts = nullptr, *d_tres = nullptr;
   int *d_n0 = nullptr;
-  size_t capIn = 0;
+  size_t capIn = 0, capInB = 0, capInTs = 0;
   const void *in_theta = nullptr, *in_cart = nullptr;  // device views used by k_in_load
   const double *in_ts = nullptr;
   bool inF64 = false, hasTheta = false, hasCart = false;
   int B = 0, n0max = 0;
   // staged outputs
-  float *d_thetaOut = nullptr, *d_cartOut = nullptr, *d_trqOut = nullptr, *d_histOut = nullptr;
+  float *d_thetaOut = nullptr, *d_cartOut = nullptr, *d_trqOut = nullptr, *d_histOut = nullptr;  // current set
+  // two sets of packed-output staging buffers: the rows of sub-chunk k travel to the host on the copy stream
+  // while the kernels of sub-chunk k+1 fill the other set
+  float *o_thetaOut[2] = {nullptr, nullptr}, *o_cartOut[2] = {nullptr, nullptr}, *o_trqOut[2] = {nullptr, nullptr},
+        *o_histOut[2] = {nullptr, nullptr};
+  cudaStream_t copyStream = 0;
   double *d_cartOutD = nullptr;
   double *d_outD = nullptr;  // [Bo][R+J][OutC] FP64 final rows (keepF64)
   double *o_mS = nullptr, *o_sOut = nullptr, *o_tauO = nullptr, *o_O5 = nullptr, *o_OA = nullptr, *o_OM = nullptr;
@@ -184,7 +194,10 @@ struct batotp_ctx {
   std::map<std::string, std::pair<double, long>> prof;
 #ifndef BATOTP_HOST_EMU
   cudaEvent_t evS0 = nullptr, evS1 = nullptr, evT[2] = {nullptr, nullptr}, evP[2] = {nullptr, nullptr};
+  cudaEvent_t evOut[2] = {nullptr, nullptr}, evCopied[2] = {nullptr, nullptr};
   bool sweepPending = false;
+#else
+  cudaEvent_t evOut[2] = {0, 0}, evCopied[2] = {0, 0};
 #endif
 };
 
@@ -408,6 +421,13 @@ void ensure_ws(batotp_ctx *h, int B, int Nc, int Sc) {
   ensure_tabs(h, std::max(Nc, Sc) + 8);
 }
 
+void select_out_set(batotp_ctx *h, int q) {
+  h->d_thetaOut = h->o_thetaOut[q];
+  h->d_cartOut = h->o_cartOut[q];
+  h->d_trqOut = h->o_trqOut[q];
+  h->d_histOut = h->o_histOut[q];
+}
+
 // output sub-chunk arrays, sized from the step capacity of the resident chunk
 void ensure_out(batotp_ctx *h, int Bo) {
   const DevCfg &c = h->cfg;
@@ -438,11 +458,14 @@ void ensure_out(batotp_ctx *h, int Bo) {
       h->o_Trq2 = out_alloc<double>(h, b * MAXD * Oc);
       h->o_TrqM = out_alloc<double>(h, b * MAXD * Oc);
     }
-    h->d_thetaOut = out_alloc<float>(h, b * c.J * OutC);
-    h->d_cartOut = out_alloc<float>(h, b * std::max(c.Cin, 1) * OutC);
-    h->d_trqOut = trq ? out_alloc<float>(h, b * c.J * OutC) : nullptr;
+    for (int q = 0; q < 2; ++q) {
+      h->o_thetaOut[q] = out_alloc<float>(h, b * c.J * OutC);
+      h->o_cartOut[q] = out_alloc<float>(h, b * std::max(c.Cin, 1) * OutC);
+      h->o_trqOut[q] = trq ? out_alloc<float>(h, b * c.J * OutC) : nullptr;
+      h->o_histOut[q] = out_alloc<float>(h, b * 4 * Sc);
+    }
+    select_out_set(h, 0);
     h->d_cartOutD = (c.C == 7) ? out_alloc<double>(h, b * 7 * OutC) : nullptr;
-    h->d_histOut = out_alloc<float>(h, b * 4 * Sc);
     h->d_outD = h->keepF64 ? out_alloc<double>(h, b * (R + c.J) * OutC) : nullptr;
     h->capBo = Bo;
     h->capOc = Oc;
@@ -715,19 +738,21 @@ void stage_inputs(batotp_ctx *h, const batotp_batch_in *in, int first, int B) {
   std::vector<double> tres(B);
   for (int b = 0; b < B; ++b) tres[b] = in->tres ? in->tres[first + b] : in->tres_all;
   const size_t need = std::max(thBytes, caBytes);
-  if (need > h->capIn || !h->d_tres) {
+  if (need > h->capIn || (size_t)B > h->capInB || (size_t)B * n0 > h->capInTs || !h->d_tres) {
     g_free(h->d_theta);
     g_free(h->d_cart);
     g_free(h->d_ts);
     g_free(h->d_tres);
     g_free(h->d_n0);
-    const size_t capB = (size_t)std::max(h->chunk, B);
+    const size_t capB = (size_t)B;
     h->d_theta = g_alloc(capB * c.J * n0 * 8);
     h->d_cart = g_alloc(capB * std::max(c.Cin, 1) * n0 * 8);
     h->d_ts = (double *)g_alloc(capB * n0 * 8);
     h->d_tres = (double *)g_alloc(capB * 8);
     h->d_n0 = (int *)g_alloc(capB * 4);
     h->capIn = capB * (size_t)std::max(c.J, c.Cin) * n0 * 8;
+    h->capInB = capB;
+    h->capInTs = capB * (size_t)n0;
   }
   ProfScope ps_(h, "copy_h2d(stage)");
   g_h2d(h->d_tres, tres.data(), (size_t)B * 8, h->stream);
@@ -1021,10 +1046,17 @@ int batotp_cuda_create(int device, batotp_handle *out) {
   h->device = device;
   memset(&h->w, 0, sizeof(h->w));
 #ifndef BATOTP_HOST_EMU
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
     return -1;
   }
+  for (int q = 0; q < 2; ++q)
+    if (cudaEventCreateWithFlags(&h->evOut[q], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->evCopied[q], cudaEventDisableTiming) != cudaSuccess) {
+      delete h;
+      return -1;
+    }
 #endif
   h->pm = make_pmat();
   *out = h;
@@ -1043,6 +1075,11 @@ int batotp_cuda_destroy(batotp_handle h) {
   g_free(h->d_n0);
 #ifndef BATOTP_HOST_EMU
   cudaStreamDestroy(h->stream);
+  cudaStreamDestroy(h->copyStream);
+  for (int q = 0; q < 2; ++q) {
+    if (h->evOut[q]) cudaEventDestroy(h->evOut[q]);
+    if (h->evCopied[q]) cudaEventDestroy(h->evCopied[q]);
+  }
 #endif
   delete h;
   return 0;
@@ -1051,7 +1088,7 @@ int batotp_cuda_destroy(batotp_handle h) {
 const char *batotp_cuda_last_error(batotp_handle h) { return h ? h->err.c_str() : "null handle"; }
 
 int batotp_cuda_set_chunk(batotp_handle h, int chunk) {
-  if (!h || chunk < 1) return -1;
+  if (!h || chunk < 0) return -1;
   h->chunk = chunk;
   return 0;
 }
@@ -1212,6 +1249,21 @@ int batotp_cuda_timer(batotp_handle h, int which, double *elapsed_ms) {
 #endif
 }
 
+// The sweep kernel keeps one trajectory per lane resident for a whole sweep (SMs x SW_MIN_BLOCKS CTAs of
+// SW_NT lanes); a chunk larger than that leaves a thin second wave running on its own.  Automatic chunking
+// splits the batch into the fewest equal chunks that fit the resident lanes.
+static int auto_chunk(batotp_handle h, int B) {
+  int sms = 148;
+#ifndef BATOTP_HOST_EMU
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+#else
+  (void)h;
+#endif
+  const int lanes = sms * SW_MIN_BLOCKS * SW_NT;
+  const int n = std::max(1, cdiv(B, lanes));
+  return std::max(SW_NT, cdiv(cdiv(B, n), SW_NT) * SW_NT);
+}
+
 static int load_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_in *in, int first, int B) {
 #ifndef BATOTP_HOST_EMU
   CU_CHECK(cudaSetDevice(h->device));
@@ -1350,20 +1402,15 @@ int batotp_cuda_interp_output(batotp_handle h) {
   }
 }
 
-// copy the results of the current output sub-chunk [w.b0, w.b0+w.Bo) to the caller's buffers;
-// `first` = index of the resident chunk's first trajectory in the caller's batch
-static void fetch_sub(batotp_handle h, batotp_batch_out *out, int first) {
-  const DevCfg &c = h->cfg;
+// per-trajectory scalars of the chunk trajectories [b0, b0+Bo) -> the caller's arrays (synchronous, small)
+static void fetch_scalars(batotp_handle h, batotp_batch_out *out, int first, int b0, int Bo) {
   const Ws &w = h->w;
-  const int Bo = w.Bo, g0 = first + w.b0;
-  ProfScope ps_(h, "copy_d2h(fetch)");
   h->hst.resize(h->B);
-  g_d2h(h->hst.data() + w.b0, w.st + w.b0, (size_t)Bo * sizeof(TrajState), h->stream);
+  g_d2h(h->hst.data() + b0, w.st + b0, (size_t)Bo * sizeof(TrajState), h->stream);
   g_sync(h->stream);
-  if (out->on_device) throw Err{"batotp_batch_out.on_device is not implemented yet"};
   for (int bl = 0; bl < Bo; ++bl) {
-    const TrajState &s = h->hst[w.b0 + bl];
-    const int g = g0 + bl;
+    const TrajState &s = h->hst[b0 + bl];
+    const int g = first + b0 + bl;
     if (out->status) out->status[g] = s.status;
     if (out->n_rev) out->n_rev[g] = s.nRev;
     if (out->n_fwd) out->n_fwd[g] = s.nFwd;
@@ -1375,28 +1422,44 @@ static void fetch_sub(batotp_handle h, batotp_batch_out *out, int first) {
     if (out->s_last_sec) out->s_last_sec[g] = s.sLastSec;
     if (out->out_sres) out->out_sres[g] = s.sresOut;
   }
+}
+
+// packed float32 rows / histories / flags of the current output sub-chunk -> the caller's buffers, enqueued
+// on stream `cs` (the staging set is the one selected when the sub-chunk was packed)
+static void fetch_rows(batotp_handle h, batotp_batch_out *out, int first, cudaStream_t cs) {
+  const DevCfg &c = h->cfg;
+  const Ws &w = h->w;
+  const int Bo = w.Bo, g0 = first + w.b0;
   const int oc = out->out_cap, wc = std::min(out->out_cap, w.OutC);
   if (out->theta_out && oc > 0)
     g_d2h_2d(out->theta_out + (size_t)g0 * c.J * oc, (size_t)oc * 4, h->d_thetaOut, (size_t)w.OutC * 4,
-             (size_t)wc * 4, (size_t)Bo * c.J, h->stream);
+             (size_t)wc * 4, (size_t)Bo * c.J, cs);
   if (out->trq_out && oc > 0 && c.trqOn)
     g_d2h_2d(out->trq_out + (size_t)g0 * c.J * oc, (size_t)oc * 4, h->d_trqOut, (size_t)w.OutC * 4,
-             (size_t)wc * 4, (size_t)Bo * c.J, h->stream);
-  if (out->cart_out && oc > 0 && c.Cin > 0) {
-    if (c.C == 7 && c.c.trig_mode == 1) {
-      host_q2aa_out(h, out, g0);
-    } else {
-      g_d2h_2d(out->cart_out + (size_t)g0 * c.Cin * oc, (size_t)oc * 4, h->d_cartOut, (size_t)w.OutC * 4,
-               (size_t)wc * 4, (size_t)Bo * c.Cin, h->stream);
-    }
-  }
+             (size_t)wc * 4, (size_t)Bo * c.J, cs);
+  if (out->cart_out && oc > 0 && c.Cin > 0 && !(c.C == 7 && c.c.trig_mode == 1))
+    g_d2h_2d(out->cart_out + (size_t)g0 * c.Cin * oc, (size_t)oc * 4, h->d_cartOut, (size_t)w.OutC * 4,
+             (size_t)wc * 4, (size_t)Bo * c.Cin, cs);
   const int hc = out->hist_cap, hw = std::min(out->hist_cap, w.Sc);
   if (out->hist && hc > 0)
     g_d2h_2d(out->hist + (size_t)g0 * 4 * hc, (size_t)hc * 4, h->d_histOut, (size_t)w.Sc * 4, (size_t)hw * 4,
-             (size_t)Bo * 4, h->stream);
+             (size_t)Bo * 4, cs);
   if (out->flags && hc > 0)
     g_d2h_2d(out->flags + (size_t)g0 * 2 * hc, (size_t)hc, w.flags + (size_t)w.b0 * 2 * w.Sc, (size_t)w.Sc,
-             (size_t)hw, (size_t)Bo * 2, h->stream);
+             (size_t)hw, (size_t)Bo * 2, cs);
+}
+
+// copy the results of the current output sub-chunk [w.b0, w.b0+w.Bo) to the caller's buffers;
+// `first` = index of the resident chunk's first trajectory in the caller's batch
+static void fetch_sub(batotp_handle h, batotp_batch_out *out, int first) {
+  const DevCfg &c = h->cfg;
+  const Ws &w = h->w;
+  ProfScope ps_(h, "copy_d2h(fetch)");
+  if (out->on_device) throw Err{"batotp_batch_out.on_device is not implemented yet"};
+  fetch_scalars(h, out, first, w.b0, w.Bo);
+  fetch_rows(h, out, first, h->stream);
+  if (out->cart_out && out->out_cap > 0 && c.Cin > 0 && c.C == 7 && c.c.trig_mode == 1)
+    host_q2aa_out(h, out, first + w.b0);
   g_sync(h->stream);
 }
 
@@ -1416,16 +1479,39 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
   if (!h || !cfg || !in || !out) return -1;
   try {
     bool first = true;
-    for (int at = 0; at < in->B; at += h->chunk) {
-      const int B = std::min(h->chunk, in->B - at);
+    const int chunk = h->chunk > 0 ? h->chunk : auto_chunk(h, in->B);
+    for (int at = 0; at < in->B; at += chunk) {
+      const int B = std::min(chunk, in->B - at);
       if (load_chunk(h, first ? cfg : nullptr, in, at, B) != 0) return -1;
       first = false;
       h->lastHaveN0 = in->n0 != nullptr;
       if (chunk_interp_input(h, h->lastHaveN0) != 0) return -1;
       if (chunk_sweeps_output(h, h->lastHaveN0) != 0) return -1;
-      for (int b0 = 0; b0 < B; b0 += h->outChunk) {
-        do_interp_output(h, b0, std::min(h->outChunk, B - b0));
-        fetch_sub(h, out, at);
+      const DevCfg &c = h->cfg;
+      const bool strictQuatOut = out->cart_out && out->out_cap > 0 && c.Cin > 0 && c.C == 7 && c.c.trig_mode == 1;
+      if (out->on_device) throw Err{"batotp_batch_out.on_device is not implemented yet"};
+      if (strictQuatOut || h->profile) {  // host post-processing per sub-chunk / serialised measurement
+        for (int b0 = 0; b0 < B; b0 += h->outChunk) {
+          do_interp_output(h, b0, std::min(h->outChunk, B - b0));
+          fetch_sub(h, out, at);
+        }
+      } else {
+        // rows of sub-chunk k go to the host on the copy stream while sub-chunk k+1 is computed into the
+        // other staging set
+        int k = 0;
+        for (int b0 = 0; b0 < B; b0 += h->outChunk, ++k) {
+          const int q = k & 1;
+          ensure_out(h, std::max(std::min(h->outChunk, B - b0), h->capBo));
+          if (k >= 2) g_stream_wait(h->stream, h->evCopied[q]);  // set q has reached the host
+          select_out_set(h, q);
+          do_interp_output(h, b0, std::min(h->outChunk, B - b0));
+          g_event_record(h->evOut[q], h->stream);
+          g_stream_wait(h->copyStream, h->evOut[q]);
+          fetch_rows(h, out, at, h->copyStream);
+          g_event_record(h->evCopied[q], h->copyStream);
+        }
+        fetch_scalars(h, out, at, 0, B);
+        g_sync(h->copyStream);
       }
     }
     return 0;

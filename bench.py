@@ -51,7 +51,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=131072, help="paths per GPU per step")
-    ap.add_argument("--chunk", type=int, default=65536, help="paths resident per device pass (input interp + sweeps)")
+    ap.add_argument("--chunk", type=int, default=0,
+                    help="paths resident per device pass (input interp + sweeps); 0 = the library's automatic split")
     ap.add_argument("--out-chunk", type=int, default=8192, help="paths per output-interpolation pass")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -281,7 +282,13 @@ def main_b200(args):
     launches_value = st["launches"]
 
     # ---- e2e: pinned host inputs in, float32 trajectories out, slice by slice ----------
-    sl = min(args.chunk, B)  # one C-ABI call per resident chunk, results of a call land in one reusable pinned buffer
+    # one C-ABI call per resident chunk; the results of a call land in one reusable pinned buffer
+    if args.chunk > 0:
+        sl = min(args.chunk, B)
+    else:  # the library's automatic split (batotp_cuda.cu auto_chunk): fewest equal chunks within SMs*3*128 lanes
+        lanes = torch.cuda.get_device_properties(local).multi_processor_count * 3 * 128
+        nch = max(1, -(-B // lanes))
+        sl = max(128, -(-(-(-B // nch)) // 128) * 128)
     out_cap = int(res_s.n_out.max()) + 64 if ok else 4096
     res_e = native.BatchResult(sl, J, 0, out_cap, 0, False, want_rows=True, want_hist=False, pinned=True)
     h_np = h_theta.numpy()
@@ -318,7 +325,7 @@ def main_b200(args):
                     config=dict(workload="GEN7DOF synthetic spline paths (generateGEN7DOFpath.m recipe: 20 knots "
                                          "U[0,5]^7 -> not-a-knot spline -> 400 pts, seeded), stock GEN7DOF config.dat "
                                          "(joint vel 5 / acc 10 limits, integRes 0.01, outRes 0.008, outSmoothFact 5)",
-                                paths_per_gpu=B, paths_total=world * B, chunk=args.chunk,
+                                paths_per_gpu=B, paths_total=world * B, chunk=(args.chunk or sl),
                                 parallelism="independent slices per GPU, no collective",
                                 l2="inputs (%.0f MB/GPU) and per-chunk tables exceed the 126 MB L2" % (theta.nbytes / 1e6),
                                 optimised=ok, mean_rk_steps=steps_rk / ntraj, mean_verifies_per_stage=ver / max(6 * steps_rk, 1)),
