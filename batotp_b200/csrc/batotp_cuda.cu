@@ -32,6 +32,7 @@ namespace {
 
 struct Err {
   std::string msg;
+  bool oom = false;  // a device allocation failed: the batch call retries with smaller chunks
 };
 
 #ifndef BATOTP_HOST_EMU
@@ -47,7 +48,15 @@ struct Err {
   } while (0)
 inline void *g_alloc(size_t bytes) {
   void *p = nullptr;
-  CU_CHECK(cudaMalloc(&p, bytes ? bytes : 8));
+  const cudaError_t e = cudaMalloc(&p, bytes ? bytes : 8);
+  if (e != cudaSuccess) {
+    cudaGetLastError();  // not sticky: clear it
+    char buf[256];
+    snprintf(buf, sizeof buf, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    Err er{buf};
+    er.oom = (e == cudaErrorMemoryAllocation);
+    throw er;
+  }
   return p;
 }
 inline void g_free(void *p) {
@@ -153,6 +162,7 @@ struct batotp_ctx {
   int capBo = 0, capOc = 0, capOs = 0, capOutC = 0, capOSc = 0;
   std::vector<void *> outAllocs;  // output sub-chunk arrays
   int outChunk = 8192;            // trajectories per output pass
+  int maxSteps = 65536;           // largest RK-step capacity the automatic retries grow to (per sweep)
   // Thomas factor tables
   double *d_cN = nullptr;  // Thomas tables (ensure_tabs)
   int tabN = 0;
@@ -179,6 +189,7 @@ struct batotp_ctx {
   double *o_OD = nullptr, *o_OD2 = nullptr, *o_Trq = nullptr, *o_Trq2 = nullptr, *o_TrqM = nullptr;
   int *o_segO = nullptr;
   bool keepF64 = false, capKeep = false, capFused = false;
+  int allocPhase = 0;  // which workspace was being (re)allocated last: 0 chunk arrays, 1 output sub-chunk arrays
   // which buffers hold the final rows after interp_output
   // high-water marks so that steady-state chunks need no planning sync
   int hwNc = 0, hwSc = 0;
@@ -386,6 +397,7 @@ void ensure_ws(batotp_ctx *h, int B, int Nc, int Sc) {
   }
   free_ws(h);
   free_out(h);
+  h->allocPhase = 0;
   Ws &w = h->w;
   memset(&w, 0, sizeof(w));
   const size_t b = (size_t)B;
@@ -441,6 +453,7 @@ void ensure_out(batotp_ctx *h, int Bo) {
   if (!(Bo <= h->capBo && Oc <= h->capOc && Os <= h->capOs && OutC <= h->capOutC && Sc == h->capOSc &&
         h->keepF64 == h->capKeep && fused_out(h) == h->capFused && c.R == h->capR && trq == h->capTrq)) {
     free_out(h);
+    h->allocPhase = 1;
     const size_t b = (size_t)Bo;
     const int R = c.R;
     h->o_mS = out_alloc<double>(h, b * Sc);
@@ -744,6 +757,10 @@ void stage_inputs(batotp_ctx *h, const batotp_batch_in *in, int first, int B) {
     g_free(h->d_ts);
     g_free(h->d_tres);
     g_free(h->d_n0);
+    h->d_theta = h->d_cart = nullptr;
+    h->d_ts = h->d_tres = nullptr;
+    h->d_n0 = nullptr;
+    h->capIn = h->capInB = h->capInTs = 0;
     const size_t capB = (size_t)B;
     h->d_theta = g_alloc(capB * c.J * n0 * 8);
     h->d_cart = g_alloc(capB * std::max(c.Cin, 1) * n0 * 8);
@@ -870,8 +887,15 @@ void do_interp_output(batotp_ctx *h, int b0, int Bo) {
   w.Bo = Bo;
   const ThomasTabs t = thomas_tabs(h);
   LAUNCH_T(h, k_out_plan, Bo, w, t);
-  LAUNCH_TP(h, k_out_s, w.Oc, Bo, w);
-  LAUNCH_TP(h, k_out_segs_par, w.Oc, Bo, w);
+  {  // s(t) at the oversampled sites and their segments, 32x32 tiles
+    const long long rows = cdiv(w.Oc, 32);
+    const long long gy = std::min<long long>(rows, 32768), gz = (rows + gy - 1) / gy;
+    ProfScope ps_(h, "k_out_s_segs");
+    BATOTP_LAUNCH_WARP(k_out_s_segs, dim3((unsigned)cdiv(Bo, 32), (unsigned)gy, (unsigned)gz), dim3(32, 8, 1), 0, h->stream,
+                       w, w.Oc, Bo);
+    g_check_launch();
+    h->launches++;
+  }
   LAUNCH_T(h, k_out_segs, Bo, w);
   double *cur = w.O5;
   int curCap = w.Oc;
@@ -882,6 +906,12 @@ void do_interp_output(batotp_ctx *h, int b0, int Bo) {
     {
       const int wv = (int)c.c.out_smooth_fact;  // smooth()'s window half-width (util.cpp:261-263) when the row is long enough
       const int wMid = wv / 2 + wv % 2 - 1;
+      const bool jointRows = c.c.path_type == BATOTP_JOINT;  // rows 0..J-1 driven, the others zero
+      if (jointRows && wMid == 2 && c.J == 7)
+        LAUNCH_TP(h, (k_out_eval_smooth_rows<2, 7>), w.Os, Bo, w, w.OA);
+      else if (jointRows && wMid == 2 && c.J == 6)
+        LAUNCH_TP(h, (k_out_eval_smooth_rows<2, 6>), w.Os, Bo, w, w.OA);
+      else
       switch (wMid) {
         case 1: LAUNCH_TP(h, k_out_eval_smooth<1>, w.Os, (long long)Bo * c.R, w, w.OA); break;
         case 2: LAUNCH_TP(h, k_out_eval_smooth<2>, w.Os, (long long)Bo * c.R, w, w.OA); break;
@@ -1348,6 +1378,20 @@ static int chunk_sweeps_output(batotp_handle h, bool haveN0) {
       h->hwSc = std::max(h->hwSc, std::min(h->w.Sc, (int)(mxF * 1.25) + 64));
       return 0;
     }
+    // A trajectory that crawls (e.g. an infeasible path whose bisection keeps failing, ba.cpp:1307-1319) runs
+    // until maxIntegTime in the reference.  The step capacity follows it up to maxSteps; beyond that the
+    // trajectory keeps BATOTP_ST_STEP_CAP (reported as not optimised) instead of holding the batch hostage.
+    if ((long long)h->w.Sc * 2 > (long long)h->maxSteps) {
+      for (int b = 0; b < h->B; ++b) {
+        const TrajState &t = h->hst[b];
+        if (t.status & ST_FATAL_MASK) continue;
+        h->cntVerify += t.nVerify;
+        h->cntSteps += (t.nRev - 1) + (t.nFwd - 1);
+        h->cntTraj++;
+      }
+      h->hwSc = std::max(h->hwSc, h->w.Sc);  // the next chunks start with this capacity: one pass each
+      return 0;
+    }
     // grow the step capacity and redo the chunk from the start (the status word is sticky)
     const int Sc = h->w.Sc * 2;
     const int Nc = h->w.Nc;
@@ -1474,19 +1518,14 @@ int batotp_cuda_fetch(batotp_handle h, batotp_batch_out *out) {
   }
 }
 
-int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_in *in,
-                               batotp_batch_out *out) {
-  if (!h || !cfg || !in || !out) return -1;
-  try {
-    bool first = true;
-    const int chunk = h->chunk > 0 ? h->chunk : auto_chunk(h, in->B);
-    for (int at = 0; at < in->B; at += chunk) {
-      const int B = std::min(chunk, in->B - at);
-      if (load_chunk(h, first ? cfg : nullptr, in, at, B) != 0) return -1;
-      first = false;
-      h->lastHaveN0 = in->n0 != nullptr;
-      if (chunk_interp_input(h, h->lastHaveN0) != 0) return -1;
-      if (chunk_sweeps_output(h, h->lastHaveN0) != 0) return -1;
+// one resident chunk [at, at+B) of the caller's batch through the whole path
+static void process_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_in *in, batotp_batch_out *out,
+                          int at, int B) {
+  if (load_chunk(h, cfg, in, at, B) != 0) throw Err{h->err};
+  h->lastHaveN0 = in->n0 != nullptr;
+  if (chunk_interp_input(h, h->lastHaveN0) != 0) throw Err{h->err};
+  if (chunk_sweeps_output(h, h->lastHaveN0) != 0) throw Err{h->err};
+  {
       const DevCfg &c = h->cfg;
       const bool strictQuatOut = out->cart_out && out->out_cap > 0 && c.Cin > 0 && c.C == 7 && c.c.trig_mode == 1;
       if (out->on_device) throw Err{"batotp_batch_out.on_device is not implemented yet"};
@@ -1513,6 +1552,34 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
         fetch_scalars(h, out, at, 0, B);
         g_sync(h->copyStream);
       }
+  }
+}
+
+int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_in *in,
+                               batotp_batch_out *out) {
+  if (!h || !cfg || !in || !out) return -1;
+  try {
+    bool first = true;
+    int chunk = h->chunk > 0 ? h->chunk : auto_chunk(h, in->B);
+    for (int at = 0; at < in->B;) {
+      const int B = std::min(chunk, in->B - at);
+      try {
+        process_chunk(h, first ? cfg : nullptr, in, out, at, B);
+      } catch (const Err &e) {
+        // a workspace did not fit (long paths, many rows): release everything and go on with smaller chunks
+        if (!e.oom || (chunk <= 256 && h->outChunk <= 256)) throw;
+        g_sync(h->stream);
+        g_sync(h->copyStream);
+        free_ws(h);
+        free_out(h);
+        if (h->allocPhase == 1 && std::min(h->outChunk, chunk) > 256)
+          h->outChunk = std::max(256, std::min(h->outChunk, chunk) / 2);
+        else
+          chunk = std::max(256, (chunk / 2 + SW_NT - 1) / SW_NT * SW_NT);
+        continue;
+      }
+      first = false;
+      at += B;
     }
     return 0;
   } catch (const Err &e) {
@@ -1597,6 +1664,12 @@ int batotp_cuda_get_f64(batotp_handle h, const char *name, int traj, int row, do
     h->err = e.msg;
     return -1;
   }
+}
+
+int batotp_cuda_set_max_steps(batotp_handle h, int n) {
+  if (!h || n < 1024) return -1;
+  h->maxSteps = n;
+  return 0;
 }
 
 int batotp_cuda_set_out_chunk(batotp_handle h, int n) {

@@ -115,10 +115,16 @@ struct EmuWarpState {
 };
 struct EmuFiber {
   EmuCtx ctx;
-  std::vector<char> stack;
+  char *stack = nullptr;  // from the per-thread pool below: allocated once, reused by every CTA
   emu_dim3 tid;
   bool finished = false;
 };
+#define EMU_STACK (1 << 19)
+static inline char *emu_stack(int t) {
+  static thread_local std::vector<char *> pool;
+  while ((int)pool.size() <= t) pool.push_back((char *)malloc(EMU_STACK));
+  return pool[t];
+}
 struct EmuCta {
   EmuCtx sched;
   std::vector<EmuFiber> fib;
@@ -140,34 +146,36 @@ template <class F>
 static inline void emu_launch_fibers(dim3 grid, dim3 block, F f) {
   gridDim = grid;
   blockDim = block;
-  const int nt = (int)block.x;
-  for (unsigned bx = 0; bx < grid.x; ++bx) {
-    EmuCta cta;
-    cta.fib.resize(nt);
-    cta.warps.resize((nt + EMU_WARP - 1) / EMU_WARP);
-    cta.body = [](void *a) { (*static_cast<F *>(a))(); };
-    cta.arg = &f;
-    emu_cta = &cta;
-    for (int t = 0; t < nt; ++t) {
-      EmuFiber &fb = cta.fib[t];
-      fb.stack.resize(1 << 19);
-      fb.tid = emu_dim3(t, 0, 0);
-      emu_ctx_make(fb.ctx, fb.stack.data(), fb.stack.size(), emu_fiber_entry);
-    }
-    int live = nt;
-    while (live > 0) {
-      live = 0;
-      for (int t = 0; t < nt; ++t) {
-        if (cta.fib[t].finished) continue;
-        ++live;
-        cta.cur = t;
-        blockIdx = emu_dim3(bx, 0, 0);
-        threadIdx = cta.fib[t].tid;
-        emu_ctx_swap(cta.sched, cta.fib[t].ctx);
+  const int nt = (int)(block.x * block.y);
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        EmuCta cta;
+        cta.fib.resize(nt);
+        cta.warps.resize((nt + EMU_WARP - 1) / EMU_WARP);
+        cta.body = [](void *a) { (*static_cast<F *>(a))(); };
+        cta.arg = &f;
+        emu_cta = &cta;
+        for (int t = 0; t < nt; ++t) {
+          EmuFiber &fb = cta.fib[t];
+          fb.stack = emu_stack(t);
+          fb.tid = emu_dim3(t % block.x, t / block.x, 0);  // linear thread id = ty * blockDim.x + tx, warps of 32
+          emu_ctx_make(fb.ctx, fb.stack, EMU_STACK, emu_fiber_entry);
+        }
+        int live = nt;
+        while (live > 0) {
+          live = 0;
+          for (int t = 0; t < nt; ++t) {
+            if (cta.fib[t].finished) continue;
+            ++live;
+            cta.cur = t;
+            blockIdx = emu_dim3(bx, by, bz);
+            threadIdx = cta.fib[t].tid;
+            emu_ctx_swap(cta.sched, cta.fib[t].ctx);
+          }
+        }
+        emu_cta = nullptr;
       }
-    }
-    emu_cta = nullptr;
-  }
 }
 // deposit `v`, wait for every lane in `mask`, return a pointer to the 32 deposited values
 static inline const unsigned long long *emu_rendezvous(unsigned mask, unsigned long long v) {
@@ -218,6 +226,11 @@ static inline T emu_shfl_idx(unsigned mask, T v, int src) {
 template <class T>
 static inline T __shfl_sync(unsigned mask, T v, int src) { return emu_shfl_idx(mask, v, src); }
 template <class T>
+static inline T __shfl_up_sync(unsigned mask, T v, unsigned delta) {
+  const int lane = emu_cta->cur % EMU_WARP;
+  return emu_shfl_idx(mask, v, lane >= (int)delta ? lane - (int)delta : lane);
+}
+template <class T>
 static inline T __shfl_xor_sync(unsigned mask, T v, int lanemask) {
   return emu_shfl_idx(mask, v, (emu_cta->cur % EMU_WARP) ^ lanemask);
 }
@@ -236,8 +249,10 @@ static inline void __syncthreads() {
 }
 #define BATOTP_LAUNCH_WARP(kern, grid, block, smem, stream, ...) \
   emu_launch_fibers((grid), (block), [&] { kern(__VA_ARGS__); })
+#define EMU_SHARED static
 #else
 #define BATOTP_LAUNCH(kern, grid, block, stream, ...) kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 #define BATOTP_LAUNCH_SMEM(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define BATOTP_LAUNCH_WARP(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define EMU_SHARED __shared__
 #endif

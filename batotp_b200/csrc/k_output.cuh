@@ -248,6 +248,68 @@ __global__ void k_out_segs(Ws w) {
   }
 }
 
+// k_out_s + k_out_segs_par in one pass over 32x32 tiles (sites x trajectories).  s(t) is read from the
+// trajectory-major history rows, so a warp takes 32 consecutive sites of ONE trajectory (its four gathers hit
+// one or two segments of that row); the tile is turned in shared memory and written with trajectories
+// fastest, the order the point-major consumers read.  The monotonicity test compares with the lane to the
+// left (the site before the tile is recomputed).  Block (32, 8).
+__global__ void k_out_s_segs(Ws w, int npts, int nb) {
+  EMU_SHARED double tS[32][33], tTau[32][33];
+  EMU_SHARED int tSeg[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int bl0 = (int)blockIdx.x * 32, i0 = (int)(blockIdx.z * gridDim.y + blockIdx.y) * 32;
+  for (int k = 0; k < 4; ++k) {
+    const int bll = ty + 8 * k, bl = bl0 + bll, i = i0 + tx;
+    bool valid = bl < nb && i < npts;
+    double a = 0, tau = 0;
+    int kseg = 0;
+    if (valid) {
+      TrajState &s = w.st[w.b0 + bl];
+      valid = !(s.status & ST_FATAL_MASK) && i < s.nOver;
+      if (valid) {
+        const int b = w.b0 + bl;
+        const double tLast = s.tStep * (double)(s.nFwd - 1);
+        UniformSites in{s.tStep};
+        const double *sF = w.hist + (size_t)b * 4 * w.Sc + 2 * (size_t)w.Sc;
+        const RV ys{const_cast<double *>(sF), 1}, ms{w.mS + (size_t)bl * w.Sc, 1};
+        auto s_at = [&](int ii) {
+          const double t = tmvc_out(ii, s.nOver, tLast);
+          const int seg = find_seg(in, s.nFwd, t);
+          const double ta = (t - in(seg)) / (in(seg + 1) - in(seg));
+          const Seg4 c = seg_coef(ys, ms, seg);
+          const double ta2 = ta * ta, ta3 = ta2 * ta;
+          return seg_value(c, ta, ta2, ta3);
+        };
+        a = s_at(i);
+        const int nIn = s.nPtsC;
+        const double res = s.sresC;
+        kseg = first_seg_uniform(res, nIn, a);
+        const double lo = res * (double)kseg, hiEdge = res * (double)(kseg + 1);
+        tau = (a - lo) / (hiEdge - lo);
+        if (tx == 0 && i > 0) {
+          if (first_seg_uniform(res, nIn, s_at(i - 1)) > kseg) s.segWalk = 1;
+        }
+      }
+    }
+    // the running maximum of findInterpSegs differs from f(a) where f decreases: sequential walk needed
+    const int kleft = __shfl_up_sync(0xffffffffu, valid ? kseg : -1, 1);
+    if (valid && tx > 0 && kleft > kseg) w.st[w.b0 + bl].segWalk = 1;
+    tS[bll][tx] = a;
+    tTau[bll][tx] = tau;
+    tSeg[bll][tx] = valid ? kseg : -1;
+  }
+  __syncthreads();
+  for (int k = 0; k < 4; ++k) {
+    const int il = ty + 8 * k, i = i0 + il, bl = bl0 + tx;
+    if (bl < nb && i < npts && tSeg[tx][il] >= 0) {
+      const size_t at = (size_t)i * w.Bo + bl;
+      w.sOut[at] = tS[tx][il];
+      w.segO[at] = tSeg[tx][il];
+      w.tauO[at] = tTau[tx][il];
+    }
+  }
+}
+
 // theta(t) / cart(t) at the oversampled sites (ba.cpp:1713-1742).  One thread per (point, trajectory, row),
 // rows fastest: the four knot gathers and the store of a point are contiguous R*8-byte runs.  Rows that are
 // not path-driven are filled by the kinematics kernel afterwards (or are the generic robot's zeros).
@@ -511,6 +573,73 @@ __global__ void k_out_eval_smooth(Ws w, double *dst, int npts, int nb) {
     v = v0 + (v1 - v0) * tau;
   }
   dst[((size_t)i * w.Bo + bl) * R + r] = v;
+}
+
+// The same for joint-driven paths with one thread per (decimated point, trajectory): the NR = nJoints driven
+// rows share the site lookups (segO/tauO are read once instead of once per row) and give the thread NR
+// independent chains.  Rows NR..R-1 are the generic robot's zeros.  (TP)
+template <int WM, int NR>
+__global__ void k_out_eval_smooth_rows(Ws w, double *dst, int npts, int nb) {
+  TP_DECOMP(nb);
+  if (i >= npts) return;
+  const int b = w.b0 + bl;
+  const TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  if (i >= s.nSm) return;
+  const int R = w.R;
+  const int nIn = s.nOver, nOut = s.nSm;
+  const int wv = (int)s.outSmooth;
+  const double aOut = ((double)(nIn - 1) / (double)(nOut - 1)) * (double)i;
+  UniformSites in{1.0};
+  const int seg = find_seg(in, nIn, aOut);
+  const double tau = (aOut - (double)seg) / ((double)(seg + 1) - (double)seg);
+  double *o = dst + ((size_t)i * w.Bo + bl) * R;
+  const size_t pst = (size_t)w.B * R;
+  int ww = imin_(wv, nIn);
+  const int wMid = ww / 2 + ww % 2 - 1;
+  if (wMid == WM && seg >= WM && seg + 1 < nIn - WM) {
+    double t0[NR], t1[NR], c3[NR], c2[NR], c1[NR], c0[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) t0[r] = t1[r] = c3[r] = c2[r] = c1[r] = c0[r] = 0.0;
+    int cseg = -1;
+#pragma unroll
+    for (int q = 0; q < 2 * WM + 2; ++q) {
+      const size_t at = (size_t)(seg - WM + q) * w.Bo + bl;
+      const int sg = w.segO[at];
+      const double ta = w.tauO[at];
+      if (sg != cseg) {
+        const double *y0 = w.P + (size_t)sg * pst + (size_t)b * R, *m0 = w.M + (size_t)sg * pst + (size_t)b * R;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const double a0 = y0[r], a1 = y0[pst + r], b0 = m0[r], b1 = m0[pst + r];
+          c3[r] = sdiv::div6(b1 - b0);
+          c2[r] = b0 / 2.0;
+          c1[r] = a1 - a0 - sdiv::div6(b1 + 2 * b0);
+          c0[r] = a0;
+        }
+        cseg = sg;
+      }
+      const double ta2 = ta * ta, ta3 = ta2 * ta;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const double x = c3[r] * ta3 + c2[r] * ta2 + c1[r] * ta + c0[r];  // seg_value
+        if (q <= 2 * WM) t0[r] += x;
+        if (q >= 1) t1[r] += x;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const double v0 = t0[r] / (2 * WM + 1), v1 = t1[r] / (2 * WM + 1);
+      o[r] = v0 + (v1 - v0) * tau;
+    }
+  } else {
+    for (int r = 0; r < NR; ++r) {
+      OverEval X{w.P, w.M, w.tauO, w.segO, pst, (size_t)b * R + r, w.Bo, bl, -1, Seg4{0, 0, 0, 0}};
+      const double v0 = smooth_at(X, nIn, wv, seg), v1 = smooth_at(X, nIn, wv, seg + 1);
+      o[r] = v0 + (v1 - v0) * tau;
+    }
+  }
+  for (int r = NR; r < R; ++r) o[r] = 0.0;
 }
 
 // ----------------------------------------------------------------------------- final (T + TP)

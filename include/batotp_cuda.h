@@ -26,7 +26,7 @@ typedef struct batotp_ctx *batotp_handle;
 #define BATOTP_ST_SRES_SMALL 4       /* ba.cpp:607-611 */
 #define BATOTP_ST_GRID_CAP 8         /* internal capacity; retried automatically */
 #define BATOTP_ST_MAX_INTEG_TIME 16  /* ba.cpp:1117-1122 = BA::MAX_INTEGRATION_TIME */
-#define BATOTP_ST_STEP_CAP 32        /* internal capacity; retried automatically */
+#define BATOTP_ST_STEP_CAP 32        /* internal capacity; retried automatically up to batotp_cuda_set_max_steps */
 #define BATOTP_ST_NUMERIC 64         /* NaN in a segment search (the reference would not return) */
 #define BATOTP_ST_BISECT_FAIL 128    /* informational: ba.cpp:1307-1319 returned -1 somewhere (sweep ignores it) */
 #define BATOTP_ST_DIV0 256           /* spline.cpp:82-86 */
@@ -45,6 +45,10 @@ const char *batotp_cuda_last_error(batotp_handle h);
 int batotp_cuda_set_chunk(batotp_handle h, int chunk);
 /* trajectories per interpOutputData pass inside a chunk (bounds the oversampled-output buffers); default 8192 */
 int batotp_cuda_set_out_chunk(batotp_handle h, int n);
+/* largest Runge-Kutta step capacity (per sweep) the automatic capacity retries grow to; default 65536.  A
+ * trajectory that needs more steps (the reference would run it until maxIntegTime, ba.cpp:1117-1122) keeps
+ * BATOTP_ST_STEP_CAP and is reported as not optimised; n >= 1024 */
+int batotp_cuda_set_max_steps(batotp_handle h, int n);
 /* number of kernels launched by this context since creation (for the benchmark's gpu_launches) */
 long batotp_cuda_launch_count(batotp_handle h);
 /* measurement hooks for bench.py.

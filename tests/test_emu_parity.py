@@ -103,3 +103,22 @@ def test_sweep_filters_decide_nearly_everything(ctx):
     assert exact < 0.01 * certain        # decisions deferred to the exact verification
     assert b_exact < 0.001 * b_joint     # bounds that needed all joints instead of the certified one
     assert v_all < 0.001 * (v_skip + v_one + 1)
+
+
+def test_step_capacity_is_bounded(ctx):
+    """A trajectory that needs more Runge-Kutta steps than the configured ceiling keeps BATOTP_ST_STEP_CAP and
+    is reported as not optimised; the batch call itself succeeds and the other trajectories are unaffected."""
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 7, 3)
+    ref = P.run_device(ctx, cfg, tres, th, None)
+    assert (ref.status & native.ST_FATAL_MASK == 0).all() and ref.n_fwd.min() > 1100
+    ctx.set_max_steps(1024)
+    try:
+        c = native.Context(0, ctx.L._name)  # fresh capacities
+        c.set_max_steps(1024)
+        capped = P.run_device(c, cfg, tres, th, None)
+        c.close()
+    finally:
+        ctx.set_max_steps(65536)
+    assert ((capped.status & 32) != 0).all() and (capped.n_out == 0).all()
+    again = P.run_device(ctx, cfg, tres, th, None)
+    assert np.array_equal(again.theta_out, ref.theta_out) and np.array_equal(again.t_total, ref.t_total)
