@@ -441,7 +441,7 @@ void select_out_set(batotp_ctx *h, int q) {
 }
 
 // output sub-chunk arrays, sized from the step capacity of the resident chunk
-void ensure_out(batotp_ctx *h, int Bo) {
+void ensure_out(batotp_ctx *h, int Bo, int minOutC = 0) {
   const DevCfg &c = h->cfg;
   Ws &w = h->w;
   const int Sc = w.Sc;
@@ -449,7 +449,7 @@ void ensure_out(batotp_ctx *h, int Bo) {
   const bool trq = c.trqOn != 0;
   int Os = Oc;
   if (!trq && smooth_uniform_on(h)) Os = (int)(Oc / c.c.out_smooth_fact) + 16;
-  const int OutC = final_cap(h, Sc, Os);
+  const int OutC = std::max(final_cap(h, Sc, Os), minOutC);
   if (!(Bo <= h->capBo && Oc <= h->capOc && Os <= h->capOs && OutC <= h->capOutC && Sc == h->capOSc &&
         h->keepF64 == h->capKeep && fused_out(h) == h->capFused && c.R == h->capR && trq == h->capTrq)) {
     free_out(h);
@@ -558,8 +558,8 @@ int check_cfg(batotp_ctx *h) {
     h->err = "torque limits need a dynamic model: only RR (serial) and CSPR3DOF (parallel) have one (robot.cpp:349-360, 463-474)";
     return -1;
   }
-  if (c.is_interp_only) {
-    h->err = "isInterpOnly is outside the accelerated scope (SURVEY §8f rank 2)";
+  if (c.is_interp_only && c.path_type == BATOTP_CART) {
+    h->err = "isInterpOnly needs joint data: the reference sizes the result by theta[0] (ba.cpp:141)";
     return -1;
   }
   return 0;
@@ -870,6 +870,58 @@ int do_interp_input(batotp_ctx *h, bool haveN0, bool planSync) {
   LAUNCH_TP(h, k_build_table, w.Nc, B, w);
   h->phase = 2;
   return 0;
+}
+
+// BA::interpInputData with _isInterpOnly (ba.cpp:139-159) for the resident chunk: re-sample every row with
+// natural splines at outRes; the result is packed like an optimised trajectory (one output "sub-chunk" =
+// the whole chunk, whose point-major layout the packing kernel reads directly).
+int do_interp_only(batotp_ctx *h, bool haveN0) {
+  const DevCfg &c = h->cfg;
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    int Nc = std::max(std::max(h->hwNc, h->n0max + 8), h->w.Nc);
+    ensure_ws(h, std::max(h->B, h->capB), Nc, std::max(h->hwSc, 1024));
+    Ws &w = h->w;
+    w.B = h->B;
+    run_load_prepare(h, haveN0);
+    int gridCap = 0;
+    read_plan_max(h, &gridCap);
+    int mx = 0;  // largest re-sampled length, the trajectories that only ran out of room included
+    for (int b = 0; b < h->B; ++b) {
+      const TrajState &t = h->hst[b];
+      if (t.status & (ST_FATAL_MASK & ~ST_GRID_CAP)) continue;
+      mx = std::max(mx, std::max(t.nNew, t.nPts));
+    }
+    if (gridCap || mx + 8 > w.Nc) {  // the re-sampled rows need more room
+      h->hwNc = std::max(h->hwNc, mx + 64);
+      free_ws(h);
+      continue;
+    }
+    const int pt = c.c.path_type;
+    if ((pt == BATOTP_CART || pt == BATOTP_BOTH) && c.Cin == 6) {  // ba.cpp:145-148
+      if (c.c.trig_mode == 1)
+        host_rows_apply(h, w.P, w.Nc, h->B, 0, false, 2);
+      else
+        LAUNCH_T(h, k_aa2q, h->B, w);
+    }
+    thomas_rows(h, w.P, w.M, h->B, 0, c.R, c.R, 0, 0);
+    LAUNCH_TP(h, k_resample, w.Nc, h->B, w);
+    LAUNCH_T(h, k_resample_commit, h->B, w);
+    std::swap(w.P, w.Q);
+    ensure_out(h, std::max(h->B, h->capBo), mx + 8);
+    w.b0 = 0;
+    w.Bo = h->B;
+    LAUNCH_T(h, k_interp_only_finish, h->B, w);
+    select_out_set(h, 0);
+    const bool strictQuat = (c.C == 7 && c.c.trig_mode == 1);
+    if (h->d_trqOut) g_zero(h->d_trqOut, (size_t)h->B * c.J * w.OutC * sizeof(float), h->stream);  // no torque rows here
+    LAUNCH_PT(h, k_out_pack, w.OutC, h->B, w, w.P, w.M, (double *)nullptr, (double *)nullptr, h->d_thetaOut,
+              h->d_cartOut, (float *)nullptr, strictQuat ? h->d_cartOutD : (double *)nullptr, h->d_outD);
+    LAUNCH_PT(h, k_pack_hist, w.Sc, h->B, w, h->d_histOut);
+    h->phase = 4;
+    return 0;
+  }
+  h->err = "grid capacity retry limit reached";
+  return -1;
 }
 
 int do_sweeps(batotp_ctx *h) {
@@ -1418,6 +1470,7 @@ int batotp_cuda_load(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_
 int batotp_cuda_interp_input(batotp_handle h) {
   if (!h || h->phase < 1) return -1;
   try {
+    if (h->cfg.c.is_interp_only) return do_interp_only(h, h->lastHaveN0);  // result ready for batotp_cuda_fetch
     return chunk_interp_input(h, h->lastHaveN0);
   } catch (const Err &e) {
     h->err = e.msg;
@@ -1523,6 +1576,11 @@ static void process_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_b
                           int at, int B) {
   if (load_chunk(h, cfg, in, at, B) != 0) throw Err{h->err};
   h->lastHaveN0 = in->n0 != nullptr;
+  if (h->cfg.c.is_interp_only) {  // ba.cpp:139-159: re-sample only
+    if (do_interp_only(h, h->lastHaveN0) != 0) throw Err{h->err};
+    fetch_sub(h, out, at);
+    return;
+  }
   if (chunk_interp_input(h, h->lastHaveN0) != 0) throw Err{h->err};
   if (chunk_sweeps_output(h, h->lastHaveN0) != 0) throw Err{h->err};
   {

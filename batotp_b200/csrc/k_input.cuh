@@ -272,6 +272,26 @@ __global__ void k_in_prepare(Ws w, const double *ts, int n0max, int hasTheta, in
     traj_linear_to4(w, w.P, b, s, R);
     nPts = s.nPts;
   }
+  if (CFG.c.is_interp_only) {
+    // ba.cpp:139-159: no optimisation, the path is only re-sampled at outRes.  Plan of
+    // evalSplineFullTraj(traj, traj.sres, _outRes) (ba.cpp:794-819); the sites are the de-duplicated
+    // timestamps when the file had them (already in sC), sres*k otherwise.
+    const double oldRes = s.sres;
+    int nNew = (int)ceil(oldRes / CFG.c.out_res * (nPts - 1)) + 1;
+    nNew = imax_(nNew, 4);
+    const RV sC = vecv(w.sC, w, b);
+    if (!ts)
+      for (int i = 0; i < nPts; ++i) sC[i] = oldRes * (double)i;
+    s.sScale = sC[nPts - 1] / (double)(nNew - 1);
+    s.nNew = nNew;
+    s.nPtsC = nPts;
+    s.sresC = s.sres;
+    s.vFact = 1 / s.sresC;
+    s.aFact = s.vFact * s.vFact;
+    s.sres = oldRes * (nPts - 1) / (nNew - 1);
+    if (nNew > w.Nc) s.status |= ST_GRID_CAP;
+    return;
+  }
   s.sLastSec = -1;
   // remClosePts(x = driving rows, y = the others, thresh)
   const bool cartDriven = (CFG.c.path_type == BATOTP_CART);
@@ -859,6 +879,22 @@ __global__ void k_resample_commit(Ws w) {
     prev = nx;
   }
   s.nPts = s.nNew;
+}
+
+// ba.cpp:155-157 after the interpolation-only resample: the result IS the output (sres = outRes)  (T)
+__global__ void k_interp_only_finish(Ws w) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= w.B) return;
+  TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  s.nOut = s.nSm = s.nPts;
+  s.nCartOut = s.nPts;
+  s.isReinterp = 0;
+  s.sres = CFG.c.out_res;
+  s.sresOut = CFG.c.out_res;
+  s.nRev = s.nFwd = 0;
+  s.tRev = s.tFwd = 0.0;
+  if (s.nOut > w.OutC) s.status |= ST_STEP_CAP;
 }
 
 // ----------------------------------------------------------------------------- final grid (T + TP)

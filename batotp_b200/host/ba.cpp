@@ -224,6 +224,15 @@ int BA::interpInputData(Traj &traj) {
     printf("interpInputData(): %s\n", batotp_cuda_last_error(_h));
     return -1;
   }
+  if (_cfg.is_interp_only) {  // ba.cpp:139-159: the re-sampled path is the result; the reference returns -1 here
+    _sweepsDone = true;
+    const bool was = _cfg.is_trq_on != 0;
+    _cfg.is_trq_on = 0;  // no torque rows in this mode
+    fillOutput(traj);
+    _cfg.is_trq_on = was;
+    _sweepsDone = false;
+    return -1;
+  }
   // status and grid size come back with the fetch after the sweeps; the grid size is available now
   std::vector<double> y;
   const int n = pull("thetaC_y", 0, y);
@@ -287,6 +296,11 @@ int BA::interpOutputData(Traj &traj) {
     printf("interpOutputData(): %s\n", batotp_cuda_last_error(_h));
     return -1;
   }
+  return fillOutput(traj);
+}
+
+// copies the packed result of the resident trajectory into Traj (FP64 rows before the float cast)
+int BA::fillOutput(Traj &traj) {
   batotp_batch_out o;
   memset(&o, 0, sizeof(o));
   int status = 0, nOut = 0, nCart = 0;

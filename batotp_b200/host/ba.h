@@ -136,6 +136,7 @@ class BA {
 
   int ensureDevice();
   int pull(const char *name, int row, std::vector<double> &v);
+  int fillOutput(Traj &traj);
 };
 
 }  // namespace BATOTP

@@ -45,7 +45,7 @@ typedef struct batotp_cfg {
   int scale_type;        /* _scaleType           ba.h:294 */
   int is_svd;            /* _isSVD               ba.h:301 (1 is not supported on the device: returns -1) */
   int is_par2ser;        /* _isPar2Ser           ba.h:302 */
-  int is_interp_only;    /* _isInterpOnly        ba.h:306 */
+  int is_interp_only;    /* _isInterpOnly        ba.h:306 (re-sample the path at outRes only, ba.cpp:139-159; needs joint rows) */
   int is_auto_integ_res; /* _isAutoIntegRes      ba.h:309 (batest forces 0, test/main.cpp:53) */
   int trig_mode;         /* 0: kinematics/dynamics trig evaluated on the device (CUDA sincos);
                             1: strict parity — the host layer evaluates the trig-bearing point

@@ -108,6 +108,8 @@ void *ref_new(const char *config_path, const char *input_folder, const char *out
   return h;
 }
 void ref_free(void *p) { delete (Handle *)p; }
+/* BA::setIsInterpOnly (ba.h public setters): interpInputData then only re-samples the path (ba.cpp:139-159) */
+void ref_set_interp_only(void *p, int on) { ((Handle *)p)->ba.setIsInterpOnly(on != 0); }
 
 int ref_load_file(void *p) {
   Handle *h = (Handle *)p;

@@ -81,6 +81,7 @@ def ref_lib():
         L.ref_new.restype = C.c_void_p
         L.ref_new.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
         L.ref_free.argtypes = [C.c_void_p]
+        L.ref_set_interp_only.argtypes = [C.c_void_p, C.c_int]
         L.ref_silence.argtypes = [C.c_int]
         L.ref_load_file.argtypes = [C.c_void_p]
         L.ref_load_raw.argtypes = [C.c_void_p, C.c_int, C.c_double, _fp, _fp, _dp]
@@ -193,6 +194,9 @@ class Ref(_Base):
         if getattr(self, "h", None):
             self.L.ref_free(self.h)
             self.h = None
+
+    def set_interp_only(self, on: bool):
+        self.L.ref_set_interp_only(self.h, int(on))
 
     def _call(self, f, *a):
         if self.silent:

@@ -175,3 +175,41 @@ def test_large_batch_matches_oracle_bit_for_bit(ctx):
     assert np.array_equal(res.t_total, tt)
     assert int(no.max()) <= out_cap
     assert np.array_equal(res.theta_out, rows)
+
+
+@pytest.mark.parametrize("name", ["RR", "UR5", "KUKA-LWR-IV", "CSPR3DOF"])
+def test_automatic_integration_resolution(ctx, name):
+    """_isAutoIntegRes = true (per-trajectory integRes / weights, ba.cpp:471-556)."""
+    cfg, tres, th, ca, ts = P.load_stock(name)
+    cfg = cfg.copy()
+    cfg.is_auto_integ_res = 1
+    res = P.run_device(ctx, cfg, tres, th, ca, ts)
+    assert res.status[0] & native.ST_FATAL_MASK == 0
+    orc = P.OracleRun(cfg, tres, None if th is None else th[0], None if ca is None else ca[0],
+                      None if ts is None else ts[0])
+    assert orc.ok and P.compare(cfg, res, 0, orc) == []
+
+
+def test_interpolation_only_mode(ctx):
+    """_isInterpOnly (ba.cpp:139-159) — the path is only re-sampled at outRes.  UR5 carries
+    joint and Cartesian rows (axis-angle -> quaternion -> axis-angle around the resample)."""
+    from _oracle import Oracle
+    cfg, tres, th, ca, ts = P.load_stock("UR5")
+    cfg = cfg.copy()
+    cfg.is_interp_only = 1
+    res = P.run_device(ctx, cfg, tres, th, ca, ts, out_cap=8192)
+    o = Oracle(cfg)
+    o.load_raw(th.shape[2], tres, th[0], ca[0], None if ts is None else ts[0])
+    assert o.interp_input() == -1
+    n = int(o.scalar("nPts"))
+    assert res.status[0] == 0 and res.n_out[0] == n and res.n_cart_out[0] == n and res.out_sres[0] == cfg.out_res
+    assert np.array_equal(res.theta_out[0, :, :n], o.rows("theta", cfg.n_joints).astype(np.float32))
+    assert np.array_equal(res.cart_out[0, :6, :n], o.rows("cart", 6).astype(np.float32))
+    assert res.n_rev[0] == 0 and res.n_fwd[0] == 0 and not res.hist.any()
+    # a batch of joint-only paths: absent Cartesian rows are zeros (the reference has no defined result there)
+    cfg2, tres2, th2, _ = P.load_synth("GEN7DOF", 0, 5)
+    cfg2 = cfg2.copy()
+    cfg2.is_interp_only = 1
+    r2 = P.run_device(ctx, cfg2, tres2, th2, None, out_cap=1024)
+    assert (r2.status == 0).all() and (r2.n_out == r2.n_out[0]).all() and r2.n_out[0] > 400
+    assert np.abs(r2.theta_out[:, :, 0] - th2[:, :, 0]).max() == 0  # a spline interpolates its first knot exactly

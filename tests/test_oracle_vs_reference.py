@@ -9,11 +9,14 @@ from _oracle import Oracle, Ref, ref_available
 pytestmark = pytest.mark.skipif(not ref_available(), reason="oracle/_ref/libbatotp_ref.so not built")
 
 
-def _pair(name, tmp_path):
+def _pair(name, tmp_path, auto=False):
     d = P.GOLD + "/stock/" + name + "/"
-    r = Ref(d + "config.dat", d, str(tmp_path) + "/")
+    r = Ref(d + "config.dat", d, str(tmp_path) + "/", auto_integ_res=auto)
     assert r.load_file() == 0
     cfg, tres, th, ca, ts = P.load_stock(name)
+    if auto:
+        cfg = cfg.copy()
+        cfg.is_auto_integ_res = 1
     rc = r.cfg()
     import ctypes as C
     assert bytes(C.string_at(C.byref(cfg), C.sizeof(cfg))) == bytes(C.string_at(C.byref(rc), C.sizeof(rc))), \
@@ -74,6 +77,51 @@ def test_switching_flags_match_instrumented_reference(name, tmp_path):
     assert o.sweep(1, 1) == 0
     assert np.array_equal(s[:-1], o.vec("hist_s1")[:-1]) and np.array_equal(sd[:-1], o.vec("hist_sdot1")[:-1])
     assert np.array_equal(fl, o.vec("flags1").astype(np.uint8))
+
+
+@pytest.mark.parametrize("name", ["RR", "UR5", "KUKA-LWR-IV", "CSPR3DOF"])
+def test_automatic_integration_resolution_matches(name, tmp_path):
+    """_isAutoIntegRes = true (the library default, ba.h:309; batest switches it off): adjust_s rewrites
+    sWeights / scaleType / integRes per trajectory (ba.cpp:471-556).  The restatement must follow the unmodified
+    reference through all three phases bit for bit.  (The generic robot has no Cartesian path to derive the
+    resolution from: both sides reject GEN7DOF in this mode.)"""
+    cfg, r, o = _pair(name, tmp_path, auto=True)
+    J = cfg.n_joints
+    assert r.interp_input() == 0 and o.interp_input() == 0
+    assert r.scalar("nPts") == o.scalar("nPts") and r.scalar("integRes") == o.scalar("integRes")
+    for d, last in ((-1, 0), (1, 1)):
+        assert r.sweep(d, last) == 0 and o.sweep(d, last) == 0
+        assert np.array_equal(r.vec("sMVC"), o.vec("sMVC")) and np.array_equal(r.vec("sdot"), o.vec("sdot"))
+    assert r.scalar("tTotalTraj") == o.scalar("tTotalTraj")
+    r.interp_output()
+    o.interp_output()
+    assert r.scalar("outRes") == o.scalar("outRes")
+    for j in range(J):
+        assert np.array_equal(r.vec("theta", j), o.vec("theta", j)), j
+    for j in range(int(r.scalar("cartRows"))):
+        assert np.array_equal(r.vec("cart", j), o.vec("cart", j)), j
+
+
+def test_interpolation_only_mode_matches(tmp_path):
+    """_isInterpOnly (ba.cpp:139-159): interpInputData only re-samples the path at outRes and returns -1.  UR5 is
+    the stock folder that carries both joint and Cartesian rows (the reference reads traj.cart[i] of an empty
+    vector for the joint-only files in this mode, so those have no defined result)."""
+    d = P.GOLD + "/stock/UR5/"
+    r = Ref(d + "config.dat", d, str(tmp_path) + "/")
+    r.set_interp_only(True)
+    assert r.load_file() == 0
+    cfg, tres, th, ca, ts = P.load_stock("UR5")
+    cfg = cfg.copy()
+    cfg.is_interp_only = 1
+    o = Oracle(cfg)
+    o.load_raw(th.shape[2], tres, th[0], ca[0], None if ts is None else ts[0])
+    assert r.interp_input() == -1 and o.interp_input() == -1
+    assert r.scalar("nPts") == o.scalar("nPts") and r.scalar("sres") == o.scalar("sres") == cfg.out_res
+    for j in range(cfg.n_joints):
+        assert np.array_equal(r.vec("theta", j), o.vec("theta", j)), j
+    assert int(r.scalar("cartRows")) == int(o.scalar("cartRows")) == 6
+    for j in range(6):
+        assert np.array_equal(r.vec("cart", j), o.vec("cart", j)), j
 
 
 def test_batch_runner_agrees(tmp_path):
