@@ -272,8 +272,24 @@ def main_b200(args):
     flops = n_eval * (5 + 18 * J) + ver * (2 + 7 * J) + n_lim * (1 + 2 * J + 3) + 110 * steps_rk
     sweep_s = st["sweep_ms"] * 1e-3
     achieved = flops / max(sweep_s, 1e-12) * 1e-12
+    # DRAM traffic of the sweep kernel: from the committed ncu --set full capture (profiles/), scaled from the
+    # trajectories of the captured launch to the trajectories per launch of this run
+    traffic, traffic_src = None, None
+    try:
+        import csv
+        prof = os.path.join(ROOT, "profiles", "r1b_sweep_ncu_full_summary.csv")
+        vals = {r[0]: (r[1], float(r[2])) for r in csv.reader(open(prof)) if len(r) == 3 and not r[0].startswith("#")
+                and r[0] != "metric"}
+        gb = sum(v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
+                 for k, (u, v) in vals.items() if k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        per_launch_traj = ntraj / max(st["sweep_launches"], 1)
+        traffic = gb / 56832.0 * per_launch_traj
+        traffic_src = "profiles/r1b_sweep_ncu_full_summary.csv (dram__bytes_read+write of a 56832-path launch, per path)"
+    except Exception:
+        pass
     roof = dict(bound="fp64", achieved=achieved, peak=peak_fma, unit="TFLOP/s", frac=achieved / max(peak_fma, 1e-12),
-                traffic=None, kernel="k_sweep<7,false,false>", launches=st["sweep_launches"],
+                traffic=traffic, traffic_unit="bytes per launch", traffic_source=traffic_src,
+                kernel="k_sweep<7,false,false>", launches=st["sweep_launches"],
                 avg_launch_ms=st["sweep_ms"] / max(st["sweep_launches"], 1),
                 peak_source="measured in this run (DFMA chains); MEASURED_PEAKS.json has no FP64 entry",
                 peak_nofma=peak_nofma, frac_of_nofma_peak=achieved / max(peak_nofma, 1e-12),
