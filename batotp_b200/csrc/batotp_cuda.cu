@@ -189,6 +189,7 @@ struct batotp_ctx {
   double *o_OD = nullptr, *o_OD2 = nullptr, *o_Trq = nullptr, *o_Trq2 = nullptr, *o_TrqM = nullptr;
   int *o_segO = nullptr;
   bool keepF64 = false, capKeep = false, capFused = false;
+  int mxSteps = 0;  // largest nFwd/nRev of the resident chunk (launch extents of the output phase)
   int allocPhase = 0;  // which workspace was being (re)allocated last: 0 chunk arrays, 1 output sub-chunk arrays
   // which buffers hold the final rows after interp_output
   // high-water marks so that steady-state chunks need no planning sync
@@ -867,7 +868,17 @@ int do_interp_input(batotp_ctx *h, bool haveN0, bool planSync) {
       LAUNCH_TP(h, k_dyn_grid, w.Nc, B, w, h->pm);
     thomas_rows(h, w.A, w.AM, B, 0, 4 * MAXD, 4 * MAXD, 0, 0);
   }
-  LAUNCH_TP(h, k_build_table, w.Nc, B, w);
+  if (!c.trqOn && w.RT <= BT_ROWS) {  // kinematic rows only: tiled through shared memory
+    const long long rows = cdiv(w.Nc, BT_SEGS);
+    const long long gy = std::min<long long>(rows, 32768), gz = (rows + gy - 1) / gy;
+    ProfScope ps_(h, "k_build_table_tile");
+    BATOTP_LAUNCH_WARP(k_build_table_tile, dim3((unsigned)cdiv(B, BT_TRAJ), (unsigned)gy, (unsigned)gz),
+                       dim3(BT_TRAJ, BT_SEGS, 1), 0, h->stream, w, w.Nc, B);
+    g_check_launch();
+    h->launches++;
+  } else {
+    LAUNCH_TP(h, k_build_table, w.Nc, B, w);
+  }
   h->phase = 2;
   return 0;
 }
@@ -938,13 +949,16 @@ void do_interp_output(batotp_ctx *h, int b0, int Bo) {
   w.b0 = b0;
   w.Bo = Bo;
   const ThomasTabs t = thomas_tabs(h);
+  // launch extents from the longest trajectory of the chunk rather than from the capacities
+  const int lOc = std::min(w.Oc, oversample_cap(h, std::max(h->mxSteps, 4)));
+  const int lOs = (w.Os == w.Oc) ? lOc : std::min(w.Os, (int)(lOc / c.c.out_smooth_fact) + 16);
   LAUNCH_T(h, k_out_plan, Bo, w, t);
   {  // s(t) at the oversampled sites and their segments, 32x32 tiles
-    const long long rows = cdiv(w.Oc, 32);
+    const long long rows = cdiv(lOc, 32);
     const long long gy = std::min<long long>(rows, 32768), gz = (rows + gy - 1) / gy;
     ProfScope ps_(h, "k_out_s_segs");
     BATOTP_LAUNCH_WARP(k_out_s_segs, dim3((unsigned)cdiv(Bo, 32), (unsigned)gy, (unsigned)gz), dim3(32, 8, 1), 0, h->stream,
-                       w, w.Oc, Bo);
+                       w, lOc, Bo);
     g_check_launch();
     h->launches++;
   }
@@ -960,31 +974,31 @@ void do_interp_output(batotp_ctx *h, int b0, int Bo) {
       const int wMid = wv / 2 + wv % 2 - 1;
       const bool jointRows = c.c.path_type == BATOTP_JOINT;  // rows 0..J-1 driven, the others zero
       if (jointRows && wMid == 2 && c.J == 7)
-        LAUNCH_TP(h, (k_out_eval_smooth_rows<2, 7>), w.Os, Bo, w, w.OA);
+        LAUNCH_TP(h, (k_out_eval_smooth_rows<2, 7>), lOs, Bo, w, w.OA);
       else if (jointRows && wMid == 2 && c.J == 6)
-        LAUNCH_TP(h, (k_out_eval_smooth_rows<2, 6>), w.Os, Bo, w, w.OA);
+        LAUNCH_TP(h, (k_out_eval_smooth_rows<2, 6>), lOs, Bo, w, w.OA);
       else
       switch (wMid) {
-        case 1: LAUNCH_TP(h, k_out_eval_smooth<1>, w.Os, (long long)Bo * c.R, w, w.OA); break;
-        case 2: LAUNCH_TP(h, k_out_eval_smooth<2>, w.Os, (long long)Bo * c.R, w, w.OA); break;
-        case 3: LAUNCH_TP(h, k_out_eval_smooth<3>, w.Os, (long long)Bo * c.R, w, w.OA); break;
-        case 4: LAUNCH_TP(h, k_out_eval_smooth<4>, w.Os, (long long)Bo * c.R, w, w.OA); break;
-        default: LAUNCH_TP(h, k_out_eval_smooth<5>, w.Os, (long long)Bo * c.R, w, w.OA); break;  // others: generic path
+        case 1: LAUNCH_TP(h, k_out_eval_smooth<1>, lOs, (long long)Bo * c.R, w, w.OA); break;
+        case 2: LAUNCH_TP(h, k_out_eval_smooth<2>, lOs, (long long)Bo * c.R, w, w.OA); break;
+        case 3: LAUNCH_TP(h, k_out_eval_smooth<3>, lOs, (long long)Bo * c.R, w, w.OA); break;
+        case 4: LAUNCH_TP(h, k_out_eval_smooth<4>, lOs, (long long)Bo * c.R, w, w.OA); break;
+        default: LAUNCH_TP(h, k_out_eval_smooth<5>, lOs, (long long)Bo * c.R, w, w.OA); break;  // others: generic path
       }
     }
     cur = w.OA;
     curCap = w.Os;
   } else {
-    LAUNCH_TP(h, k_out_eval, w.Oc, (long long)Bo * c.R, w);
+    LAUNCH_TP(h, k_out_eval, lOc, (long long)Bo * c.R, w);
     apply_kinematics(h, 2);
     if (c.trqOn) {
       // re-spline theta(t) (and cart(t) for the parallel robot) to get time derivatives
       thomas_rows(h, w.O5, w.OM, Bo, b0, c.c.is_parallel ? c.R : c.J, c.R, 1, c.c.is_parallel ? 0 : 1);
-      LAUNCH_TP(h, k_out_knot_eval, w.Oc, Bo, w);
+      LAUNCH_TP(h, k_out_knot_eval, lOc, Bo, w);
       if (!c.c.is_parallel && c.c.trig_mode == 1)
         host_dyn_rr_out(h);
       else
-        LAUNCH_TP(h, k_out_trq, w.Oc, Bo, w, h->pm);
+        LAUNCH_TP(h, k_out_trq, lOc, Bo, w, h->pm);
       cur = w.OA;
     }
     LAUNCH_T(h, k_out_smooth_plan, Bo, w);
@@ -1419,6 +1433,7 @@ static int chunk_sweeps_output(batotp_handle h, bool haveN0) {
       if (h->hst[b].status & ST_STEP_CAP) stepCap = true;
       mxF = std::max(mxF, std::max(h->hst[b].nFwd, h->hst[b].nRev));
     }
+    h->mxSteps = mxF;
     if (!stepCap) {
       for (int b = 0; b < h->B; ++b) {
         const TrajState &t = h->hst[b];

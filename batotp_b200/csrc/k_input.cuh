@@ -153,6 +153,16 @@ __host__ __device__ __forceinline__ int find_seg(const AIn &aIn, int nIn, double
   return lo;
 }
 
+// the same answer from a starting guess (sites that are nearly uniform: two or three probes instead of
+// log2(n)): the first k with aOut < aIn[k+1] cannot lie below a k with aIn[k] <= aOut
+template <class AIn>
+__host__ __device__ __forceinline__ int find_seg_from(const AIn &aIn, int nIn, double aOut, int guess) {
+  int k = imin_(imax_(guess, 0), nIn - 2);
+  while (k > 0 && aOut < aIn(k)) k--;
+  while (k < nIn - 2 && !(aOut < aIn(k + 1))) k++;
+  return k;
+}
+
 struct UniformSites {  // a[k] = res * k   (util.h:101-107 applied to an iota, e.g. ba.cpp:803-805)
   double res;
   __host__ __device__ __forceinline__ double operator()(int k) const { return res * (double)k; }
@@ -844,7 +854,10 @@ __global__ void k_resample(Ws w, int npts, int nb) {
   const int nOld = s.nPts;
   const double aOut = s.sScale * (double)i;
   ViewSites in{sC};
-  const int seg = find_seg(in, nOld, aOut);
+  // the sites are the arc lengths of the constant-ds march: nearly uniform, so the search starts at the
+  // proportional position (a NaN or out-of-range estimate only costs probes)
+  const double est = aOut / sC[nOld - 1] * (double)(nOld - 1);
+  const int seg = find_seg_from(in, nOld, aOut, (est > 0.0 && est < 2.0e9) ? (int)est : 0);
   const double lo = sC[seg];
   const double den = sC[seg + 1] - lo;
   const double tau = (aOut - lo) / den;
@@ -855,9 +868,9 @@ __global__ void k_resample(Ws w, int npts, int nb) {
   double *qo = w.Q + (size_t)i * pst + (size_t)b * w.R;
   for (int r = 0; r < CFG.R; ++r) {
     Seg4 c;
-    c.c3 = (m1[r] - m0[r]) / 6.0;
+    c.c3 = sdiv::div6(m1[r] - m0[r]);
     c.c2 = m0[r] / 2.0;
-    c.c1 = y1[r] - y0[r] - (m1[r] + 2 * m0[r]) / 6.0;
+    c.c1 = y1[r] - y0[r] - sdiv::div6(m1[r] + 2 * m0[r]);
     c.c0 = y0[r];
     qo[r] = seg_value(c, tau, tau2, tau3);
   }
@@ -952,6 +965,47 @@ __global__ void k_build_table(Ws w, int npts, int nb) {
         t[rt * 4 + 2] = c.c1;
         t[rt * 4 + 3] = c.c0;
       }
+  }
+}
+
+// The same table for runs without dynamics rows (RT <= 10), built through shared-memory tiles of 16 segments
+// x 8 trajectories: the knots are read with trajectories fastest (the point-major order of P/M), the table is
+// written one trajectory at a time as contiguous 16*RT*32-byte runs.  Block (8, 16).
+#define BT_TRAJ 8
+#define BT_SEGS 16
+#define BT_ROWS 10
+__global__ void k_build_table_tile(Ws w, int npts, int nb) {
+  EMU_SHARED double tile[BT_TRAJ][BT_SEGS][BT_ROWS * 4];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int b0 = (int)blockIdx.x * BT_TRAJ, i0 = (int)(blockIdx.z * gridDim.y + blockIdx.y) * BT_SEGS;
+  const int RT = w.RT;
+  {
+    const int b = b0 + tx, i = i0 + ty;
+    if (b < nb && i < npts) {
+      const TrajState &s = w.st[b];
+      if (!(s.status & ST_FATAL_MASK) && i < s.nPtsC - 1) {
+        for (int r = 0; r < RT; ++r) {
+          const Seg4 c = seg_coef(rowv(w.P, w, b, r), rowv(w.M, w, b, r), i);
+          tile[tx][ty][r * 4 + 0] = 3 * c.c3;
+          tile[tx][ty][r * 4 + 1] = 2 * c.c2;
+          tile[tx][ty][r * 4 + 2] = c.c1;
+          tile[tx][ty][r * 4 + 3] = 6 * c.c3;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int tid = ty * BT_TRAJ + tx, per = RT * 4, run = BT_SEGS * per;
+  for (int bl = 0; bl < BT_TRAJ; ++bl) {
+    const int b = b0 + bl;
+    if (b >= nb) break;
+    const TrajState &s = w.st[b];
+    if (s.status & ST_FATAL_MASK) continue;
+    const int nSeg = imin_(imin_(s.nPtsC - 1, npts) - i0, BT_SEGS);  // valid segments of this tile
+    if (nSeg <= 0) continue;
+    double *t = w.tab + ((size_t)b * w.Nc + i0) * (size_t)per;
+    for (int e = tid; e < nSeg * per; e += BT_TRAJ * BT_SEGS) t[e] = tile[bl][e / per][e % per];
+    (void)run;
   }
 }
 
