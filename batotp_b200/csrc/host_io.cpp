@@ -378,3 +378,130 @@ int batotp_write_traj_csv(const char *path, const char *header, double sres, int
 }
 
 }  // extern "C"
+
+// ----------------------------------------------------------------------------- batch writer
+// BA::writeOutputData (ba.cpp:2510-2528) for the trajectories of a batch result, on writer threads of its own:
+// while they serialise chunk k (traj_out_<index>.dat = trajWriteBIN, s-sdot_<index>.dat = sdotWrite) the
+// caller's thread is free to run batotp_cuda_optimize_batch on chunk k+1.
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+
+struct batotp_writer {
+  struct Job {
+    batotp_cfg cfg;
+    batotp_batch_out out;  // shallow copy: the arrays stay the caller's until batotp_writer_wait returns
+    long long base;
+    int first, count;
+  };
+  std::string dir;
+  std::vector<std::thread> threads;
+  std::mutex mu;
+  std::condition_variable cvWork, cvIdle;
+  std::deque<std::pair<Job, int>> queue;  // (job, index within the job)
+  int busy = 0;
+  bool stop = false;
+  std::atomic<long long> written{0}, failed{0};
+
+  static int write_one(const std::string &dir, const Job &j, int b) {
+    const batotp_batch_out &o = j.out;
+    const int J = j.cfg.n_joints, C = j.cfg.n_cart;
+    if (o.status && (o.status[b] & BATOTP_ST_FATAL_MASK)) return 1;  // not optimised: the reference writes nothing
+    if (!o.theta_out || !o.n_out || o.out_cap <= 0) return -1;
+    const int n = o.n_out[b];
+    if (n <= 0 || n > o.out_cap) return -1;
+    const double sres = o.out_sres ? o.out_sres[b] : j.cfg.out_res;
+    char name[64];
+    snprintf(name, sizeof name, "traj_out_%07lld.dat", j.base + b);
+    const bool cartFull = o.cart_out && C > 0 && o.n_cart_out && o.n_cart_out[b] == n;  // ba.cpp:2629
+    const bool trqFull = j.cfg.is_trq_on && o.trq_out;
+    int rc = batotp_write_traj_bin((dir + name).c_str(), sres, (unsigned)n, J,
+                                   o.theta_out + (size_t)b * J * o.out_cap, C,
+                                   cartFull ? o.cart_out + (size_t)b * C * o.out_cap : nullptr,
+                                   trqFull ? o.trq_out + (size_t)b * J * o.out_cap : nullptr, o.out_cap);
+    if (rc == 0 && j.cfg.is_sdot_out && !j.cfg.is_interp_only && o.hist && o.hist_cap > 0 && o.n_rev && o.n_fwd) {
+      const float *h = o.hist + (size_t)b * 4 * o.hist_cap;
+      snprintf(name, sizeof name, "s-sdot_%07lld.dat", j.base + b);
+      rc = batotp_write_s_sdot((dir + name).c_str(), sres, o.n_rev[b], h, h + o.hist_cap, o.n_fwd[b],
+                               h + 2 * (size_t)o.hist_cap, h + 3 * (size_t)o.hist_cap);
+    }
+    return rc;
+  }
+  void run() {
+    for (;;) {
+      std::pair<Job, int> it;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cvWork.wait(lk, [&] { return stop || !queue.empty(); });
+        if (queue.empty()) return;
+        it = queue.front();
+        queue.pop_front();
+        busy++;
+      }
+      // one queue entry = a run of trajectories, so that the lock is taken rarely
+      const Job &j = it.first;
+      const int lo = it.second, hi = std::min(j.first + j.count, lo + 64);
+      for (int b = lo; b < hi; ++b) {
+        const int rc = write_one(dir, j, b);
+        if (rc == 0)
+          written++;
+        else if (rc < 0)
+          failed++;
+      }
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        busy--;
+        if (queue.empty() && busy == 0) cvIdle.notify_all();
+      }
+    }
+  }
+};
+
+extern "C" {
+
+int batotp_writer_create(const char *dir, int threads, batotp_writer **out) {
+  if (!dir || !out || threads < 1) return -1;
+  batotp_writer *w = new batotp_writer();
+  w->dir = dir;
+  if (!w->dir.empty() && w->dir.back() != '/') w->dir += '/';
+  for (int t = 0; t < threads; ++t) w->threads.emplace_back([w] { w->run(); });
+  *out = w;
+  return 0;
+}
+
+int batotp_writer_submit(batotp_writer *w, const batotp_cfg *cfg, const batotp_batch_out *out, long long base_index,
+                         int first, int count) {
+  if (!w || !cfg || !out || first < 0 || count < 0) return -1;
+  batotp_writer::Job j{*cfg, *out, base_index, first, count};
+  {
+    std::lock_guard<std::mutex> lk(w->mu);
+    for (int b = first; b < first + count; b += 64) w->queue.emplace_back(j, b);
+  }
+  w->cvWork.notify_all();
+  return 0;
+}
+
+int batotp_writer_wait(batotp_writer *w, long long *files_written, long long *files_failed) {
+  if (!w) return -1;
+  std::unique_lock<std::mutex> lk(w->mu);
+  w->cvIdle.wait(lk, [&] { return w->queue.empty() && w->busy == 0; });
+  if (files_written) *files_written = w->written.load();
+  if (files_failed) *files_failed = w->failed.load();
+  return w->failed.load() ? -1 : 0;
+}
+
+int batotp_writer_destroy(batotp_writer *w) {
+  if (!w) return -1;
+  {
+    std::lock_guard<std::mutex> lk(w->mu);
+    w->stop = true;
+  }
+  w->cvWork.notify_all();
+  for (auto &t : w->threads) t.join();
+  delete w;
+  return 0;
+}
+
+}  // extern "C"

@@ -82,8 +82,47 @@ def load(path: Optional[str] = None):
     L.batotp_cuda_fetch.argtypes = [C.c_void_p, C.POINTER(BatchOut)]
     L.batotp_cuda_mvc_per_sample.argtypes = [C.c_void_p, C.c_double, _dp, C.c_int]
     L.batotp_cuda_get_f64.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, _dp, C.c_int]
+    L.batotp_writer_create.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.batotp_writer_submit.argtypes = [C.c_void_p, C.POINTER(BatotpCfg), C.POINTER(BatchOut), C.c_longlong, C.c_int,
+                                       C.c_int]
+    L.batotp_writer_wait.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.batotp_writer_destroy.argtypes = [C.c_void_p]
     _libs[path] = L
     return L
+
+
+class Writer:
+    """Batch file writer (include/batotp_cuda.h: batotp_writer_*): traj_out_<index>.dat / s-sdot_<index>.dat."""
+
+    def __init__(self, directory: str, threads: int = 4, lib_path: Optional[str] = None):
+        self.L = load(lib_path)
+        h = C.c_void_p()
+        if self.L.batotp_writer_create(directory.encode(), threads, C.byref(h)) != 0:
+            raise NativeError("batotp_writer_create failed")
+        self.h = h
+        self._keep = []
+
+    def submit(self, cfg: BatotpCfg, res: "BatchResult", base_index: int, first: int, count: int):
+        self._keep.append((cfg, res))  # the arrays must outlive the write
+        if self.L.batotp_writer_submit(self.h, C.byref(cfg), C.byref(res.c), base_index, first, count) != 0:
+            raise NativeError("batotp_writer_submit failed")
+
+    def wait(self):
+        w, f = C.c_longlong(0), C.c_longlong(0)
+        rc = self.L.batotp_writer_wait(self.h, C.byref(w), C.byref(f))
+        self._keep.clear()
+        return rc, w.value, f.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.batotp_writer_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class BatchResult:

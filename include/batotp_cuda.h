@@ -165,6 +165,20 @@ int batotp_write_s_sdot(const char *path, double sres, int n_rev, const float *s
 int batotp_write_traj_csv(const char *path, const char *header, double sres, int n_pts, int n_joints,
                           const float *theta, int n_cart, const float *cart, int pitch);
 
+/* ---- batch writer: BA::writeOutputData (ba.cpp:2510-2528) for the trajectories of a batch result --------
+ * `threads` writer threads serialise <dir>/traj_out_<index>.dat (trajWriteBIN, ba.cpp:2582-2651) and, when the
+ * result carries the histories and is_sdotOut is set, <dir>/s-sdot_<index>.dat (sdotWrite, ba.cpp:2726-2759),
+ * index = base_index + b printed as %07lld, for b in [first, first+count).  _submit returns at once; the arrays
+ * of `out` must stay untouched until _wait returns, so a caller that alternates two result buffers overlaps
+ * the file output of chunk k with batotp_cuda_optimize_batch on chunk k+1.  Trajectories that were not
+ * optimised (fatal status) get no file, like the reference's early returns.  _wait returns -1 if a file failed. */
+typedef struct batotp_writer *batotp_writer_handle;
+int batotp_writer_create(const char *dir, int threads, batotp_writer_handle *out);
+int batotp_writer_submit(batotp_writer_handle w, const batotp_cfg *cfg, const batotp_batch_out *out,
+                         long long base_index, int first, int count);
+int batotp_writer_wait(batotp_writer_handle w, long long *files_written, long long *files_failed);
+int batotp_writer_destroy(batotp_writer_handle w);
+
 #ifdef __cplusplus
 }
 #endif

@@ -161,3 +161,34 @@ def test_interpolation_only_mode(ctx):
     r2 = P.run_device(ctx, cfg2, tres2, th2, None, out_cap=1024)
     assert (r2.status == 0).all() and (r2.n_out == r2.n_out[0]).all() and r2.n_out[0] > 400
     assert np.abs(r2.theta_out[:, :, 0] - th2[:, :, 0]).max() == 0  # a spline interpolates its first knot exactly
+
+
+def test_batch_writer_files_are_the_reference_formats(ctx, tmp_path):
+    """the batch writer's traj_out_<i>.dat / s-sdot_<i>.dat are trajWriteBIN / sdotWrite
+    byte for byte: the stock GEN7DOF folder gives the reference's own files, synthetic paths the packers that
+    the golden files pin; a trajectory that was not optimised gets no file."""
+    import os
+    g = __import__("__graft_entry__")
+    w = native.Writer(str(tmp_path), threads=3, lib_path=g.build_emu())
+    cfg, tres, th, ca, ts = P.load_stock("GEN7DOF")
+    res = P.run_device(ctx, cfg, tres, th, ca, ts)
+    w.submit(cfg, res, 100, 0, 1)
+    cfg2, tres2, th2, _ = P.load_synth("GEN7DOF", 20, 6)
+    th2 = th2.copy()
+    th2[3] = th2[3][:, :1]  # a path that does not move: not optimised
+    res2 = P.run_device(ctx, cfg2, tres2, th2, None)
+    assert res2.status[3] & native.ST_FATAL_MASK
+    w.submit(cfg2, res2, 0, 0, 6)
+    rc, written, failed = w.wait()
+    w.close()
+    assert (rc, written, failed) == (0, 6, 0)
+    d = P.GOLD + "/stock/GEN7DOF"
+    assert open(os.path.join(str(tmp_path), "traj_out_0000100.dat"), "rb").read() == open(d + "/ref_traj_out.dat", "rb").read()
+    assert open(os.path.join(str(tmp_path), "s-sdot_0000100.dat"), "rb").read() == open(d + "/ref_s-sdot.dat", "rb").read()
+    for b in range(6):
+        f = os.path.join(str(tmp_path), "traj_out_%07d.dat" % b)
+        if b == 3:
+            assert not os.path.exists(f)
+            continue
+        assert open(f, "rb").read() == P.device_traj_out_bytes(cfg2, res2, b)
+        assert open(os.path.join(str(tmp_path), "s-sdot_%07d.dat" % b), "rb").read() == P.device_s_sdot_bytes(res2, b)
