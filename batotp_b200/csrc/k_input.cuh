@@ -934,10 +934,11 @@ __global__ void k_final_plan(Ws w) {
   if (nNew > w.Nc) s.status |= ST_GRID_CAP;
 }
 
-// Sweep table (TP over segments): per (segment k, row r) four doubles.
-//   kinematic rows (joints, then Cartesian xyz when a Cartesian constraint is on):
-//       {3*c3, 2*c2, c1, 6*c3}  — the products evalSplinePartials forms first (ba.cpp:1359-1360)
-//   dynamics rows a1..a4 (torque on): {c3, c2, c1, c0}  (ba.cpp:1387-1405)
+// Segment table (TP over segments): per (segment k, row r) the four spline coefficients {c3, c2, c1, c0}
+// (spline.cpp:205-208) of the kinematic rows (joints, then Cartesian xyz when a Cartesian constraint is on)
+// and, with torque limits, of the dynamics rows a1..a4 (ba.cpp:1387-1405).  The sweep forms the products
+// evalSplinePartials starts from (3*c3, 2*c2, 6*c3; ba.cpp:1359-1360) when it loads a segment; the output
+// phase evaluates theta(t) from the same rows, so no consumer repeats the /6 divisions.
 __global__ void k_build_table(Ws w, int npts, int nb) {
   TP_DECOMP(nb);
   if (i >= npts) return;
@@ -951,10 +952,10 @@ __global__ void k_build_table(Ws w, int npts, int nb) {
   const int nKin = J + (CFG.cartOn ? 3 : 0);
   for (int r = 0; r < nKin; ++r, ++rt) {
     const Seg4 c = seg_coef(rowv(w.P, w, b, r), rowv(w.M, w, b, r), i);
-    t[rt * 4 + 0] = 3 * c.c3;
-    t[rt * 4 + 1] = 2 * c.c2;
+    t[rt * 4 + 0] = c.c3;
+    t[rt * 4 + 1] = c.c2;
     t[rt * 4 + 2] = c.c1;
-    t[rt * 4 + 3] = 6 * c.c3;
+    t[rt * 4 + 3] = c.c0;
   }
   if (CFG.trqOn) {
     for (int a = 0; a < 4; ++a)
@@ -986,10 +987,10 @@ __global__ void k_build_table_tile(Ws w, int npts, int nb) {
       if (!(s.status & ST_FATAL_MASK) && i < s.nPtsC - 1) {
         for (int r = 0; r < RT; ++r) {
           const Seg4 c = seg_coef(rowv(w.P, w, b, r), rowv(w.M, w, b, r), i);
-          tile[tx][ty][r * 4 + 0] = 3 * c.c3;
-          tile[tx][ty][r * 4 + 1] = 2 * c.c2;
+          tile[tx][ty][r * 4 + 0] = c.c3;
+          tile[tx][ty][r * 4 + 1] = c.c2;
           tile[tx][ty][r * 4 + 2] = c.c1;
-          tile[tx][ty][r * 4 + 3] = 6 * c.c3;
+          tile[tx][ty][r * 4 + 3] = c.c0;
         }
       }
     }

@@ -199,8 +199,8 @@ __global__ void k_out_s(Ws w, int npts, int nb) {
 __host__ __device__ __forceinline__ int first_seg_uniform(double res, int nIn, double a) {
   const int last = nIn - 2;
   int k = 0;
-  const double g = a / res;  // estimate only: corrected against the products the reference compares with
-  if (g > 0.0) k = (g < (double)last) ? (int)g : last;
+  const float g = (float)a / (float)res;  // estimate only: corrected against the products the reference compares with
+  if (g > 0.0f) k = (g < (float)last) ? (int)g : last;
   while (k > 0 && a < res * (double)k) k--;
   while (k < last && !(a < res * (double)(k + 1))) k++;
   return k;
@@ -272,9 +272,10 @@ __global__ void k_out_s_segs(Ws w, int npts, int nb) {
         UniformSites in{s.tStep};
         const double *sF = w.hist + (size_t)b * 4 * w.Sc + 2 * (size_t)w.Sc;
         const RV ys{const_cast<double *>(sF), 1}, ms{w.mS + (size_t)bl * w.Sc, 1};
+        const float rStep = 1.0f / (float)s.tStep;  // only steers the search
         auto s_at = [&](int ii) {
           const double t = tmvc_out(ii, s.nOver, tLast);
-          const int seg = find_seg(in, s.nFwd, t);
+          const int seg = find_seg_from(in, s.nFwd, t, (int)((float)t * rStep));
           const double ta = (t - in(seg)) / (in(seg + 1) - in(seg));
           const Seg4 c = seg_coef(ys, ms, seg);
           const double ta2 = ta * ta, ta3 = ta2 * ta;
@@ -598,38 +599,62 @@ __global__ void k_out_eval_smooth_rows(Ws w, double *dst, int npts, int nb) {
   int ww = imin_(wv, nIn);
   const int wMid = ww / 2 + ww % 2 - 1;
   if (wMid == WM && seg >= WM && seg + 1 < nIn - WM) {
-    double t0[NR], t1[NR], c3[NR], c2[NR], c1[NR], c0[NR];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) t0[r] = t1[r] = c3[r] = c2[r] = c1[r] = c0[r] = 0.0;
-    int cseg = -1;
+    // sites of the two windows first (independent loads), then one pass per distinct segment among them — the
+    // sites are in ascending segment order, so the sums still run over ascending q as smooth() does — with the
+    // coefficients {c3,c2,c1,c0} read from the segment table (no division left in this kernel's main path)
+    int sgq[2 * WM + 2];
+    double taq[2 * WM + 2];
 #pragma unroll
     for (int q = 0; q < 2 * WM + 2; ++q) {
       const size_t at = (size_t)(seg - WM + q) * w.Bo + bl;
-      const int sg = w.segO[at];
-      const double ta = w.tauO[at];
-      if (sg != cseg) {
-        const double *y0 = w.P + (size_t)sg * pst + (size_t)b * R, *m0 = w.M + (size_t)sg * pst + (size_t)b * R;
+      sgq[q] = w.segO[at];
+      taq[q] = w.tauO[at];
+    }
+    double t0[NR], t1[NR];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          const double a0 = y0[r], a1 = y0[pst + r], b0 = m0[r], b1 = m0[pst + r];
-          c3[r] = sdiv::div6(b1 - b0);
-          c2[r] = b0 / 2.0;
-          c1[r] = a1 - a0 - sdiv::div6(b1 + 2 * b0);
-          c0[r] = a0;
-        }
-        cseg = sg;
-      }
-      const double ta2 = ta * ta, ta3 = ta2 * ta;
+    for (int r = 0; r < NR; ++r) t0[r] = t1[r] = 0.0;
+    int sgc = sgq[0];
+    for (;;) {
+      const double *t = w.tab + ((size_t)b * w.Nc + sgc) * (size_t)w.RT * 4;
+      double c3[NR], c2[NR], c1[NR], c0[NR];
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
-        const double x = c3[r] * ta3 + c2[r] * ta2 + c1[r] * ta + c0[r];  // seg_value
-        if (q <= 2 * WM) t0[r] += x;
-        if (q >= 1) t1[r] += x;
+#ifdef BATOTP_HOST_EMU
+        c3[r] = t[r * 4 + 0];
+        c2[r] = t[r * 4 + 1];
+        c1[r] = t[r * 4 + 2];
+        c0[r] = t[r * 4 + 3];
+#else
+        const double2 lo = *reinterpret_cast<const double2 *>(t + r * 4);
+        const double2 hi = *reinterpret_cast<const double2 *>(t + r * 4 + 2);
+        c3[r] = lo.x;
+        c2[r] = lo.y;
+        c1[r] = hi.x;
+        c0[r] = hi.y;
+#endif
       }
+      int nx = 0x7fffffff;
+#pragma unroll
+      for (int q = 0; q < 2 * WM + 2; ++q) {
+        if (sgq[q] == sgc) {
+          const double ta = taq[q], ta2 = ta * ta, ta3 = ta2 * ta;
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            const double x = c3[r] * ta3 + c2[r] * ta2 + c1[r] * ta + c0[r];  // seg_value
+            if (q <= 2 * WM) t0[r] += x;
+            if (q >= 1) t1[r] += x;
+          }
+        } else if (sgq[q] > sgc) {
+          nx = imin_(nx, sgq[q]);
+        }
+      }
+      if (nx == 0x7fffffff) break;
+      sgc = nx;
     }
+    const sdiv::Rcp rw = {1.0 / (double)(2 * WM + 1), true};  // RN(1/w): folded at compile time
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-      const double v0 = t0[r] / (2 * WM + 1), v1 = t1[r] / (2 * WM + 1);
+      const double v0 = sdiv::div(t0[r], (double)(2 * WM + 1), rw), v1 = sdiv::div(t1[r], (double)(2 * WM + 1), rw);
       o[r] = v0 + (v1 - v0) * tau;
     }
   } else {
