@@ -10,7 +10,7 @@ import _parity as P  # noqa: E402
 from batotp_b200 import native  # noqa: E402
 
 ctx = native.Context(0)
-for name, n in (("GEN7DOF", 96), ("CSPR3DOF", 4)):
+for name, n in (("GEN7DOF", int(os.environ.get("TINY_N", "96"))), ("CSPR3DOF", 4)):
     cfg, tres, th, ca = P.load_synth(name, 0, n)
     ctx.set_out_chunk(40)
     res = P.run_device(ctx, cfg, tres, th, ca, out_cap=8192, hist_cap=8192)
