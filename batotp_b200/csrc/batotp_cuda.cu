@@ -1346,8 +1346,10 @@ int batotp_cuda_timer(batotp_handle h, int which, double *elapsed_ms) {
 }
 
 // The sweep kernel keeps one trajectory per lane resident for a whole sweep (SMs x SW_MIN_BLOCKS CTAs of
-// SW_NT lanes); a chunk larger than that leaves a thin second wave running on its own.  Automatic chunking
-// splits the batch into the fewest equal chunks that fit the resident lanes.
+// SW_NT lanes) and its duration hardly depends on how many lanes are filled (it is bound by the latency of
+// one trajectory), so a chunk larger than the resident lanes leaves a thin second wave running on its own and
+// a smaller one wastes lanes: automatic chunking takes full waves and leaves the remainder to the last chunk
+// (measured on the 131072-path step: 817 ms against 828 ms for three equal chunks).
 static int auto_chunk(batotp_handle h, int B) {
   int sms = 148;
 #ifndef BATOTP_HOST_EMU
@@ -1356,8 +1358,7 @@ static int auto_chunk(batotp_handle h, int B) {
   (void)h;
 #endif
   const int lanes = sms * SW_MIN_BLOCKS * SW_NT;
-  const int n = std::max(1, cdiv(B, lanes));
-  return std::max(SW_NT, cdiv(cdiv(B, n), SW_NT) * SW_NT);
+  return std::max(SW_NT, std::min(lanes, cdiv(B, SW_NT) * SW_NT));
 }
 
 static int load_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_in *in, int first, int B) {

@@ -301,10 +301,9 @@ def main_b200(args):
     # one C-ABI call per resident chunk; the results of a call land in one reusable pinned buffer
     if args.chunk > 0:
         sl = min(args.chunk, B)
-    else:  # the library's automatic split (batotp_cuda.cu auto_chunk): fewest equal chunks within SMs*3*128 lanes
+    else:  # the library's automatic split (batotp_cuda.cu auto_chunk): full waves of SMs*3*128 resident lanes
         lanes = torch.cuda.get_device_properties(local).multi_processor_count * 3 * 128
-        nch = max(1, -(-B // lanes))
-        sl = max(128, -(-(-(-B // nch)) // 128) * 128)
+        sl = max(128, min(lanes, -(-B // 128) * 128))
     out_cap = int(res_s.n_out.max()) + 64 if ok else 4096
     res_e = native.BatchResult(sl, J, 0, out_cap, 0, False, want_rows=True, want_hist=False, pinned=True)
     h_np = h_theta.numpy()

@@ -40,8 +40,8 @@ int batotp_cuda_create(int device, batotp_handle *out);
 int batotp_cuda_destroy(batotp_handle h);
 const char *batotp_cuda_last_error(batotp_handle h);
 /* trajectories resident per device pass (input interpolation + both sweeps run over the whole chunk; the
- * tables and histories of one chunk live in HBM).  0 (default) = automatic: a batch is split into the
- * fewest equal chunks that fit the sweep kernel's resident lanes (SMs x 3 CTAs x 128) */
+ * tables and histories of one chunk live in HBM).  0 (default) = automatic: chunks of the sweep kernel's
+ * resident lanes (SMs x 3 CTAs x 128 = 56832 on a B200), the remainder in the last chunk */
 int batotp_cuda_set_chunk(batotp_handle h, int chunk);
 /* trajectories per interpOutputData pass inside a chunk (bounds the oversampled-output buffers); default 8192 */
 int batotp_cuda_set_out_chunk(batotp_handle h, int n);
