@@ -168,10 +168,27 @@ struct batotp_ctx {
   int tabN = 0;
   Pmat pm;
   // staged inputs
-  void *d_theta = nullptr, *d_cart = nullptr;
-  double *d_ts = nullptr, *d_tres = nullptr;
+  // two input staging sets: while chunk k is computed from one, the host rows of chunk k+1 travel into the other
+  // on the copy stream (issue_inputs); d_tres / d_n0 point into the set bound to the resident chunk
+  struct InSet {
+    void *theta = nullptr, *cart = nullptr;
+    double *ts = nullptr, *tres = nullptr;
+    int *n0 = nullptr;
+    size_t capIn = 0, capInB = 0, capInTs = 0;
+    std::vector<double> tresHost;
+    const batotp_batch_in *src = nullptr;  // what the set holds: chunk [first, first+B) of this batch
+    int first = -1, B = 0;
+    bool onCopyStream = false;
+#ifndef BATOTP_HOST_EMU
+    cudaEvent_t ev = nullptr;
+#else
+    cudaEvent_t ev = 0;
+#endif
+  } inSet[2];
+  int curIn = 0;
+  double *d_tres = nullptr;
   int *d_n0 = nullptr;
-  size_t capIn = 0, capInB = 0, capInTs = 0;
+  bool copiesPending = false;  // row copies of the previous chunk may still be in flight on the copy stream
   const void *in_theta = nullptr, *in_cart = nullptr;  // device views used by k_in_load
   const double *in_ts = nullptr;
   bool inF64 = false, hasTheta = false, hasCart = false;
@@ -738,56 +755,101 @@ int dispatch_sweep(batotp_ctx *h) {
 #include "host_strict.inl"
 namespace {
 // ---- phases ---------------------------------------------------------------------------
+void free_inset(batotp_ctx::InSet &q) {
+  g_free(q.theta);
+  g_free(q.cart);
+  g_free(q.ts);
+  g_free(q.tres);
+  g_free(q.n0);
+  q.theta = q.cart = nullptr;
+  q.ts = q.tres = nullptr;
+  q.n0 = nullptr;
+  q.capIn = q.capInB = q.capInTs = 0;
+  q.src = nullptr;
+  q.first = -1;
+}
+
+// host rows of chunk [first, first+B) -> staging set `qi`, enqueued on stream `st`
+void issue_inputs(batotp_ctx *h, const batotp_batch_in *in, int first, int B, int qi, cudaStream_t st, bool onCopy) {
+  const DevCfg &c = h->cfg;
+  batotp_ctx::InSet &q = h->inSet[qi];
+  const int n0 = in->n0_max;
+  const bool f64 = (in->theta_f64 || in->cart_f64);
+  const size_t es = f64 ? 8 : 4;
+  const size_t thBytes = (size_t)B * c.J * n0 * es, caBytes = (size_t)B * c.Cin * n0 * es;
+  const void *th = f64 ? (const void *)in->theta_f64 : (const void *)in->theta_f32;
+  const void *ca = f64 ? (const void *)in->cart_f64 : (const void *)in->cart_f32;
+#ifndef BATOTP_HOST_EMU
+  if (!q.ev) CU_CHECK(cudaEventCreateWithFlags(&q.ev, cudaEventDisableTiming));
+  CU_CHECK(cudaEventSynchronize(q.ev));  // the set's previous transfer has left tresHost
+#endif
+  q.src = nullptr;
+  const size_t need = in->on_device ? 0 : std::max(thBytes, caBytes);  // resident rows are used where they are
+  const size_t needTs = in->on_device ? 0 : (size_t)B * n0;
+  if (need > q.capIn || (size_t)B > q.capInB || needTs > q.capInTs || !q.tres) {
+    free_inset(q);
+    const size_t capB = (size_t)B;
+    if (!in->on_device) {
+      q.theta = g_alloc(capB * c.J * n0 * 8);
+      q.cart = g_alloc(capB * std::max(c.Cin, 1) * n0 * 8);
+      q.ts = (double *)g_alloc(capB * n0 * 8);
+    }
+    q.tres = (double *)g_alloc(capB * 8);
+    q.n0 = (int *)g_alloc(capB * 4);
+    q.capIn = in->on_device ? 0 : capB * (size_t)std::max(c.J, c.Cin) * n0 * 8;
+    q.capInB = capB;
+    q.capInTs = in->on_device ? 0 : capB * (size_t)n0;
+  }
+  q.tresHost.resize(B);
+  for (int b = 0; b < B; ++b) q.tresHost[b] = in->tres ? in->tres[first + b] : in->tres_all;  // per-trajectory tres (small)
+  g_h2d(q.tres, q.tresHost.data(), (size_t)B * 8, st);
+  if (!in->on_device) {
+    if (th) g_h2d(q.theta, (const char *)th + (size_t)first * c.J * n0 * es, thBytes, st);
+    if (ca) g_h2d(q.cart, (const char *)ca + (size_t)first * c.Cin * n0 * es, caBytes, st);
+    if (in->timestamp) g_h2d(q.ts, in->timestamp + (size_t)first * n0, (size_t)B * n0 * 8, st);
+  }
+  if (in->n0) g_h2d(q.n0, in->n0 + first, (size_t)B * 4, st);
+  g_event_record(q.ev, st);
+  q.src = in;
+  q.first = first;
+  q.B = B;
+  q.onCopyStream = onCopy;
+}
+
+// binds the staging set that holds chunk [first, first+B) (transferring it now if no prefetch did)
 void stage_inputs(batotp_ctx *h, const batotp_batch_in *in, int first, int B) {
   const DevCfg &c = h->cfg;
   const int n0 = in->n0_max;
+  ProfScope ps_(h, "copy_h2d(stage)");
+  int qi = -1;
+  for (int k = 0; k < 2; ++k)
+    if (h->inSet[k].src == in && h->inSet[k].first == first && h->inSet[k].B == B) qi = k;
+  if (qi < 0) {
+    qi = h->curIn ^ 1;
+    issue_inputs(h, in, first, B, qi, h->stream, false);
+  } else if (h->inSet[qi].onCopyStream) {
+    g_stream_wait(h->stream, h->inSet[qi].ev);
+  }
+  h->curIn = qi;
+  const batotp_ctx::InSet &q = h->inSet[qi];
+  h->inSet[qi].src = nullptr;  // consumed: a later call with the same arguments must transfer again
   h->inF64 = (in->theta_f64 || in->cart_f64);
   h->hasTheta = (in->theta_f32 || in->theta_f64);
   h->hasCart = (in->cart_f32 || in->cart_f64);
   const size_t es = h->inF64 ? 8 : 4;
-  const size_t thBytes = (size_t)B * c.J * n0 * es, caBytes = (size_t)B * c.Cin * n0 * es;
   const void *th = h->inF64 ? (const void *)in->theta_f64 : (const void *)in->theta_f32;
   const void *ca = h->inF64 ? (const void *)in->cart_f64 : (const void *)in->cart_f32;
-  // per-trajectory tres / n0 (small)
-  std::vector<double> tres(B);
-  for (int b = 0; b < B; ++b) tres[b] = in->tres ? in->tres[first + b] : in->tres_all;
-  const size_t need = std::max(thBytes, caBytes);
-  if (need > h->capIn || (size_t)B > h->capInB || (size_t)B * n0 > h->capInTs || !h->d_tres) {
-    g_free(h->d_theta);
-    g_free(h->d_cart);
-    g_free(h->d_ts);
-    g_free(h->d_tres);
-    g_free(h->d_n0);
-    h->d_theta = h->d_cart = nullptr;
-    h->d_ts = h->d_tres = nullptr;
-    h->d_n0 = nullptr;
-    h->capIn = h->capInB = h->capInTs = 0;
-    const size_t capB = (size_t)B;
-    h->d_theta = g_alloc(capB * c.J * n0 * 8);
-    h->d_cart = g_alloc(capB * std::max(c.Cin, 1) * n0 * 8);
-    h->d_ts = (double *)g_alloc(capB * n0 * 8);
-    h->d_tres = (double *)g_alloc(capB * 8);
-    h->d_n0 = (int *)g_alloc(capB * 4);
-    h->capIn = capB * (size_t)std::max(c.J, c.Cin) * n0 * 8;
-    h->capInB = capB;
-    h->capInTs = capB * (size_t)n0;
-  }
-  ProfScope ps_(h, "copy_h2d(stage)");
-  g_h2d(h->d_tres, tres.data(), (size_t)B * 8, h->stream);
   if (in->on_device) {
     h->in_theta = th ? (const char *)th + (size_t)first * c.J * n0 * es : nullptr;
     h->in_cart = ca ? (const char *)ca + (size_t)first * c.Cin * n0 * es : nullptr;
     h->in_ts = in->timestamp ? in->timestamp + (size_t)first * n0 : nullptr;
   } else {
-    if (th) g_h2d(h->d_theta, (const char *)th + (size_t)first * c.J * n0 * es, thBytes, h->stream);
-    if (ca) g_h2d(h->d_cart, (const char *)ca + (size_t)first * c.Cin * n0 * es, caBytes, h->stream);
-    if (in->timestamp) g_h2d(h->d_ts, in->timestamp + (size_t)first * n0, (size_t)B * n0 * 8, h->stream);
-    h->in_theta = th ? h->d_theta : nullptr;
-    h->in_cart = ca ? h->d_cart : nullptr;
-    h->in_ts = in->timestamp ? h->d_ts : nullptr;
+    h->in_theta = th ? q.theta : nullptr;
+    h->in_cart = ca ? q.cart : nullptr;
+    h->in_ts = in->timestamp ? q.ts : nullptr;
   }
-  if (in->n0) g_h2d(h->d_n0, in->n0 + first, (size_t)B * 4, h->stream);
-  g_sync(h->stream);  // `tres` is a local
+  h->d_tres = q.tres;
+  h->d_n0 = q.n0;
   h->B = B;
   h->n0max = n0;
 }
@@ -1164,11 +1226,12 @@ int batotp_cuda_destroy(batotp_handle h) {
   free_ws(h);
   free_out(h);
   g_free(h->d_cN);
-  g_free(h->d_theta);
-  g_free(h->d_cart);
-  g_free(h->d_ts);
-  g_free(h->d_tres);
-  g_free(h->d_n0);
+  for (int k = 0; k < 2; ++k) {
+    free_inset(h->inSet[k]);
+#ifndef BATOTP_HOST_EMU
+    if (h->inSet[k].ev) cudaEventDestroy(h->inSet[k].ev);
+#endif
+  }
 #ifndef BATOTP_HOST_EMU
   cudaStreamDestroy(h->stream);
   cudaStreamDestroy(h->copyStream);
@@ -1477,7 +1540,10 @@ int batotp_cuda_load(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_
   try {
     if (in->B > h->chunk) h->chunk = in->B;
     h->lastHaveN0 = in->n0 != nullptr;
-    return load_chunk(h, cfg, in, 0, in->B);
+    h->inSet[0].src = h->inSet[1].src = nullptr;
+    const int rc = load_chunk(h, cfg, in, 0, in->B);
+    if (rc == 0) g_sync(h->stream);  // the caller's arrays are free again when this call returns
+    return rc;
   } catch (const Err &e) {
     h->err = e.msg;
     return -1;
@@ -1589,15 +1655,30 @@ int batotp_cuda_fetch(batotp_handle h, batotp_batch_out *out) {
 
 // one resident chunk [at, at+B) of the caller's batch through the whole path
 static void process_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_in *in, batotp_batch_out *out,
-                          int at, int B) {
+                          int at, int B, int nextB) {
   if (load_chunk(h, cfg, in, at, B) != 0) throw Err{h->err};
   h->lastHaveN0 = in->n0 != nullptr;
+  if (nextB > 0 && !in->on_device && !h->profile) {
+    // the host rows of the next chunk travel while this one is computed
+    try {
+      issue_inputs(h, in, at + B, nextB, h->curIn ^ 1, h->copyStream, true);
+    } catch (const Err &) {
+      h->inSet[h->curIn ^ 1].src = nullptr;  // no room for the second set: that chunk is staged when its turn comes
+    }
+  }
   if (h->cfg.c.is_interp_only) {  // ba.cpp:139-159: re-sample only
     if (do_interp_only(h, h->lastHaveN0) != 0) throw Err{h->err};
     fetch_sub(h, out, at);
     return;
   }
   if (chunk_interp_input(h, h->lastHaveN0) != 0) throw Err{h->err};
+  if (h->copiesPending) {
+    // the last rows / flags of the previous chunk may still be on their way to the host: the sweeps and the
+    // output phase (which overwrite the flags and the staging sets) queue up behind those copies
+    g_stream_wait(h->stream, h->evCopied[0]);
+    g_stream_wait(h->stream, h->evCopied[1]);
+    h->copiesPending = false;
+  }
   if (chunk_sweeps_output(h, h->lastHaveN0) != 0) throw Err{h->err};
   {
       const DevCfg &c = h->cfg;
@@ -1624,7 +1705,7 @@ static void process_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_b
           g_event_record(h->evCopied[q], h->copyStream);
         }
         fetch_scalars(h, out, at, 0, B);
-        g_sync(h->copyStream);
+        h->copiesPending = true;  // waited for before the next chunk's sweeps, or before the call returns
       }
   }
 }
@@ -1635,15 +1716,18 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
   try {
     bool first = true;
     int chunk = h->chunk > 0 ? h->chunk : auto_chunk(h, in->B);
+    h->inSet[0].src = h->inSet[1].src = nullptr;
     for (int at = 0; at < in->B;) {
       const int B = std::min(chunk, in->B - at);
       try {
-        process_chunk(h, first ? cfg : nullptr, in, out, at, B);
+        process_chunk(h, first ? cfg : nullptr, in, out, at, B, std::min(chunk, in->B - at - B));
       } catch (const Err &e) {
         // a workspace did not fit (long paths, many rows): release everything and go on with smaller chunks
         if (!e.oom || (chunk <= 256 && h->outChunk <= 256)) throw;
         g_sync(h->stream);
         g_sync(h->copyStream);
+        h->copiesPending = false;
+        h->inSet[0].src = h->inSet[1].src = nullptr;
         free_ws(h);
         free_out(h);
         if (h->allocPhase == 1 && std::min(h->outChunk, chunk) > 256)
@@ -1655,9 +1739,15 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
       first = false;
       at += B;
     }
+    g_sync(h->copyStream);  // every row has reached the caller's buffers
+    h->copiesPending = false;
     return 0;
   } catch (const Err &e) {
     h->err = e.msg;
+#ifndef BATOTP_HOST_EMU
+    cudaStreamSynchronize(h->copyStream);
+#endif
+    h->copiesPending = false;
     return -1;
   }
 }
