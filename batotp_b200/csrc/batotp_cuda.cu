@@ -909,7 +909,16 @@ int do_interp_input(batotp_ctx *h, bool haveN0, bool planSync) {
       if (need > w.Nc) return need;  // caller grows the workspace and restarts the chunk
     }
     thomas_rows(h, w.P, w.M, B, 0, c.R, c.R, 0, 0);
-    LAUNCH_T(h, k_march, B, w);
+    if (c.J == 7 && c.C == 3)
+      LAUNCH_T(h, (k_march<7, 3>), B, w);
+    else if (c.J == 6 && c.C == 7)
+      LAUNCH_T(h, (k_march<6, 7>), B, w);
+    else if (c.J == 3 && c.C == 3)
+      LAUNCH_T(h, (k_march<3, 3>), B, w);
+    else if (c.J == 2 && c.C == 3)
+      LAUNCH_T(h, (k_march<2, 3>), B, w);
+    else
+      LAUNCH_T(h, (k_march<0, 0>), B, w);
     std::swap(w.P, w.Q);
     apply_kinematics(h, 1);
     LAUNCH_T(h, k_adjust_s, B, w, 0);

@@ -714,12 +714,15 @@ __global__ void k_thomas_rows(Ws w, double *src, double *dst, int nb, int b0, in
 // ba.cpp:651-781: constant-ds march along the weighted arc length.  Source rows P (+M), emits Q.
 // evalSplinePartials (ba.cpp:1341-1380) supplies the values; the Cartesian rows are refreshed
 // only when a Cartesian constraint is on, otherwise Traj::cartpt keeps its previous content.
+// JT / CT: joints and Cartesian rows as compile-time constants (0 = take them from the configuration), so that
+// the joint loops unroll and `last` / `cartpt` stay in registers instead of local memory.
+template <int JT, int CT>
 __global__ void k_march(Ws w) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= w.B) return;
   TrajState &s = w.st[b];
   if (s.status & ST_FATAL_MASK) return;
-  const int J = CFG.J, C = CFG.C, R = CFG.R;
+  const int J = JT ? JT : CFG.J, C = CT ? CT : CFG.C, R = J + C;
   const int nPts = s.nPts;
   const RV sC = vecv(w.sC, w, b);
   const size_t pst = (size_t)w.B * w.R;
@@ -727,8 +730,11 @@ __global__ void k_march(Ws w) {
   double *Q = w.Q + (size_t)b * w.R;
   const int Nc = w.Nc;
   double last[MAXD + 3];  // the previously emitted point (theta rows, cart xyz)
+  #pragma unroll
   for (int r = 0; r < R; ++r) Q[r] = P[r];
+  #pragma unroll
   for (int j = 0; j < J; ++j) last[j] = P[j];
+  #pragma unroll
   for (int j = 0; j < 3; ++j) last[MAXD + j] = P[J + j];
   double sPrv = 0, prv_ds = 0;
   int CurNewPt = 1, CurOldPt = 1;
@@ -737,16 +743,19 @@ __global__ void k_march(Ws w) {
   const int lastSeg = nPts - 2;
   const bool cartEval = CFG.cartOn != 0;
   double cartpt[MAXD];
+  #pragma unroll
   for (int q = 0; q < MAXD; ++q) cartpt[q] = s.cartpt[q];
   const double sCend = sC[nPts - 1];
   while (!isDone) {
     const double *po = P + (size_t)CurOldPt * pst;
     double dthetaSQ = 0;
+    #pragma unroll
     for (int j = 0; j < J; ++j) {
       const double d = po[j] - last[j];
       dthetaSQ += d * d;
     }
     double dcartSQ = 0;
+    #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const double d = po[J + j] - last[MAXD + j];
       dcartSQ += d * d;
@@ -794,6 +803,7 @@ __global__ void k_march(Ws w) {
         }
         const double *y0 = P + (size_t)seg * pst, *y1 = y0 + pst, *m0 = M + (size_t)seg * pst, *m1 = m0 + pst;
         double *qo = Q + (size_t)CurNewPt * pst;
+        #pragma unroll
         for (int j = 0; j < J; ++j) {
           Seg4 c;
           c.c3 = sdiv::div6(m1[j] - m0[j]);
@@ -805,6 +815,7 @@ __global__ void k_march(Ws w) {
           last[j] = v;
         }
         if (cartEval)
+          #pragma unroll
           for (int j = 0; j < C; ++j) {
             const int r = J + j;
             Seg4 c;
@@ -814,7 +825,9 @@ __global__ void k_march(Ws w) {
             c.c0 = y0[r];
             cartpt[j] = seg_value(c, tau, tau2, tau3);
           }
+        #pragma unroll
         for (int j = 0; j < C; ++j) qo[J + j] = cartpt[j];
+        #pragma unroll
         for (int j = 0; j < 3; ++j) last[MAXD + j] = cartpt[j];
         CurOldPt = seg + 1;
         CurNewPt++;
@@ -832,8 +845,10 @@ __global__ void k_march(Ws w) {
   {
     const double *pe = P + (size_t)(nPts - 1) * pst;
     double *qo = Q + (size_t)CurNewPt * pst;
+    #pragma unroll
     for (int r = 0; r < R; ++r) qo[r] = pe[r];
   }
+  #pragma unroll
   for (int q = 0; q < MAXD; ++q) s.cartpt[q] = cartpt[q];
   s.nPts = CurNewPt + 1;
   s.sres = s.sResNew;
