@@ -10,7 +10,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -221,6 +224,12 @@ struct batotp_ctx {
   // optional per-kernel device timing (batotp_cuda_set_profile): serialises every launch
   bool profile = false;
   std::map<std::string, std::pair<double, long>> prof;
+  // tail overlap (batotp_cuda_optimize_batch): a last chunk that fills at most one sweep CTA per SM runs on a second
+  // context (own streams and workspaces, one host thread) next to the output / input phases of the full chunks
+  batotp_ctx *helper = nullptr;
+  bool tailOverlap = true;
+  std::function<void()> onSweepsDone;  // called once the sweeps of a chunk have completed on the device
+  std::function<void()> beforeSweeps;  // called after interpInputData of a chunk has been enqueued (may block)
 #ifndef BATOTP_HOST_EMU
   cudaEvent_t evS0 = nullptr, evS1 = nullptr, evT[2] = {nullptr, nullptr}, evP[2] = {nullptr, nullptr};
   cudaEvent_t evOut[2] = {nullptr, nullptr}, evCopied[2] = {nullptr, nullptr};
@@ -1232,6 +1241,8 @@ int batotp_cuda_create(int device, batotp_handle *out) {
 
 int batotp_cuda_destroy(batotp_handle h) {
   if (!h) return -1;
+  if (h->helper) batotp_cuda_destroy(h->helper);
+  h->helper = nullptr;
   free_ws(h);
   free_out(h);
   g_free(h->d_cN);
@@ -1681,6 +1692,7 @@ static void process_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_b
     return;
   }
   if (chunk_interp_input(h, h->lastHaveN0) != 0) throw Err{h->err};
+  if (h->beforeSweeps) h->beforeSweeps();
   if (h->copiesPending) {
     // the last rows / flags of the previous chunk may still be on their way to the host: the sweeps and the
     // output phase (which overwrite the flags and the staging sets) queue up behind those copies
@@ -1689,6 +1701,7 @@ static void process_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_b
     h->copiesPending = false;
   }
   if (chunk_sweeps_output(h, h->lastHaveN0) != 0) throw Err{h->err};
+  if (h->onSweepsDone) h->onSweepsDone();
   {
       const DevCfg &c = h->cfg;
       const bool strictQuatOut = out->cart_out && out->out_cap > 0 && c.Cin > 0 && c.C == 7 && c.c.trig_mode == 1;
@@ -1719,44 +1732,149 @@ static void process_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_b
   }
 }
 
+int batotp_cuda_set_tail_overlap(batotp_handle h, int on) {
+  if (!h) return -1;
+  h->tailOverlap = on != 0;
+  return 0;
+}
+
+// The chunks [0, mainB) of a batch on context h, one after the other (out-of-memory: smaller chunks)
+static void run_chunks(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_in *in, batotp_batch_out *out,
+                       int from, int mainB, int &chunk, bool &first) {
+  for (int at = from; at < mainB;) {
+    const int B = std::min(chunk, mainB - at);
+    try {
+      process_chunk(h, first ? cfg : nullptr, in, out, at, B, std::min(chunk, mainB - at - B));
+    } catch (const Err &e) {
+      // a workspace did not fit (long paths, many rows): release everything and go on with smaller chunks
+      if (!e.oom || (chunk <= 256 && h->outChunk <= 256)) throw;
+      g_sync(h->stream);
+      g_sync(h->copyStream);
+      h->copiesPending = false;
+      h->inSet[0].src = h->inSet[1].src = nullptr;
+      free_ws(h);
+      free_out(h);
+      if (h->allocPhase == 1 && std::min(h->outChunk, chunk) > 256)
+        h->outChunk = std::max(256, std::min(h->outChunk, chunk) / 2);
+      else
+        chunk = std::max(256, (chunk / 2 + SW_NT - 1) / SW_NT * SW_NT);
+      continue;
+    }
+    first = false;
+    at += B;
+  }
+}
+
+// Tail overlap.  The sweep kernel is bound by the latency of one trajectory, so a last chunk that fills only a
+// fraction of the resident lanes costs a whole sweep on its own (131072 paths = 2 full waves + 17408 paths).  When
+// that tail fits into ONE sweep CTA per SM it leaves two thirds of every SM free: it is handed to a second context
+// (own streams and workspaces, driven by one host thread): its input interpolation runs at once, its sweeps
+// start when the sweeps of the first full chunk have completed, so that they run beside the bandwidth-bound
+// output / input phases of the full chunks instead of after them.  Results are the same bytes either way (trajectories are independent).
 int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_in *in,
                                batotp_batch_out *out) {
   if (!h || !cfg || !in || !out) return -1;
+  bool first = true;
+  int chunk = h->chunk > 0 ? h->chunk : auto_chunk(h, in->B);
+  int mainB = in->B, tail = 0;
+  std::thread tailThread;
+  std::mutex mu;
+  std::condition_variable cv;
+  int go = 0;  // 0 wait, 1 run the tail, 2 skip it
+  struct { bool failed = false, oom = false; std::string msg; } tailRes;
+  auto signal = [&](int v) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (go == 0) go = v;
+    cv.notify_all();
+  };
+  auto finish_tail = [&](int v) {  // every exit path: let the tail thread go (or skip) and wait for it
+    h->onSweepsDone = nullptr;
+    if (tailThread.joinable()) {
+      signal(v);
+      tailThread.join();
+    }
+  };
   try {
-    bool first = true;
-    int chunk = h->chunk > 0 ? h->chunk : auto_chunk(h, in->B);
     h->inSet[0].src = h->inSet[1].src = nullptr;
-    for (int at = 0; at < in->B;) {
-      const int B = std::min(chunk, in->B - at);
-      try {
-        process_chunk(h, first ? cfg : nullptr, in, out, at, B, std::min(chunk, in->B - at - B));
-      } catch (const Err &e) {
-        // a workspace did not fit (long paths, many rows): release everything and go on with smaller chunks
-        if (!e.oom || (chunk <= 256 && h->outChunk <= 256)) throw;
-        g_sync(h->stream);
-        g_sync(h->copyStream);
-        h->copiesPending = false;
-        h->inSet[0].src = h->inSet[1].src = nullptr;
-        free_ws(h);
-        free_out(h);
-        if (h->allocPhase == 1 && std::min(h->outChunk, chunk) > 256)
-          h->outChunk = std::max(256, std::min(h->outChunk, chunk) / 2);
-        else
-          chunk = std::max(256, (chunk / 2 + SW_NT - 1) / SW_NT * SW_NT);
-        continue;
+#ifndef BATOTP_HOST_EMU
+    if (h->tailOverlap && !h->profile && !out->on_device && !cfg->is_interp_only && in->B > chunk) {
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+      const int t = in->B % chunk;
+      if (t > 0 && t <= sms * SW_NT) {
+        if (!h->helper && batotp_cuda_create(h->device, &h->helper) != 0) h->helper = nullptr;
+        if (h->helper) {
+          tail = t;
+          mainB = in->B - tail;
+          batotp_ctx *hp = h->helper;
+          hp->tailOverlap = false;
+          hp->chunk = 0;
+          hp->outChunk = h->outChunk;
+          hp->maxSteps = h->maxSteps;
+          hp->keepF64 = h->keepF64;
+          h->onSweepsDone = [&]() { signal(1); };
+          // the tail's input interpolation runs at once (beside that of the first full chunk); its sweeps wait
+          // until the sweeps of the first full chunk have completed, so that they run beside output / input phases
+          hp->beforeSweeps = [&]() {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return go != 0; });
+            if (go != 1) throw Err{"tail chunk skipped"};
+          };
+          tailThread = std::thread([&, hp]() {
+            try {
+              hp->inSet[0].src = hp->inSet[1].src = nullptr;
+              const bool same = hp->haveCfg && memcmp(&hp->cfg.c, cfg, sizeof(batotp_cfg)) == 0;
+              process_chunk(hp, same ? nullptr : cfg, in, out, mainB, tail, 0);
+              g_sync(hp->copyStream);
+              hp->copiesPending = false;
+              hp->beforeSweeps = nullptr;
+            } catch (const Err &e) {
+              hp->beforeSweeps = nullptr;
+              tailRes.failed = true;
+              tailRes.oom = e.oom;
+              tailRes.msg = e.msg;
+              cudaStreamSynchronize(hp->stream);
+              cudaStreamSynchronize(hp->copyStream);
+              hp->copiesPending = false;
+            }
+          });
+        }
       }
-      first = false;
-      at += B;
+    }
+#endif
+    run_chunks(h, cfg, in, out, 0, mainB, chunk, first);
+    finish_tail(1);
+    if (tail > 0) {
+      batotp_ctx *hp = h->helper;
+      h->sweepMs += hp->sweepMs;
+      h->sweepLaunches += hp->sweepLaunches;
+      h->cntVerify += hp->cntVerify;
+      h->cntSteps += hp->cntSteps;
+      h->cntTraj += hp->cntTraj;
+      h->launches += hp->launches;
+      batotp_cuda_stats_reset(hp);
+      if (tailRes.failed) {
+        if (!tailRes.oom) throw Err{tailRes.msg};
+        // no room for the second context's workspaces: release them and run the tail here
+        free_ws(hp);
+        free_out(hp);
+        run_chunks(h, cfg, in, out, mainB, in->B, chunk, first);
+      }
     }
     g_sync(h->copyStream);  // every row has reached the caller's buffers
     h->copiesPending = false;
     return 0;
   } catch (const Err &e) {
+    finish_tail(2);
     h->err = e.msg;
 #ifndef BATOTP_HOST_EMU
     cudaStreamSynchronize(h->copyStream);
 #endif
     h->copiesPending = false;
+    return -1;
+  } catch (...) {
+    finish_tail(2);
+    h->err = "unexpected exception in batotp_cuda_optimize_batch";
     return -1;
   }
 }

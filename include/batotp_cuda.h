@@ -49,6 +49,11 @@ int batotp_cuda_set_out_chunk(batotp_handle h, int n);
  * trajectory that needs more steps (the reference would run it until maxIntegTime, ba.cpp:1117-1122) keeps
  * BATOTP_ST_STEP_CAP and is reported as not optimised; n >= 1024 */
 int batotp_cuda_set_max_steps(batotp_handle h, int n);
+/* tail overlap of batotp_cuda_optimize_batch (default on): when the last chunk of a batch fills at most one sweep
+ * CTA per SM (<= SMs x 128 trajectories) it runs on a second context inside the library (own streams and
+ * workspaces, one host thread), beside the output / input phases of the full chunks instead of after them.
+ * Results are identical either way; 0 switches it off (one context, chunks strictly one after the other) */
+int batotp_cuda_set_tail_overlap(batotp_handle h, int on);
 /* number of kernels launched by this context since creation (for the benchmark's gpu_launches) */
 long batotp_cuda_launch_count(batotp_handle h);
 /* measurement hooks for bench.py.

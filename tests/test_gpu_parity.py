@@ -61,6 +61,30 @@ def test_chunking_does_not_change_results(ctx):
         assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
 
 
+def test_tail_overlap_does_not_change_results(ctx):
+    """A last chunk that fits one sweep CTA per SM runs on the library's second context beside the full chunks
+    (batotp_cuda_set_tail_overlap); every output and the work counters are the same as with one context."""
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 7000, 2 * 1024 + 300)
+    ctx.set_chunk(1024)
+    try:
+        runs = []
+        for on in (True, False, True):
+            ctx.set_tail_overlap(on)
+            ctx.stats_reset()
+            r = P.run_device(ctx, cfg, tres, th, None, out_cap=4096, hist_cap=4096)
+            runs.append((r, ctx.stats()))
+    finally:
+        ctx.set_tail_overlap(True)
+        ctx.set_chunk(16384)
+    (a, sa), (b, sb), (c, sc) = runs
+    assert (a.status & native.ST_FATAL_MASK == 0).all()
+    for nm in ("status", "n_rev", "n_fwd", "n_out", "t_total", "theta_out", "hist", "flags"):
+        assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
+        assert np.array_equal(getattr(a, nm), getattr(c, nm)), nm
+    for k in ("verifies", "steps", "trajectories", "sweep_launches"):
+        assert sa[k] == sb[k] == sc[k], k
+
+
 def test_ragged_short_and_degenerate_inputs(ctx):
     cfg, tres, th, _ = P.load_synth("GEN7DOF", 7, 6)
     th = th.copy()
