@@ -277,14 +277,14 @@ def main_b200(args):
     traffic, traffic_src = None, None
     try:
         import csv
-        prof = os.path.join(ROOT, "profiles", "r1d_sweep_ncu_full_summary.csv")
+        prof = os.path.join(ROOT, "profiles", "r1f_sweep_ncu_full_summary.csv")
         vals = {r[0]: (r[1], float(r[2])) for r in csv.reader(open(prof)) if len(r) == 3 and not r[0].startswith("#")
                 and r[0] != "metric"}
         gb = sum(v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
                  for k, (u, v) in vals.items() if k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
         per_launch_traj = ntraj / max(st["sweep_launches"], 1)
         traffic = gb / 56832.0 * per_launch_traj
-        traffic_src = "profiles/r1d_sweep_ncu_full_summary.csv (dram__bytes_read+write of a 56832-path launch, per path)"
+        traffic_src = "profiles/r1f_sweep_ncu_full_summary.csv (dram__bytes_read+write of a 56832-path launch, per path)"
     except Exception:
         pass
     roof = dict(bound="fp64", achieved=achieved, peak=peak_fma, unit="TFLOP/s", frac=achieved / max(peak_fma, 1e-12),
