@@ -191,7 +191,7 @@ def main_reference(args):
                                   sample="%d paths per step, %d timed steps, wall %.1f s" % (per_step, args.steps, wall)),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
-    print(json.dumps(line))
+    emit_line(json.dumps(line))
     return 0
 
 
@@ -358,7 +358,7 @@ def main_b200(args):
                 line["cpu_baseline"] = cpu_sample_rate(theta, tres, args.cpu_seconds)
             except Exception as e:  # the checker libraries are optional at bench time
                 line["cpu_baseline"] = dict(value=None, unit=UNIT, cores=cpu_threads(), kind="unavailable", sample=str(e))
-        print(json.dumps(line))
+        emit_line(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -366,8 +366,26 @@ def main_b200(args):
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit_line(text):
+    """The one JSON line of this process, on the real stdout (see main)."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        print(text, flush=True)
+        return
+    os.write(_REAL_STDOUT, (text + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    # Rank 0's stdout carries exactly one JSON line: whatever libraries print there meanwhile (NCCL's version
+    # banner, for one) goes to stderr; emit_line writes to the saved descriptor.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return main_reference(args)
     return main_b200(args)
