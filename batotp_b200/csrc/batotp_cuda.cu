@@ -1100,8 +1100,19 @@ void do_interp_output(batotp_ctx *h, int b0, int Bo) {
     if (c.trqOn) thomas_rows(h, trqCur, w.TrqM, Bo, b0, c.J, MAXD, 2, 0);
   }
   const bool strictQuat = (c.C == 7 && c.c.trig_mode == 1);
-  LAUNCH_PT(h, k_out_pack, w.OutC, Bo, w, cur, w.OM, trqCur, w.TrqM, h->d_thetaOut, h->d_cartOut, h->d_trqOut,
-            strictQuat ? h->d_cartOutD : (double *)nullptr, h->d_outD);
+  if (c.c.robot_type == BATOTP_GENJNT && c.C != 7 && c.Cin <= MAXD && !c.trqOn && !h->d_outD && w.OutC > 0 && Bo > 0) {
+    // generic robot, float rows only: warp-per-tile staging through shared memory (k_out_pack_rows)
+    const long long rows = cdiv(Bo, OP_WARPS);
+    const long long gy = std::min<long long>(rows, 32768), gz = (rows + gy - 1) / gy;
+    ProfScope ps_(h, "k_out_pack_rows");
+    BATOTP_LAUNCH_WARP(k_out_pack_rows, dim3((unsigned)cdiv(w.OutC, 32), (unsigned)gy, (unsigned)gz),
+                       dim3(32, OP_WARPS, 1), 0, h->stream, w, cur, w.OM, h->d_thetaOut, h->d_cartOut, w.OutC, Bo);
+    g_check_launch();
+    h->launches++;
+  } else {
+    LAUNCH_PT(h, k_out_pack, w.OutC, Bo, w, cur, w.OM, trqCur, w.TrqM, h->d_thetaOut, h->d_cartOut, h->d_trqOut,
+              strictQuat ? h->d_cartOutD : (double *)nullptr, h->d_outD);
+  }
   LAUNCH_PT(h, k_pack_hist, w.Sc, Bo, w, h->d_histOut);
   h->phase = 4;
 }

@@ -780,6 +780,109 @@ __global__ void k_out_pack(Ws w, double *src, double *srcM, double *trqSrc, doub
   }
 }
 
+// k_out_pack for a generic robot without torque rows and without the FP64 copy (GEN7DOF / GENJNT batches): one warp
+// per (trajectory, 32 consecutive output points).  The source rows are point-major, so the knots a tile needs -
+// the points seg(i0) .. seg(i0+31)+1 of ONE trajectory, J contiguous doubles each - are staged cooperatively in
+// shared memory (lanes run over (point, row), rows fastest: each request touches a few 8*J-byte runs instead of
+// 32 scattered sectors), then every lane evaluates its output point for all rows with the expressions of
+// k_out_pack and the float rows are written coalesced.  The Cartesian rows of a generic robot are plain copies
+// of the source rows at the same index (k_out_pack: `re && !generic`), staged the same way.  A tile whose
+// source range does not fit the staging buffer (output much coarser than the source) reads the knots directly.
+// Block (32, OP_WARPS).
+#define OP_WARPS 8
+#define OP_CAP 40
+struct SView {
+  const double *p;
+  int st;
+  __host__ __device__ __forceinline__ double operator[](int i) const { return p[i * st]; }
+};
+__global__ void k_out_pack_rows(Ws w, double *src, double *srcM, float *thetaOut, float *cartOut, int npts, int nb) {
+  EMU_SHARED double sY[OP_WARPS][OP_CAP * MAXD];
+  EMU_SHARED double sM[OP_WARPS][OP_CAP * MAXD];
+  const int lane = threadIdx.x, wy = threadIdx.y;
+  const int i0 = (int)blockIdx.x * 32, i = i0 + lane;
+  const int bl = (int)(blockIdx.z * gridDim.y + blockIdx.y) * OP_WARPS + wy;
+  if (bl >= nb) return;  // the whole warp
+  const TrajState &s = w.st[w.b0 + bl];
+  const int J = CFG.J, Cin = CFG.Cin;
+  const bool fatal = (s.status & ST_FATAL_MASK) != 0;
+  const bool inRange = i < npts;
+  const size_t pst = (size_t)w.Bo * w.R;
+  // ---------------- joint rows
+  const int nOut = fatal ? 0 : imin_(s.nOut, npts);
+  const bool live = i < nOut;
+  if (i0 < nOut) {  // warp-uniform
+    const bool re = s.isReinterp != 0;
+    int seg = live ? i : nOut - 1;
+    double tau = 0, tau2 = 0, tau3 = 0;
+    if (re) {
+      UniformSites s1{1. / (double)(s.nSm - 1)}, s2{1. / (double)(s.nOut - 1)};
+      const double a = s2(live ? i : nOut - 1);
+      seg = find_seg(s1, s.nSm, a);
+      tau = (a - s1(seg)) / (s1(seg + 1) - s1(seg));
+      tau2 = tau * tau;
+      tau3 = tau2 * tau;
+    }
+    const int lastLive = imin_(nOut - 1 - i0, 31);
+    const int segLo = __shfl_sync(0xffffffffu, seg, 0);
+    const int segHi = __shfl_sync(0xffffffffu, seg, lastLive) + (re ? 1 : 0);
+    const int np = segHi - segLo + 1;
+    // every live lane's knots inside the staged range (they are, for the non-decreasing seg of regular sites)
+    const bool inside = !live || (seg >= segLo && seg + (re ? 1 : 0) <= segHi);
+    if (__all_sync(0xffffffffu, inside) && np <= OP_CAP && np > 0) {  // warp-uniform
+      const double *py = src + (size_t)bl * w.R + (size_t)segLo * pst;
+      const double *pm = srcM + (size_t)bl * w.R + (size_t)segLo * pst;
+      for (int e = lane; e < np * J; e += 32) {
+        const int p = e / J, r = e - p * J;
+        sY[wy][e] = py[(size_t)p * pst + r];
+        if (re) sM[wy][e] = pm[(size_t)p * pst + r];
+      }
+      __syncwarp();
+      if (live) {
+        const int o = (seg - segLo) * J;
+        for (int r = 0; r < J; ++r) {
+          double v;
+          if (re)
+            v = seg_value(seg_coef(SView{&sY[wy][o + r], J}, SView{&sM[wy][o + r], J}, 0), tau, tau2, tau3);
+          else
+            v = sY[wy][o + r];
+          thetaOut[((size_t)bl * J + r) * w.OutC + i] = (float)v;
+        }
+      }
+      __syncwarp();  // the staging buffer is reused below
+    } else if (live) {
+      for (int r = 0; r < J; ++r) {
+        double v;
+        if (re)
+          v = seg_value(seg_coef(orowv(src, w, bl, r), orowv(srcM, w, bl, r), seg), tau, tau2, tau3);
+        else
+          v = orowv(src, w, bl, r)[i];
+        thetaOut[((size_t)bl * J + r) * w.OutC + i] = (float)v;
+      }
+    }
+  }
+  if (!live && inRange)  // rows are zero beyond their length (and for trajectories that were not optimised)
+    for (int r = 0; r < J; ++r) thetaOut[((size_t)bl * J + r) * w.OutC + i] = 0.f;
+  // ---------------- Cartesian rows (generic robot: the source rows J.. at the same index, no re-interpolation)
+  if (Cin > 0 && cartOut) {
+    const int nC = fatal ? 0 : imin_(s.nCartOut, npts);
+    const bool liveC = i < nC;
+    if (i0 < nC) {  // warp-uniform
+      const int npc = imin_(nC - i0, 32);
+      const double *pc = src + (size_t)bl * w.R + J + (size_t)i0 * pst;
+      for (int e = lane; e < npc * Cin; e += 32) {
+        const int p = e / Cin, r = e - p * Cin;
+        sY[wy][e] = pc[(size_t)p * pst + r];
+      }
+      __syncwarp();
+      if (liveC)
+        for (int r = 0; r < Cin; ++r) cartOut[((size_t)bl * Cin + r) * w.OutC + i] = (float)sY[wy][lane * Cin + r];
+    }
+    if (!liveC && inRange)
+      for (int r = 0; r < Cin; ++r) cartOut[((size_t)bl * Cin + r) * w.OutC + i] = 0.f;
+  }
+}
+
 // s-sdot histories in sdotWrite order (ascending s for the reverse sweep) as float32 (TP over Sc,
 // points fastest); also clears the switching flags beyond the recorded steps.
 __global__ void k_pack_hist(Ws w, float *histOut, int npts, int nb) {
