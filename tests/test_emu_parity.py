@@ -89,8 +89,8 @@ def test_per_sample_mvc_matches_oracle(ctx):
 
 
 def test_sweep_filters_decide_nearly_everything(ctx):
-    """The sweep kernel takes the bisection decisions from float enclosures and falls back to the exact code
-    when they do not separate.  Results are exact either way (checked above); this guards the speed path:
+    """The sweep kernel takes the bisection decisions from float models of the bounds (one common margin, then
+    per-joint margins) and falls back to the exact quotients when neither separates.  Results are exact either way (checked above); this guards the speed path:
     the fallbacks must stay rare, otherwise the kernel silently degenerates into the all-exact one."""
     import ctypes as C
     out = (C.c_longlong * 8)()

@@ -171,7 +171,7 @@ def test_shared_reciprocal_division_is_ieee(ctx):
 def test_large_batch_matches_oracle_bit_for_bit(ctx):
     """4096 GEN7DOF paths (BASELINE configs[2] size) through the C-ABI against the oracle restatement run on
     the host cores: switching counts, total time and every float32 output sample.  The sweep kernel takes its
-    bisection decisions from certified float enclosures and forms only the binding quotients exactly; a wrong
+    bisection decisions from certified float models of the bounds and forms only the binding quotients exactly; a wrong
     certificate anywhere would change a step count here (the algorithm is chaotic at the last bit)."""
     import ctypes as C
     import os
