@@ -1410,6 +1410,57 @@ int batotp_emu_filter_stats(long long *out, int n, int reset) {
   if (reset) memset(g_emu_filter, 0, sizeof(g_emu_filter));
   return 0;
 }
+// TEST-ONLY: the branch-free bracket update of the sweep kernel (Bisect::step_any) against the reference-shaped
+// one (Bisect::step, ba.cpp:1270-1321) on n random problems "feasible iff sdot^2 <= T": same result code and
+// same next candidate after every verification, same settled value and iteration count.  Returns the number of
+// problems that differ.  kinds: thresholds all over the range, at / next to a candidate, zero, negative start.
+long long batotp_emu_bisect_selftest(unsigned long long seed, long long n) {
+  auto rnd = [&]() {
+    seed += 0x9E3779B97F4A7C15ull;
+    unsigned long long z = seed;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return (double)((z ^ (z >> 31)) >> 11) * (1.0 / 9007199254740992.0);
+  };
+  long long bad = 0;
+  for (long long k = 0; k < n; ++k) {
+    const int kind = (int)(rnd() * 8);
+    double start = std::exp((rnd() - 0.5) * 40.0);
+    if (kind == 5) start = -start;
+    if (kind == 6) start = 0.0;
+    double T = start * start * std::exp(-rnd() * (kind == 1 ? 60.0 : 6.0));
+    if (kind == 2) T = 0.0;                          // nothing but sdot = 0 is feasible
+    if (kind == 3) T = -1.0;                         // nothing is feasible: the bracket collapses or 100 passes
+    if (kind == 4) T = start * start * (1.0 + 1e-3);  // feasible at once
+    if (kind == 7) {                                 // threshold exactly at a candidate of the sequence
+      Bisect p;
+      p.begin(start);
+      const int stop = 1 + (int)(rnd() * 12);
+      for (int it = 0; it < stop; ++it)
+        if (p.step(true) != 0) break;
+      T = p.sdotCur * p.sdotCur;
+    }
+    Bisect a, b;
+    a.begin(start);
+    b.begin(start);
+    int ra = 0, rb = 0, guard = 0;
+    bool same = true;
+    while (ra == 0 && rb == 0 && guard++ < 300) {
+      const bool va = !(a.sdotCur * a.sdotCur <= T), vb = !(b.sdotCur * b.sdotCur <= T);
+      ra = a.step(va);
+      rb = b.step_any(vb);
+      if (ra != rb) same = false;
+      if (ra == 0 && memcmp(&a.sdotCur, &b.sdotCur, sizeof(double)) != 0) same = false;
+      if (!same) break;
+    }
+    if (same) {
+      const double inB = (rb == 2) ? start : b.sdotCur;  // what the sweep kernel forms after the loop
+      if (ra != rb || memcmp(&a.sdotIn, &inB, sizeof(double)) != 0 || a.nIter != b.nIter) same = false;
+    }
+    if (!same) bad++;
+  }
+  return bad;
+}
 #endif
 int batotp_cuda_timer(batotp_handle h, int which, double *elapsed_ms) {
 #ifndef BATOTP_HOST_EMU

@@ -105,6 +105,17 @@ def test_sweep_filters_decide_nearly_everything(ctx):
     assert v_all < 0.001 * (v_skip + v_one + 1)
 
 
+def test_branch_free_bracket_update_equals_the_reference_shaped_one(ctx):
+    """Bisect::step_any (one straight-line pass for every verification of the sweep kernel) against Bisect::step
+    (the shape of ba.cpp:1270-1321) on random feasibility thresholds, including thresholds exactly at a
+    candidate, zero / negative thresholds (bracket collapse, 100-pass limit) and non-positive start values."""
+    import ctypes as C
+    f = ctx.L.batotp_emu_bisect_selftest
+    f.argtypes = [C.c_ulonglong, C.c_longlong]
+    f.restype = C.c_longlong
+    assert f(12345, 400000) == 0
+
+
 def test_step_capacity_is_bounded(ctx):
     """A trajectory that needs more Runge-Kutta steps than the configured ceiling keeps BATOTP_ST_STEP_CAP and
     is reported as not optimised; the batch call itself succeeds and the other trajectories are unaffected."""
