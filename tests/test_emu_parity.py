@@ -105,6 +105,24 @@ def test_sweep_filters_decide_nearly_everything(ctx):
     assert v_all < 0.001 * (v_skip + v_one + 1)
 
 
+@pytest.mark.parametrize("acc,vel,integ", [(0.05, 1.0, 1.0), (20.0, 0.2, 1.0), (1.0, 5.0, 1.0), (1.0, 1.0, 0.25),
+                                           (300.0, 30.0, 0.5)])
+def test_limit_regimes_match_oracle(ctx, acc, vel, integ):
+    """The float models of the sweep kernel certify decisions relative to the size of the bounds they see, so the
+    GEN7DOF paths are run with the limits and the step scaled far away from the stock values: acceleration-starved
+    (every point bisects), velocity-bound, nearly unconstrained (the +-sddotmax clamp and the sdot cap come into
+    play), and a fine step (larger clamp).  Everything must still equal the oracle bit for bit."""
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 900, 3)
+    for i in range(cfg.n_joints):
+        cfg.jnt_acc_max[i] *= acc
+        cfg.jnt_vel_max[i] *= vel
+    cfg.integ_res *= integ
+    res = P.run_device(ctx, cfg, tres, th, None, out_cap=65536, hist_cap=65536)
+    for b in range(3):
+        orc = P.OracleRun(cfg, tres, th[b], None)
+        assert P.compare(cfg, res, b, orc) == [], b
+
+
 def test_branch_free_bracket_update_equals_the_reference_shaped_one(ctx):
     """Bisect::step_any (one straight-line pass for every verification of the sweep kernel) against Bisect::step
     (the shape of ba.cpp:1270-1321) on random feasibility thresholds, including thresholds exactly at a

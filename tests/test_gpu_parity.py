@@ -237,3 +237,23 @@ def test_interpolation_only_mode(ctx):
     r2 = P.run_device(ctx, cfg2, tres2, th2, None, out_cap=1024)
     assert (r2.status == 0).all() and (r2.n_out == r2.n_out[0]).all() and r2.n_out[0] > 400
     assert np.abs(r2.theta_out[:, :, 0] - th2[:, :, 0]).max() == 0  # a spline interpolates its first knot exactly
+
+
+@pytest.mark.parametrize("acc,vel,integ", [(0.05, 1.0, 1.0), (20.0, 0.2, 1.0), (1.0, 5.0, 1.0), (1.0, 1.0, 0.25),
+                                           (300.0, 30.0, 0.5)])
+def test_limit_regimes_match_oracle(ctx, acc, vel, integ):
+    """GEN7DOF paths with the limits and the step scaled far away from the stock values (acceleration-starved,
+    velocity-bound, nearly unconstrained, fine step): the float certificates of the sweep kernel are relative to
+    the bounds they see, so every regime must still equal the oracle bit for bit (rcp.approx and FFMA on the
+    device, against the plain divisions of the host emulation in tests/test_emu_parity.py)."""
+    B = 48
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 20000, B)
+    for i in range(cfg.n_joints):
+        cfg.jnt_acc_max[i] *= acc
+        cfg.jnt_vel_max[i] *= vel
+    cfg.integ_res *= integ
+    res = P.run_device(ctx, cfg, tres, th, None, out_cap=65536, hist_cap=65536)
+    assert (res.status & native.ST_FATAL_MASK == 0).all()
+    for b in range(0, B, 3):
+        orc = P.OracleRun(cfg, tres, th[b], None)
+        assert P.compare(cfg, res, b, orc) == [], b
