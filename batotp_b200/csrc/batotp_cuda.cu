@@ -1406,7 +1406,7 @@ int batotp_cuda_profile_dump(batotp_handle h, char *buf, int cap) {
 #ifdef BATOTP_HOST_EMU
 // TEST-ONLY (host emulation build): counters of the sweep kernel's float filters, see k_sweep.cuh
 int batotp_emu_filter_stats(long long *out, int n, int reset) {
-  for (int i = 0; i < n && i < 8; ++i) out[i] = g_emu_filter[i];
+  for (int i = 0; i < n && i < 16; ++i) out[i] = g_emu_filter[i];
   if (reset) memset(g_emu_filter, 0, sizeof(g_emu_filter));
   return 0;
 }

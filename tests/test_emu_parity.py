@@ -93,12 +93,13 @@ def test_sweep_filters_decide_nearly_everything(ctx):
     per-joint margins) and falls back to the exact quotients when neither separates.  Results are exact either way (checked above); this guards the speed path:
     the fallbacks must stay rare, otherwise the kernel silently degenerates into the all-exact one."""
     import ctypes as C
-    out = (C.c_longlong * 8)()
-    ctx.L.batotp_emu_filter_stats(out, 8, 1)
+    out = (C.c_longlong * 16)()
+    ctx.L.batotp_emu_filter_stats(out, 16, 1)
     cfg, tres, th, ca = P.load_synth("GEN7DOF", 100, 8)
     P.run_device(ctx, cfg, tres, th, ca)
-    ctx.L.batotp_emu_filter_stats(out, 8, 1)
+    ctx.L.batotp_emu_filter_stats(out, 16, 1)
     certain, exact, b_joint, b_exact, v_skip, v_one, v_all = list(out)[:7]
+    assert list(out)[8:11] == [0, 0, 0]  # every shortcut agreed with the full exact computation (TEST-ONLY blocks)
     assert certain > 100000
     assert exact < 0.01 * certain        # decisions deferred to the exact verification
     assert b_exact < 0.001 * b_joint     # bounds that needed all joints instead of the certified one
@@ -117,10 +118,17 @@ def test_limit_regimes_match_oracle(ctx, acc, vel, integ):
         cfg.jnt_acc_max[i] *= acc
         cfg.jnt_vel_max[i] *= vel
     cfg.integ_res *= integ
+    import ctypes as C
+    st = (C.c_longlong * 16)()
+    ctx.L.batotp_emu_filter_stats(st, 16, 1)
     res = P.run_device(ctx, cfg, tres, th, None, out_cap=65536, hist_cap=65536)
+    ctx.L.batotp_emu_filter_stats(st, 16, 1)
     for b in range(3):
         orc = P.OracleRun(cfg, tres, th[b], None)
         assert P.compare(cfg, res, b, orc) == [], b
+    # the host build cross-checks every shortcut against the full exact computation: decisions, settled bounds,
+    # velocity caps (k_sweep.cuh, TEST-ONLY blocks)
+    assert st[0] > 10000 and list(st)[8:11] == [0, 0, 0], list(st)
 
 
 def test_branch_free_bracket_update_equals_the_reference_shaped_one(ctx):
