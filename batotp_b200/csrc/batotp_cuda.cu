@@ -1898,6 +1898,13 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
               cudaStreamSynchronize(hp->stream);
               cudaStreamSynchronize(hp->copyStream);
               hp->copiesPending = false;
+            } catch (...) {
+              hp->beforeSweeps = nullptr;
+              tailRes.failed = true;
+              tailRes.msg = "unexpected exception in the tail chunk";
+              cudaStreamSynchronize(hp->stream);
+              cudaStreamSynchronize(hp->copyStream);
+              hp->copiesPending = false;
             }
           });
         }
