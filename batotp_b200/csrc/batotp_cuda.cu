@@ -1800,6 +1800,15 @@ int batotp_cuda_set_tail_overlap(batotp_handle h, int on) {
   return 0;
 }
 
+// drain both streams of a context without raising (error paths)
+static void sync_quiet(batotp_handle h) {
+#ifndef BATOTP_HOST_EMU
+  cudaStreamSynchronize(h->stream);
+  cudaStreamSynchronize(h->copyStream);
+#endif
+  h->copiesPending = false;
+}
+
 // The chunks [0, mainB) of a batch on context h, one after the other (out-of-memory: smaller chunks)
 static void run_chunks(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_in *in, batotp_batch_out *out,
                        int from, int mainB, int &chunk, bool &first) {
@@ -1858,10 +1867,11 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
   };
   try {
     h->inSet[0].src = h->inSet[1].src = nullptr;
-#ifndef BATOTP_HOST_EMU
     if (h->tailOverlap && !h->profile && !out->on_device && !cfg->is_interp_only && in->B > chunk) {
       int sms = 148;
+#ifndef BATOTP_HOST_EMU
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+#endif
       const int t = in->B % chunk;
       if (t > 0 && t <= sms * SW_NT) {
         if (!h->helper && batotp_cuda_create(h->device, &h->helper) != 0) h->helper = nullptr;
@@ -1895,22 +1905,17 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
               tailRes.failed = true;
               tailRes.oom = e.oom;
               tailRes.msg = e.msg;
-              cudaStreamSynchronize(hp->stream);
-              cudaStreamSynchronize(hp->copyStream);
-              hp->copiesPending = false;
+              sync_quiet(hp);
             } catch (...) {
               hp->beforeSweeps = nullptr;
               tailRes.failed = true;
               tailRes.msg = "unexpected exception in the tail chunk";
-              cudaStreamSynchronize(hp->stream);
-              cudaStreamSynchronize(hp->copyStream);
-              hp->copiesPending = false;
+              sync_quiet(hp);
             }
           });
         }
       }
     }
-#endif
     run_chunks(h, cfg, in, out, 0, mainB, chunk, first);
     finish_tail(1);
     if (tail > 0) {

@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #define __global__
 #define __device__
@@ -33,8 +34,15 @@ typedef int cudaStream_t;
 typedef int cudaError_t;
 #define cudaSuccess 0
 
+// One emulated launch at a time: kernels keep their "shared memory" in function-local statics and the fibre stacks
+// come from one pool, so host threads that drive different contexts (the tail chunk of a batch) take turns.
+static inline std::recursive_mutex &emu_launch_mutex() {
+  static std::recursive_mutex m;
+  return m;
+}
 template <class F>
 static inline void emu_launch(dim3 grid, dim3 block, F f) {
+  std::lock_guard<std::recursive_mutex> emu_lk(emu_launch_mutex());
   gridDim = grid;
   blockDim = block;
   for (unsigned bz = 0; bz < grid.z; ++bz)
@@ -144,6 +152,7 @@ static void emu_fiber_entry() {
 }
 template <class F>
 static inline void emu_launch_fibers(dim3 grid, dim3 block, F f) {
+  std::lock_guard<std::recursive_mutex> emu_lk(emu_launch_mutex());
   gridDim = grid;
   blockDim = block;
   const int nt = (int)(block.x * block.y);

@@ -88,6 +88,34 @@ def test_per_sample_mvc_matches_oracle(ctx):
         assert want.min() > 0 and want.max() < 1.0e3
 
 
+def test_tail_overlap_does_not_change_results(ctx):
+    """The last chunk of a batch runs on the library's second context, driven by its own host thread, when it fits
+    one sweep CTA per SM (batotp_cuda_optimize_batch).  Under the emulation the launches of the two threads take
+    turns, so this checks the hand-over logic: same outputs and same work counters with and without it."""
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 60, 11)
+    ctx.set_chunk(4)  # 2 full chunks on the main context, 3 paths on the second one
+    try:
+        runs = []
+        for on in (True, False, True):
+            ctx.set_tail_overlap(on)
+            ctx.stats_reset()
+            r = P.run_device(ctx, cfg, tres, th, None)
+            runs.append((r, ctx.stats()))
+    finally:
+        ctx.set_tail_overlap(True)
+        ctx.set_chunk(16384)
+    (a, sa), (b, sb), (c, sc) = runs
+    assert (a.status & native.ST_FATAL_MASK == 0).all()
+    for nm in ("status", "n_rev", "n_fwd", "n_out", "t_total", "theta_out", "hist", "flags"):
+        assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
+        assert np.array_equal(getattr(a, nm), getattr(c, nm)), nm
+    for k in ("verifies", "steps", "trajectories", "sweep_launches", "launches"):
+        assert sa[k] == sb[k] == sc[k], k
+    for bb in (0, 5, 9, 10):
+        orc = P.OracleRun(cfg, tres, th[bb], None)
+        assert P.compare(cfg, a, bb, orc) == [], bb
+
+
 def test_sweep_filters_decide_nearly_everything(ctx):
     """The sweep kernel takes the bisection decisions from float models of the bounds (one common margin, then
     per-joint margins) and falls back to the exact quotients when neither separates.  Results are exact either way (checked above); this guards the speed path:
