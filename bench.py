@@ -294,6 +294,9 @@ def main_b200(args):
                 peak_source="measured in this run (DFMA chains); MEASURED_PEAKS.json has no FP64 entry",
                 peak_nofma=peak_nofma, frac_of_nofma_peak=achieved / max(peak_nofma, 1e-12),
                 flops_per_trajectory=flops / ntraj, share_of_step=sweep_s / max(ms * 1e-3, 1e-12),
+                share_note="sum of the sweep launches' own durations / step time; the launch of a tail chunk runs "
+                           "beside other kernels (tail overlap), so with a tail this exceeds the sweep's share of "
+                           "the timeline (49 % on one full wave: profiles/r1f_launch_list_step.csv)",
                 counting="SURVEY 8d: 1 flop per FP64 add/sub/mul/div/sqrt; A5=5+18J, A4=2+7J, A2=4+2J, RK=110/step")
     launches_value = st["launches"]
 
