@@ -1410,6 +1410,11 @@ int batotp_emu_filter_stats(long long *out, int n, int reset) {
   if (reset) memset(g_emu_filter, 0, sizeof(g_emu_filter));
   return 0;
 }
+// TEST-ONLY: perturb the float reciprocal of the sweep kernel's models by k ulps (see f_rcp)
+int batotp_emu_set_rcp_ulps(int k) {
+  g_emu_rcp_ulps = k;
+  return 0;
+}
 // TEST-ONLY: the branch-free bracket update of the sweep kernel (Bisect::step_any) against the reference-shaped
 // one (Bisect::step, ba.cpp:1270-1321) on n random problems "feasible iff sdot^2 <= T": same result code and
 // same next candidate after every verification, same settled value and iteration count.  Returns the number of

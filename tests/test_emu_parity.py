@@ -159,6 +159,29 @@ def test_limit_regimes_match_oracle(ctx, acc, vel, integ):
     assert st[0] > 10000 and list(st)[8:11] == [0, 0, 0], list(st)
 
 
+@pytest.mark.parametrize("ulps", [-2, 2])
+def test_results_do_not_depend_on_the_float_reciprocal(ctx, ulps):
+    """The floats of the sweep kernel only certify outcomes of the exact computation, so moving the approximate
+    reciprocal they are built from by 2 units in the last place (rcp.approx on the device is good to 1) may change
+    neither a single output bit nor a single cross-check."""
+    import ctypes as C
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 1500, 4)
+    for i in range(cfg.n_joints):
+        cfg.jnt_acc_max[i] *= 0.3
+    st = (C.c_longlong * 16)()
+    ctx.L.batotp_emu_set_rcp_ulps(ulps)
+    try:
+        ctx.L.batotp_emu_filter_stats(st, 16, 1)
+        res = P.run_device(ctx, cfg, tres, th, None, out_cap=65536, hist_cap=65536)
+        ctx.L.batotp_emu_filter_stats(st, 16, 1)
+    finally:
+        ctx.L.batotp_emu_set_rcp_ulps(0)
+    for b in range(4):
+        orc = P.OracleRun(cfg, tres, th[b], None)
+        assert P.compare(cfg, res, b, orc) == [], b
+    assert st[0] > 10000 and list(st)[8:11] == [0, 0, 0], list(st)
+
+
 def test_branch_free_bracket_update_equals_the_reference_shaped_one(ctx):
     """Bisect::step_any (one straight-line pass for every verification of the sweep kernel) against Bisect::step
     (the shape of ba.cpp:1270-1321) on random feasibility thresholds, including thresholds exactly at a
