@@ -35,7 +35,8 @@ namespace {
 
 struct Err {
   std::string msg;
-  bool oom = false;  // a device allocation failed: the batch call retries with smaller chunks
+  bool oom = false;  // a device allocation failed (or would fail): the batch call retries with smaller chunks
+  int fitB = 0;      // with oom: how many trajectories per chunk the free memory would hold (0 = unknown)
 };
 
 #ifndef BATOTP_HOST_EMU
@@ -67,16 +68,16 @@ inline void g_free(void *p) {
 }
 inline void g_zero(void *p, size_t bytes, cudaStream_t s) { CU_CHECK(cudaMemsetAsync(p, 0, bytes, s)); }
 inline void g_h2d(void *d, const void *h, size_t bytes, cudaStream_t s) {
-  CU_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s));
+  CU_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyDefault, s));
 }
 inline void g_d2h(void *h, const void *d, size_t bytes, cudaStream_t s) {
-  CU_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s));
+  CU_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDefault, s));
 }
 inline void g_d2d(void *d, const void *s0, size_t bytes, cudaStream_t s) {
   CU_CHECK(cudaMemcpyAsync(d, s0, bytes, cudaMemcpyDeviceToDevice, s));
 }
 inline void g_d2h_2d(void *h, size_t hp, const void *d, size_t dp, size_t width, size_t rows, cudaStream_t s) {
-  CU_CHECK(cudaMemcpy2DAsync(h, hp, d, dp, width, rows, cudaMemcpyDeviceToHost, s));
+  CU_CHECK(cudaMemcpy2DAsync(h, hp, d, dp, width, rows, cudaMemcpyDefault, s));
 }
 inline void g_h2d_2d(void *d, size_t dp, const void *h, size_t hp, size_t width, size_t rows, cudaStream_t s) {
   CU_CHECK(cudaMemcpy2DAsync(d, dp, h, hp, width, rows, cudaMemcpyHostToDevice, s));
@@ -87,9 +88,6 @@ inline void g_d2d_2d(void *d, size_t dp, const void *s0, size_t sp, size_t width
 inline void g_sync(cudaStream_t s) { CU_CHECK(cudaStreamSynchronize(s)); }
 inline void g_event_record(cudaEvent_t e, cudaStream_t s) { CU_CHECK(cudaEventRecord(e, s)); }
 inline void g_stream_wait(cudaStream_t s, cudaEvent_t e) { CU_CHECK(cudaStreamWaitEvent(s, e, 0)); }
-inline void g_set_cfg(const DevCfg &c, cudaStream_t s) {
-  CU_CHECK(cudaMemcpyToSymbolAsync(g_cfg, &c, sizeof(DevCfg), 0, cudaMemcpyHostToDevice, s));
-}
 inline void g_check_launch() { CU_CHECK(cudaGetLastError()); }
 #else
 inline void *g_alloc(size_t bytes) { return calloc(1, bytes ? bytes : 8); }
@@ -114,11 +112,20 @@ inline void g_sync(cudaStream_t) {}
 typedef int cudaEvent_t;
 inline void g_event_record(cudaEvent_t, cudaStream_t) {}
 inline void g_stream_wait(cudaStream_t, cudaEvent_t) {}
-inline void g_set_cfg(const DevCfg &c, cudaStream_t) { g_cfg = c; }
 inline void g_check_launch() {}
 #endif
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+// bytes the device can still hand out (host emulation: "plenty")
+inline size_t g_free_bytes() {
+#ifndef BATOTP_HOST_EMU
+  size_t fr = 0, tot = 0;
+  if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return (size_t)1 << 62;
+  return fr;
+#else
+  return (size_t)1 << 62;
+#endif
+}
 
 // robot.cpp:291-322 — cable attachment points of the CSPR (host, once)
 Pmat make_pmat() {
@@ -165,7 +172,11 @@ struct batotp_ctx {
   int capBo = 0, capOc = 0, capOs = 0, capOutC = 0, capOSc = 0;
   std::vector<void *> outAllocs;  // output sub-chunk arrays
   int outChunk = 8192;            // trajectories per output pass
+  // row pitch (points) of the packed float32 rows / histories: the caller's out_cap / hist_cap inside
+  // batotp_cuda_optimize_batch (a sub-chunk then leaves in one contiguous copy), 0 = the device capacities
+  int rowPitch = 0, histPitch = 0, capRowPitch = 0, capHistPitch = 0;
   int maxSteps = 65536;           // largest RK-step capacity the automatic retries grow to (per sweep)
+  int stepHint = 0;               // RK-step capacity a chunk starts with (0 = automatic: max(1024, 2 x grid points))
   // Thomas factor tables
   double *d_cN = nullptr;  // Thomas tables (ensure_tabs)
   int tabN = 0;
@@ -177,7 +188,7 @@ struct batotp_ctx {
     void *theta = nullptr, *cart = nullptr;
     double *ts = nullptr, *tres = nullptr;
     int *n0 = nullptr;
-    size_t capIn = 0, capInB = 0, capInTs = 0;
+    size_t capTheta = 0, capCart = 0, capInB = 0, capInTs = 0;  // bytes (theta, cart), trajectories, timestamps
     std::vector<double> tresHost;
     const batotp_batch_in *src = nullptr;  // what the set holds: chunk [first, first+B) of this batch
     int first = -1, B = 0;
@@ -228,6 +239,12 @@ struct batotp_ctx {
   // context (own streams and workspaces, one host thread) next to the output / input phases of the full chunks
   batotp_ctx *helper = nullptr;
   bool tailOverlap = true;
+  // stragglers: the few trajectories of a chunk that outgrow the step capacity keep BATOTP_ST_STEP_CAP for the
+  // moment and are re-run together, with a larger capacity, after the chunks of the batch (optimize_batch)
+  std::vector<int> stragglers;  // indices in the caller's batch
+  int stragglerSc = 0;          // the step capacity they outgrew
+  int chunkFirst = 0;           // index of the resident chunk's first trajectory in the caller's batch
+  bool collectStragglers = false;
   std::function<void()> onSweepsDone;  // called once the sweeps of a chunk have completed on the device
   std::function<void()> beforeSweeps;  // called after interpInputData of a chunk has been enqueued (may block)
 #ifndef BATOTP_HOST_EMU
@@ -331,6 +348,7 @@ void free_out(batotp_ctx *h) {
   for (void *p : h->outAllocs) g_free(p);
   h->outAllocs.clear();
   h->capBo = 0;
+  h->capRowPitch = h->capHistPitch = 0;
 }
 
 template <class T>
@@ -414,6 +432,31 @@ int final_cap(const batotp_ctx *h, int Sc, int Os) {
   return std::max(std::max(n, 16), Os);
 }
 
+// bytes of chunk-resident workspace per trajectory (the arrays of ensure_ws)
+size_t chunk_bytes_per_traj(const DevCfg &c, int Nc, int Sc) {
+  const size_t n = (size_t)Nc, sc = (size_t)Sc;
+  size_t per = 3 * (size_t)c.R * n * 8 + n * 8 + 2 * n * 8 + n * (size_t)c.RT * 32 + 4 * sc * 8 + 2 * sc + sizeof(TrajState);
+  if (c.trqOn) per += 2 * (size_t)4 * MAXD * n * 8 + 2 * (size_t)c.R * n * 8;
+  return per;
+}
+
+// bytes of output sub-chunk workspace per trajectory (the arrays of ensure_out) for a step capacity Sc
+size_t out_bytes_per_traj(const batotp_ctx *h, int Sc) {
+  const DevCfg &c = h->cfg;
+  const size_t Oc = (size_t)oversample_cap(h, Sc);
+  const bool trq = c.trqOn != 0;
+  size_t Os = Oc;
+  if (!trq && smooth_uniform_on(h)) Os = (size_t)(Oc / c.c.out_smooth_fact) + 16;
+  const size_t OutC = (size_t)final_cap(h, Sc, (int)Os), R = (size_t)c.R;
+  size_t per = (size_t)Sc * 8 + Oc * 20 + (fused_out(h) ? 0 : R * Oc * 8) + 2 * R * Os * 8;
+  if (trq) per += 2 * R * Oc * 8 + 3 * (size_t)MAXD * Oc * 8;
+  per += 2 * ((size_t)c.J * OutC * 4 + (size_t)std::max(c.Cin, 1) * OutC * 4 + (trq ? (size_t)c.J * OutC * 4 : 0) +
+              4 * (size_t)Sc * 4);
+  if (c.C == 7) per += 7 * OutC * 8;
+  if (h->keepF64) per += (R + c.J) * OutC * 8;
+  return per;
+}
+
 // chunk-resident arrays (input phase + sweeps)
 void ensure_ws(batotp_ctx *h, int B, int Nc, int Sc) {
   const DevCfg &c = h->cfg;
@@ -425,8 +468,27 @@ void ensure_ws(batotp_ctx *h, int B, int Nc, int Sc) {
   free_ws(h);
   free_out(h);
   h->allocPhase = 0;
+  {
+    // footprint of one trajectory in the chunk-resident arrays below; a chunk that cannot fit is refused before
+    // anything is allocated, with the size that would fit (the batch call continues with smaller chunks)
+    const size_t per = chunk_bytes_per_traj(c, Nc, Sc);
+    const size_t fr = g_free_bytes();
+    // what else this context will ask for: the output sub-chunk arrays (ensure_out) and some slack for the
+    // staging sets / the tail helper
+    const size_t reserve = ((size_t)2 << 30) + out_bytes_per_traj(h, Sc) * (size_t)std::min(B, h->outChunk);
+    if ((double)per * B > 0.94 * (double)(fr > reserve ? fr - reserve : 0)) {
+      char buf[200];
+      snprintf(buf, sizeof buf, "chunk of %d trajectories needs %.1f GB of workspace (%zu bytes each), %.1f GB free", B,
+               (double)per * B * 1e-9, per, (double)fr * 1e-9);
+      Err er{buf};
+      er.oom = true;
+      er.fitB = (int)std::min<double>(2.0e9, 0.9 * (double)(fr > reserve ? fr - reserve : 0) / (double)per);
+      throw er;
+    }
+  }
   Ws &w = h->w;
   memset(&w, 0, sizeof(w));
+  w.cfg = h->cfg;
   const size_t b = (size_t)B;
   const int R = c.R, RT = c.RT;
   w.B = B;
@@ -460,6 +522,9 @@ void ensure_ws(batotp_ctx *h, int B, int Nc, int Sc) {
   ensure_tabs(h, std::max(Nc, Sc) + 8);
 }
 
+inline int row_pitch(const batotp_ctx *h) { return h->rowPitch > 0 ? h->rowPitch : h->w.OutC; }
+inline int hist_pitch(const batotp_ctx *h) { return h->histPitch > 0 ? h->histPitch : h->w.Sc; }
+
 void select_out_set(batotp_ctx *h, int q) {
   h->d_thetaOut = h->o_thetaOut[q];
   h->d_cartOut = h->o_cartOut[q];
@@ -477,7 +542,9 @@ void ensure_out(batotp_ctx *h, int Bo, int minOutC = 0) {
   int Os = Oc;
   if (!trq && smooth_uniform_on(h)) Os = (int)(Oc / c.c.out_smooth_fact) + 16;
   const int OutC = std::max(final_cap(h, Sc, Os), minOutC);
+  const int rowP = h->rowPitch > 0 ? h->rowPitch : OutC, histP = h->histPitch > 0 ? h->histPitch : Sc;
   if (!(Bo <= h->capBo && Oc <= h->capOc && Os <= h->capOs && OutC <= h->capOutC && Sc == h->capOSc &&
+        rowP <= h->capRowPitch && histP <= h->capHistPitch &&
         h->keepF64 == h->capKeep && fused_out(h) == h->capFused && c.R == h->capR && trq == h->capTrq)) {
     free_out(h);
     h->allocPhase = 1;
@@ -499,11 +566,13 @@ void ensure_out(batotp_ctx *h, int Bo, int minOutC = 0) {
       h->o_TrqM = out_alloc<double>(h, b * MAXD * Oc);
     }
     for (int q = 0; q < 2; ++q) {
-      h->o_thetaOut[q] = out_alloc<float>(h, b * c.J * OutC);
-      h->o_cartOut[q] = out_alloc<float>(h, b * std::max(c.Cin, 1) * OutC);
-      h->o_trqOut[q] = trq ? out_alloc<float>(h, b * c.J * OutC) : nullptr;
-      h->o_histOut[q] = out_alloc<float>(h, b * 4 * Sc);
+      h->o_thetaOut[q] = out_alloc<float>(h, b * c.J * rowP);
+      h->o_cartOut[q] = out_alloc<float>(h, b * std::max(c.Cin, 1) * rowP);
+      h->o_trqOut[q] = trq ? out_alloc<float>(h, b * c.J * rowP) : nullptr;
+      h->o_histOut[q] = out_alloc<float>(h, b * 4 * histP);
     }
+    h->capRowPitch = rowP;
+    h->capHistPitch = histP;
     select_out_set(h, 0);
     h->d_cartOutD = (c.C == 7) ? out_alloc<double>(h, b * 7 * OutC) : nullptr;
     h->d_outD = h->keepF64 ? out_alloc<double>(h, b * (R + c.J) * OutC) : nullptr;
@@ -563,8 +632,8 @@ void set_cfg(batotp_ctx *h, const batotp_cfg *cfg) {
     h->hwSc = 0;
   }
   h->cfg = d;
+  h->w.cfg = d;  // the options travel with every launch (Ws is a kernel parameter)
   h->haveCfg = true;
-  g_set_cfg(d, h->stream);
 }
 
 int check_cfg(batotp_ctx *h) {
@@ -773,7 +842,7 @@ void free_inset(batotp_ctx::InSet &q) {
   q.theta = q.cart = nullptr;
   q.ts = q.tres = nullptr;
   q.n0 = nullptr;
-  q.capIn = q.capInB = q.capInTs = 0;
+  q.capTheta = q.capCart = q.capInB = q.capInTs = 0;
   q.src = nullptr;
   q.first = -1;
 }
@@ -793,21 +862,23 @@ void issue_inputs(batotp_ctx *h, const batotp_batch_in *in, int first, int B, in
   CU_CHECK(cudaEventSynchronize(q.ev));  // the set's previous transfer has left tresHost
 #endif
   q.src = nullptr;
-  const size_t need = in->on_device ? 0 : std::max(thBytes, caBytes);  // resident rows are used where they are
-  const size_t needTs = in->on_device ? 0 : (size_t)B * n0;
-  if (need > q.capIn || (size_t)B > q.capInB || needTs > q.capInTs || !q.tres) {
+  // resident rows are used where they are; host rows need room for what this call copies (the staging set may
+  // have been sized for another robot / path length: each block keeps its own capacity)
+  const size_t needTh = (in->on_device || !th) ? 0 : thBytes, needCa = (in->on_device || !ca) ? 0 : caBytes;
+  const size_t needTs = (in->on_device || !in->timestamp) ? 0 : (size_t)B * n0;
+  if (needTh > q.capTheta || needCa > q.capCart || (size_t)B > q.capInB || needTs > q.capInTs || !q.tres) {
+    const size_t capB = std::max((size_t)B, q.capInB);
+    const size_t cTh = std::max(needTh, q.capTheta), cCa = std::max(needCa, q.capCart), cTs = std::max(needTs, q.capInTs);
     free_inset(q);
-    const size_t capB = (size_t)B;
-    if (!in->on_device) {
-      q.theta = g_alloc(capB * c.J * n0 * 8);
-      q.cart = g_alloc(capB * std::max(c.Cin, 1) * n0 * 8);
-      q.ts = (double *)g_alloc(capB * n0 * 8);
-    }
+    if (cTh) q.theta = g_alloc(cTh);
+    if (cCa) q.cart = g_alloc(cCa);
+    if (cTs) q.ts = (double *)g_alloc(cTs * 8);
     q.tres = (double *)g_alloc(capB * 8);
     q.n0 = (int *)g_alloc(capB * 4);
-    q.capIn = in->on_device ? 0 : capB * (size_t)std::max(c.J, c.Cin) * n0 * 8;
+    q.capTheta = cTh;
+    q.capCart = cCa;
     q.capInB = capB;
-    q.capInTs = in->on_device ? 0 : capB * (size_t)n0;
+    q.capInTs = cTs;
   }
   q.tresHost.resize(B);
   for (int b = 0; b < B; ++b) q.tresHost[b] = in->tres ? in->tres[first + b] : in->tres_all;  // per-trajectory tres (small)
@@ -1004,10 +1075,11 @@ int do_interp_only(batotp_ctx *h, bool haveN0) {
     LAUNCH_T(h, k_interp_only_finish, h->B, w);
     select_out_set(h, 0);
     const bool strictQuat = (c.C == 7 && c.c.trig_mode == 1);
-    if (h->d_trqOut) g_zero(h->d_trqOut, (size_t)h->B * c.J * w.OutC * sizeof(float), h->stream);  // no torque rows here
-    LAUNCH_PT(h, k_out_pack, w.OutC, h->B, w, w.P, w.M, (double *)nullptr, (double *)nullptr, h->d_thetaOut,
-              h->d_cartOut, (float *)nullptr, strictQuat ? h->d_cartOutD : (double *)nullptr, h->d_outD);
-    LAUNCH_PT(h, k_pack_hist, w.Sc, h->B, w, h->d_histOut);
+    const int rp = row_pitch(h), hp = hist_pitch(h);
+    if (h->d_trqOut) g_zero(h->d_trqOut, (size_t)h->B * c.J * rp * sizeof(float), h->stream);  // no torque rows here
+    LAUNCH_PT(h, k_out_pack, std::max(w.OutC, rp), h->B, w, w.P, w.M, (double *)nullptr, (double *)nullptr, h->d_thetaOut,
+              h->d_cartOut, (float *)nullptr, strictQuat ? h->d_cartOutD : (double *)nullptr, h->d_outD, rp);
+    LAUNCH_PT(h, k_pack_hist, std::max(w.Sc, hp), h->B, w, h->d_histOut, hp);
     h->phase = 4;
     return 0;
   }
@@ -1100,20 +1172,21 @@ void do_interp_output(batotp_ctx *h, int b0, int Bo) {
     if (c.trqOn) thomas_rows(h, trqCur, w.TrqM, Bo, b0, c.J, MAXD, 2, 0);
   }
   const bool strictQuat = (c.C == 7 && c.c.trig_mode == 1);
-  if (c.c.robot_type == BATOTP_GENJNT && c.C != 7 && c.Cin <= MAXD && !c.trqOn && !h->d_outD && w.OutC > 0 && Bo > 0) {
+  const int rp = row_pitch(h), hp = hist_pitch(h);
+  if (c.c.robot_type == BATOTP_GENJNT && c.C != 7 && c.Cin <= MAXD && !c.trqOn && !h->d_outD && rp > 0 && Bo > 0) {
     // generic robot, float rows only: warp-per-tile staging through shared memory (k_out_pack_rows)
     const long long rows = cdiv(Bo, OP_WARPS);
     const long long gy = std::min<long long>(rows, 32768), gz = (rows + gy - 1) / gy;
     ProfScope ps_(h, "k_out_pack_rows");
-    BATOTP_LAUNCH_WARP(k_out_pack_rows, dim3((unsigned)cdiv(w.OutC, 32), (unsigned)gy, (unsigned)gz),
-                       dim3(32, OP_WARPS, 1), 0, h->stream, w, cur, w.OM, h->d_thetaOut, h->d_cartOut, w.OutC, Bo);
+    BATOTP_LAUNCH_WARP(k_out_pack_rows, dim3((unsigned)cdiv(rp, 32), (unsigned)gy, (unsigned)gz),
+                       dim3(32, OP_WARPS, 1), 0, h->stream, w, cur, w.OM, h->d_thetaOut, h->d_cartOut, rp, rp, Bo);
     g_check_launch();
     h->launches++;
   } else {
-    LAUNCH_PT(h, k_out_pack, w.OutC, Bo, w, cur, w.OM, trqCur, w.TrqM, h->d_thetaOut, h->d_cartOut, h->d_trqOut,
-              strictQuat ? h->d_cartOutD : (double *)nullptr, h->d_outD);
+    LAUNCH_PT(h, k_out_pack, std::max(w.OutC, rp), Bo, w, cur, w.OM, trqCur, w.TrqM, h->d_thetaOut, h->d_cartOut,
+              h->d_trqOut, strictQuat ? h->d_cartOutD : (double *)nullptr, h->d_outD, rp);
   }
-  LAUNCH_PT(h, k_pack_hist, w.Sc, Bo, w, h->d_histOut);
+  LAUNCH_PT(h, k_pack_hist, std::max(w.Sc, hp), Bo, w, h->d_histOut, hp);
   h->phase = 4;
 }
 
@@ -1531,6 +1604,19 @@ static int load_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_batch
     h->err = "mixing float32 and float64 payloads is not supported";
     return -1;
   }
+  if (in->n0_max < 1) {
+    h->err = "batch input: n0_max must be at least 1";
+    return -1;
+  }
+  if (in->n0)  // caller-supplied lengths index the payload rows: never trust them past the row pitch
+    for (int b = 0; b < B; ++b)
+      if (in->n0[first + b] < 1 || in->n0[first + b] > in->n0_max) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "batch input: n0[%d] = %d is outside 1..n0_max (%d)", first + b, in->n0[first + b],
+                 in->n0_max);
+        h->err = buf;
+        return -1;
+      }
   stage_inputs(h, in, first, B);
   h->phase = 1;
   return 0;
@@ -1539,7 +1625,7 @@ static int load_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_batch
 // one chunk through interpInputData with capacity planning / retry
 static int chunk_interp_input(batotp_handle h, bool haveN0) {
   int Nc = std::max(h->hwNc, h->n0max + 8);
-  int Sc = std::max(h->hwSc, std::max(1024, 2 * Nc));
+  int Sc = std::max(h->hwSc, h->stepHint > 0 ? h->stepHint : std::max(1024, 2 * Nc));
   bool plan = (h->hwNc == 0);
   for (int attempt = 0; attempt < 8; ++attempt) {
     ensure_ws(h, std::max(h->B, h->capB), Nc, Sc);
@@ -1579,12 +1665,25 @@ static int chunk_sweeps_output(batotp_handle h, bool haveN0) {
     }
 #endif
     bool stepCap = false;
-    int mxF = 0;
+    int mxF = 0, nCap = 0;
     for (int b = 0; b < h->B; ++b) {
-      if (h->hst[b].status & ST_STEP_CAP) stepCap = true;
+      if (h->hst[b].status & ST_STEP_CAP) {
+        stepCap = true;
+        nCap++;
+      }
       mxF = std::max(mxF, std::max(h->hst[b].nFwd, h->hst[b].nRev));
     }
     h->mxSteps = mxF;
+    if (stepCap && h->collectStragglers && nCap <= std::max(8, h->B / 64) && h->w.Sc < h->maxSteps) {
+      // a few trajectories outgrew a capacity that serves the rest of the chunk: they keep BATOTP_ST_STEP_CAP for
+      // now (the output phase skips them) and are re-run together after the chunks of the batch, instead of the
+      // whole chunk being redone with twice the capacity for their sake
+      for (int b = 0; b < h->B; ++b)
+        if ((h->hst[b].status & ST_STEP_CAP) && !(h->hst[b].status & (ST_FATAL_MASK & ~ST_STEP_CAP)))
+          h->stragglers.push_back(h->chunkFirst + b);
+      h->stragglerSc = std::max(h->stragglerSc, h->w.Sc);
+      stepCap = false;
+    }
     if (!stepCap) {
       for (int b = 0; b < h->B; ++b) {
         const TrajState &t = h->hst[b];
@@ -1625,9 +1724,11 @@ static int chunk_sweeps_output(batotp_handle h, bool haveN0) {
 int batotp_cuda_load(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_in *in) {
   if (!h || !in) return -1;
   try {
-    if (in->B > h->chunk) h->chunk = in->B;
     h->lastHaveN0 = in->n0 != nullptr;
     h->inSet[0].src = h->inSet[1].src = nullptr;
+    h->rowPitch = h->histPitch = 0;  // phase-wise calls pack at the device capacities
+    h->chunkFirst = 0;
+    h->collectStragglers = false;
     const int rc = load_chunk(h, cfg, in, 0, in->B);
     if (rc == 0) g_sync(h->stream);  // the caller's arrays are free again when this call returns
     return rc;
@@ -1668,9 +1769,16 @@ int batotp_cuda_interp_output(batotp_handle h) {
   }
 }
 
-// per-trajectory scalars of the chunk trajectories [b0, b0+Bo) -> the caller's arrays (synchronous, small)
+// per-trajectory scalars of the chunk trajectories [b0, b0+Bo) -> the caller's arrays (host arrays: synchronous,
+// small; device arrays: one kernel on the context's stream)
 static void fetch_scalars(batotp_handle h, batotp_batch_out *out, int first, int b0, int Bo) {
   const Ws &w = h->w;
+  if (out->on_device) {
+    const ScalarOut so{out->status, out->n_rev, out->n_fwd, out->n_out, out->n_cart_out, out->n_grid,
+                       out->t_total, out->t_rev, out->s_last_sec, out->out_sres};
+    LAUNCH_T(h, k_fetch_scalars, Bo, w, so, first, b0, Bo);
+    return;
+  }
   h->hst.resize(h->B);
   g_d2h(h->hst.data() + b0, w.st + b0, (size_t)Bo * sizeof(TrajState), h->stream);
   g_sync(h->stream);
@@ -1690,29 +1798,32 @@ static void fetch_scalars(batotp_handle h, batotp_batch_out *out, int first, int
   }
 }
 
-// packed float32 rows / histories / flags of the current output sub-chunk -> the caller's buffers, enqueued
-// on stream `cs` (the staging set is the one selected when the sub-chunk was packed)
+// one block of packed rows (rows x `have` points at device pitch dp) -> the caller's block at pitch `want`:
+// a single contiguous copy when the staging set was packed at the caller's pitch
+static void copy_rows(void *dst, size_t want, const void *src, size_t dp, size_t rows, size_t es, cudaStream_t cs) {
+  if (want == dp)
+    g_d2h(dst, src, rows * dp * es, cs);
+  else
+    g_d2h_2d(dst, want * es, src, dp * es, std::min(want, dp) * es, rows, cs);
+}
+
+// packed float32 rows / histories / flags of the current output sub-chunk -> the caller's buffers (host or
+// device memory), enqueued on stream `cs` (the staging set is the one selected when the sub-chunk was packed)
 static void fetch_rows(batotp_handle h, batotp_batch_out *out, int first, cudaStream_t cs) {
   const DevCfg &c = h->cfg;
   const Ws &w = h->w;
   const int Bo = w.Bo, g0 = first + w.b0;
-  const int oc = out->out_cap, wc = std::min(out->out_cap, w.OutC);
+  const size_t oc = (size_t)out->out_cap, rp = (size_t)row_pitch(h);
   if (out->theta_out && oc > 0)
-    g_d2h_2d(out->theta_out + (size_t)g0 * c.J * oc, (size_t)oc * 4, h->d_thetaOut, (size_t)w.OutC * 4,
-             (size_t)wc * 4, (size_t)Bo * c.J, cs);
+    copy_rows(out->theta_out + (size_t)g0 * c.J * oc, oc, h->d_thetaOut, rp, (size_t)Bo * c.J, 4, cs);
   if (out->trq_out && oc > 0 && c.trqOn)
-    g_d2h_2d(out->trq_out + (size_t)g0 * c.J * oc, (size_t)oc * 4, h->d_trqOut, (size_t)w.OutC * 4,
-             (size_t)wc * 4, (size_t)Bo * c.J, cs);
+    copy_rows(out->trq_out + (size_t)g0 * c.J * oc, oc, h->d_trqOut, rp, (size_t)Bo * c.J, 4, cs);
   if (out->cart_out && oc > 0 && c.Cin > 0 && !(c.C == 7 && c.c.trig_mode == 1))
-    g_d2h_2d(out->cart_out + (size_t)g0 * c.Cin * oc, (size_t)oc * 4, h->d_cartOut, (size_t)w.OutC * 4,
-             (size_t)wc * 4, (size_t)Bo * c.Cin, cs);
-  const int hc = out->hist_cap, hw = std::min(out->hist_cap, w.Sc);
-  if (out->hist && hc > 0)
-    g_d2h_2d(out->hist + (size_t)g0 * 4 * hc, (size_t)hc * 4, h->d_histOut, (size_t)w.Sc * 4, (size_t)hw * 4,
-             (size_t)Bo * 4, cs);
+    copy_rows(out->cart_out + (size_t)g0 * c.Cin * oc, oc, h->d_cartOut, rp, (size_t)Bo * c.Cin, 4, cs);
+  const size_t hc = (size_t)out->hist_cap, hp = (size_t)hist_pitch(h);
+  if (out->hist && hc > 0) copy_rows(out->hist + (size_t)g0 * 4 * hc, hc, h->d_histOut, hp, (size_t)Bo * 4, 4, cs);
   if (out->flags && hc > 0)
-    g_d2h_2d(out->flags + (size_t)g0 * 2 * hc, (size_t)hc, w.flags + (size_t)w.b0 * 2 * w.Sc, (size_t)w.Sc,
-             (size_t)hw, (size_t)Bo * 2, cs);
+    copy_rows(out->flags + (size_t)g0 * 2 * hc, hc, w.flags + (size_t)w.b0 * 2 * w.Sc, (size_t)w.Sc, (size_t)Bo * 2, 1, cs);
 }
 
 // copy the results of the current output sub-chunk [w.b0, w.b0+w.Bo) to the caller's buffers;
@@ -1721,11 +1832,12 @@ static void fetch_sub(batotp_handle h, batotp_batch_out *out, int first) {
   const DevCfg &c = h->cfg;
   const Ws &w = h->w;
   ProfScope ps_(h, "copy_d2h(fetch)");
-  if (out->on_device) throw Err{"batotp_batch_out.on_device is not implemented yet"};
+  const bool strictQuatOut = out->cart_out && out->out_cap > 0 && c.Cin > 0 && c.C == 7 && c.c.trig_mode == 1;
+  if (out->on_device && strictQuatOut)
+    throw Err{"batotp_batch_out.on_device: axis-angle rows in strict-trig mode are finished on the host; use trig_mode 0"};
   fetch_scalars(h, out, first, w.b0, w.Bo);
   fetch_rows(h, out, first, h->stream);
-  if (out->cart_out && out->out_cap > 0 && c.Cin > 0 && c.C == 7 && c.c.trig_mode == 1)
-    host_q2aa_out(h, out, first + w.b0);
+  if (strictQuatOut) host_q2aa_out(h, out, first + w.b0);
   g_sync(h->stream);
 }
 
@@ -1745,6 +1857,10 @@ static void process_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_b
                           int at, int B, int nextB) {
   if (load_chunk(h, cfg, in, at, B) != 0) throw Err{h->err};
   h->lastHaveN0 = in->n0 != nullptr;
+  h->chunkFirst = at;
+  // the staging sets are packed at the caller's pitches: a sub-chunk then leaves in one contiguous copy
+  h->rowPitch = ((out->theta_out || out->cart_out || out->trq_out) && out->out_cap > 0) ? out->out_cap : 0;
+  h->histPitch = (out->hist && out->hist_cap > 0) ? out->hist_cap : 0;
   if (nextB > 0 && !in->on_device && !h->profile) {
     // the host rows of the next chunk travel while this one is computed
     try {
@@ -1772,7 +1888,6 @@ static void process_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_b
   {
       const DevCfg &c = h->cfg;
       const bool strictQuatOut = out->cart_out && out->out_cap > 0 && c.Cin > 0 && c.C == 7 && c.c.trig_mode == 1;
-      if (out->on_device) throw Err{"batotp_batch_out.on_device is not implemented yet"};
       if (strictQuatOut || h->profile) {  // host post-processing per sub-chunk / serialised measurement
         for (int b0 = 0; b0 < B; b0 += h->outChunk) {
           do_interp_output(h, b0, std::min(h->outChunk, B - b0));
@@ -1830,15 +1945,161 @@ static void run_chunks(batotp_handle h, const batotp_cfg *cfg, const batotp_batc
       h->inSet[0].src = h->inSet[1].src = nullptr;
       free_ws(h);
       free_out(h);
-      if (h->allocPhase == 1 && std::min(h->outChunk, chunk) > 256)
+      if (e.fitB > 0 && e.fitB < chunk)  // the workspace planner knows what fits
+        chunk = std::max(256, e.fitB / SW_NT * SW_NT);
+      else if (h->allocPhase == 1 && std::min(h->outChunk, chunk) > 256)
         h->outChunk = std::max(256, std::min(h->outChunk, chunk) / 2);
       else
         chunk = std::max(256, (chunk / 2 + SW_NT - 1) / SW_NT * SW_NT);
+      h->capB = 0;
       continue;
     }
     first = false;
     at += B;
   }
+}
+
+// Stragglers.  The trajectories that outgrew the step capacity of their chunk (chunk_sweeps_output) are gathered
+// into one small batch and run again with four times that capacity (growing further, up to maxSteps, by the
+// ordinary capacity retries of a chunk); their results replace the BATOTP_ST_STEP_CAP placeholders in the caller's
+// arrays.  Trajectories are independent, so the results are the ones a single large-capacity pass would give.
+static void run_stragglers(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_in *in, batotp_batch_out *out) {
+  std::vector<int> idx = h->stragglers;
+  h->stragglers.clear();
+  std::sort(idx.begin(), idx.end());
+  idx.erase(std::unique(idx.begin(), idx.end()), idx.end());
+  const int n = (int)idx.size();
+  if (n == 0) return;
+  const DevCfg &c = h->cfg;
+  const int n0 = in->n0_max, J = c.J, Cin = c.Cin;
+  const bool f64 = (in->theta_f64 || in->cart_f64);
+  const size_t es = f64 ? 8 : 4;
+  const void *th = f64 ? (const void *)in->theta_f64 : (const void *)in->theta_f32;
+  const void *ca = f64 ? (const void *)in->cart_f64 : (const void *)in->cart_f32;
+  const size_t thRow = (size_t)J * n0 * es, caRow = (size_t)Cin * n0 * es;
+  // ---- gather the inputs (host rows into host vectors, resident rows into a device block)
+  std::vector<char> hTh, hCa;
+  std::vector<double> hTs, hTres(n);
+  std::vector<int> hN0(n);
+  void *dTh = nullptr, *dCa = nullptr;
+  double *dTs = nullptr;
+  struct Guard {
+    void *&a, *&b;
+    double *&c;
+    ~Guard() {
+      g_free(a);
+      g_free(b);
+      g_free(c);
+    }
+  } guard{dTh, dCa, dTs};
+  if (in->on_device) {
+    if (th) dTh = g_alloc((size_t)n * thRow);
+    if (ca) dCa = g_alloc((size_t)n * caRow);
+    if (in->timestamp) dTs = (double *)g_alloc((size_t)n * n0 * 8);
+  } else {
+    if (th) hTh.resize((size_t)n * thRow);
+    if (ca) hCa.resize((size_t)n * caRow);
+    if (in->timestamp) hTs.resize((size_t)n * n0);
+  }
+  for (int k = 0; k < n; ++k) {
+    const size_t g = (size_t)idx[k];
+    hTres[k] = in->tres ? in->tres[g] : in->tres_all;
+    hN0[k] = in->n0 ? in->n0[g] : n0;
+    if (in->on_device) {
+      if (th) g_d2d((char *)dTh + k * thRow, (const char *)th + g * thRow, thRow, h->stream);
+      if (ca) g_d2d((char *)dCa + k * caRow, (const char *)ca + g * caRow, caRow, h->stream);
+      if (in->timestamp) g_d2d(dTs + (size_t)k * n0, in->timestamp + g * n0, (size_t)n0 * 8, h->stream);
+    } else {
+      if (th) memcpy(hTh.data() + k * thRow, (const char *)th + g * thRow, thRow);
+      if (ca) memcpy(hCa.data() + k * caRow, (const char *)ca + g * caRow, caRow);
+      if (in->timestamp) memcpy(hTs.data() + (size_t)k * n0, in->timestamp + g * n0, (size_t)n0 * 8);
+    }
+  }
+  batotp_batch_in in2 = *in;
+  in2.B = n;
+  in2.n0 = in->n0 ? hN0.data() : nullptr;
+  in2.tres = hTres.data();
+  const void *pTh = in->on_device ? dTh : (th ? (void *)hTh.data() : nullptr);
+  const void *pCa = in->on_device ? dCa : (ca ? (void *)hCa.data() : nullptr);
+  in2.theta_f32 = f64 ? nullptr : (const float *)pTh;
+  in2.cart_f32 = f64 ? nullptr : (const float *)pCa;
+  in2.theta_f64 = f64 ? (const double *)pTh : nullptr;
+  in2.cart_f64 = f64 ? (const double *)pCa : nullptr;
+  in2.timestamp = in->timestamp ? (in->on_device ? dTs : hTs.data()) : nullptr;
+  // ---- results into host vectors with the caller's pitches
+  const size_t oc = (size_t)out->out_cap, hc = (size_t)out->hist_cap;
+  std::vector<int> oI[6];
+  std::vector<double> oD[4];
+  for (auto &v : oI) v.assign(n, 0);
+  for (auto &v : oD) v.assign(n, 0.0);
+  std::vector<float> oTh, oCa, oTq, oHist;
+  std::vector<unsigned char> oFl;
+  batotp_batch_out o2;
+  memset(&o2, 0, sizeof(o2));
+  o2.out_cap = out->out_cap;
+  o2.hist_cap = out->hist_cap;
+  o2.status = oI[0].data();
+  o2.n_rev = oI[1].data();
+  o2.n_fwd = oI[2].data();
+  o2.n_out = oI[3].data();
+  o2.n_cart_out = oI[4].data();
+  o2.n_grid = oI[5].data();
+  o2.t_total = oD[0].data();
+  o2.t_rev = oD[1].data();
+  o2.s_last_sec = oD[2].data();
+  o2.out_sres = oD[3].data();
+  if (out->theta_out && oc) { oTh.assign((size_t)n * J * oc, 0.f); o2.theta_out = oTh.data(); }
+  if (out->cart_out && oc && Cin > 0) { oCa.assign((size_t)n * Cin * oc, 0.f); o2.cart_out = oCa.data(); }
+  if (out->trq_out && oc && c.trqOn) { oTq.assign((size_t)n * J * oc, 0.f); o2.trq_out = oTq.data(); }
+  if (out->hist && hc) { oHist.assign((size_t)n * 4 * hc, 0.f); o2.hist = oHist.data(); }
+  if (out->flags && hc) { oFl.assign((size_t)n * 2 * hc, 0); o2.flags = oFl.data(); }
+  // ---- run them as one chunk with a larger step capacity; the capacity marks of the batch are put back after
+  const int keepHwSc = h->hwSc;
+  const bool keepCollect = h->collectStragglers;
+  h->collectStragglers = false;
+  h->hwSc = (int)std::min<long long>(h->maxSteps, (long long)std::max(h->stragglerSc, 1024) * 4);
+  h->stragglerSc = 0;
+  g_sync(h->stream);
+  g_sync(h->copyStream);
+  h->copiesPending = false;
+  h->inSet[0].src = h->inSet[1].src = nullptr;
+  try {
+    process_chunk(h, cfg, &in2, &o2, 0, n, 0);
+    g_sync(h->copyStream);
+    g_sync(h->stream);
+    h->copiesPending = false;
+  } catch (...) {
+    h->hwSc = keepHwSc;
+    h->collectStragglers = keepCollect;
+    throw;
+  }
+  h->hwSc = keepHwSc;
+  h->collectStragglers = keepCollect;
+  free_ws(h);  // the large-capacity workspace is not what the next batch needs
+  free_out(h);
+  // ---- scatter
+  auto put = [&](void *dst, const void *src, size_t bytes) {
+    if (!bytes) return;
+    if (out->on_device)
+      g_h2d(dst, src, bytes, h->stream);
+    else
+      memcpy(dst, src, bytes);
+  };
+  for (int k = 0; k < n; ++k) {
+    const size_t g = (size_t)idx[k];
+    int *const dI[6] = {out->status, out->n_rev, out->n_fwd, out->n_out, out->n_cart_out, out->n_grid};
+    double *const dD[4] = {out->t_total, out->t_rev, out->s_last_sec, out->out_sres};
+    for (int q = 0; q < 6; ++q)
+      if (dI[q]) put(dI[q] + g, &oI[q][k], sizeof(int));
+    for (int q = 0; q < 4; ++q)
+      if (dD[q]) put(dD[q] + g, &oD[q][k], sizeof(double));
+    if (o2.theta_out) put(out->theta_out + g * J * oc, oTh.data() + (size_t)k * J * oc, (size_t)J * oc * 4);
+    if (o2.cart_out) put(out->cart_out + g * Cin * oc, oCa.data() + (size_t)k * Cin * oc, (size_t)Cin * oc * 4);
+    if (o2.trq_out) put(out->trq_out + g * J * oc, oTq.data() + (size_t)k * J * oc, (size_t)J * oc * 4);
+    if (o2.hist) put(out->hist + g * 4 * hc, oHist.data() + (size_t)k * 4 * hc, 4 * hc * 4);
+    if (o2.flags) put(out->flags + g * 2 * hc, oFl.data() + (size_t)k * 2 * hc, 2 * hc);
+  }
+  g_sync(h->stream);
 }
 
 // Tail overlap.  The sweep kernel is bound by the latency of one trajectory, so a last chunk that fills only a
@@ -1872,6 +2133,9 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
   };
   try {
     h->inSet[0].src = h->inSet[1].src = nullptr;
+    h->stragglers.clear();
+    h->stragglerSc = 0;
+    h->collectStragglers = !cfg->is_interp_only;
     if (h->tailOverlap && !h->profile && !out->on_device && !cfg->is_interp_only && in->B > chunk) {
       int sms = 148;
 #ifndef BATOTP_HOST_EMU
@@ -1888,7 +2152,12 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
           hp->chunk = 0;
           hp->outChunk = h->outChunk;
           hp->maxSteps = h->maxSteps;
+          if (hp->stepHint != h->stepHint) hp->hwSc = 0;
+          hp->stepHint = h->stepHint;
           hp->keepF64 = h->keepF64;
+          hp->stragglers.clear();
+          hp->stragglerSc = 0;
+          hp->collectStragglers = true;
           h->onSweepsDone = [&]() { signal(1); };
           // the tail's input interpolation runs at once (beside that of the first full chunk); its sweeps wait
           // until the sweeps of the first full chunk have completed, so that they run beside output / input phases
@@ -1932,6 +2201,9 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
       h->cntTraj += hp->cntTraj;
       h->launches += hp->launches;
       batotp_cuda_stats_reset(hp);
+      h->stragglers.insert(h->stragglers.end(), hp->stragglers.begin(), hp->stragglers.end());
+      h->stragglerSc = std::max(h->stragglerSc, hp->stragglerSc);
+      hp->stragglers.clear();
       if (tailRes.failed) {
         if (!tailRes.oom) throw Err{tailRes.msg};
         // no room for the second context's workspaces: release them and run the tail here
@@ -1942,9 +2214,12 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
     }
     g_sync(h->copyStream);  // every row has reached the caller's buffers
     h->copiesPending = false;
+    if (!h->stragglers.empty()) run_stragglers(h, cfg, in, out);
+    h->collectStragglers = false;
     return 0;
   } catch (const Err &e) {
     finish_tail(2);
+    h->collectStragglers = false;
     h->err = e.msg;
 #ifndef BATOTP_HOST_EMU
     cudaStreamSynchronize(h->copyStream);
@@ -1969,10 +2244,16 @@ int batotp_cuda_mvc_per_sample(batotp_handle h, double sdot_start, double *sdot_
 }
 
 int batotp_cuda_get_f64(batotp_handle h, const char *name, int traj, int row, double *buf, int cap) {
-  if (!h || h->phase < 2 || traj < 0 || traj >= h->B) return -1;
+  if (!h || !name || h->phase < 2 || traj < 0 || traj >= h->B || row < 0 || cap < 0) return -1;
   try {
     const DevCfg &c = h->cfg;
     const Ws &w = h->w;
+    {  // row must exist in the family the name selects
+      const std::string nn(name);
+      const bool thetaFam = nn.compare(0, 5, "theta") == 0 || nn == "trq_out" || nn[0] == 'a';
+      const bool cartFam = nn.compare(0, 4, "cart") == 0;
+      if ((thetaFam && row >= c.J) || (cartFam && row >= c.C)) return -1;
+    }
     TrajState s;
     g_d2h(&s, w.st + traj, sizeof(TrajState), h->stream);
     g_sync(h->stream);
@@ -1983,6 +2264,12 @@ int batotp_cuda_get_f64(batotp_handle h, const char *name, int traj, int row, do
     const size_t pst = (size_t)w.B * c.R, ast = (size_t)w.B * 4 * MAXD;
     auto prow = [&](const double *base, int r) { return base + (size_t)traj * c.R + r; };
     auto arow = [&](const double *base, int k, int r) { return base + (size_t)traj * 4 * MAXD + (size_t)k * MAXD + r; };
+    if (n == "integ_res" || n == "t_step" || n == "t_total" || n == "t_rev") {
+      // per-trajectory scalars of the sweeps (integRes may be the automatically chosen step, ba.cpp:493-556)
+      const double v = n == "integ_res" ? s.integRes : (n == "t_step" ? s.tStep : (n == "t_total" ? s.tFwd : s.tRev));
+      if (buf && cap > 0) buf[0] = v;
+      return 1;
+    }
     if (n == "thetaC_y") { src = prow(w.P, row); stride = pst; len = s.nPtsC; }
     else if (n == "thetaC_m") { src = prow(w.M, row); stride = pst; len = s.nPtsC; }
     else if (n == "cartC_y") { src = prow(w.P, c.J + row); stride = pst; len = s.nPtsC; }
@@ -2039,6 +2326,13 @@ int batotp_cuda_get_f64(batotp_handle h, const char *name, int traj, int row, do
 int batotp_cuda_set_max_steps(batotp_handle h, int n) {
   if (!h || n < 1024) return -1;
   h->maxSteps = n;
+  return 0;
+}
+
+int batotp_cuda_set_step_hint(batotp_handle h, int n) {
+  if (!h || n < 0) return -1;
+  h->stepHint = n;
+  h->hwSc = 0;  // the hint replaces what earlier chunks have learnt
   return 0;
 }
 

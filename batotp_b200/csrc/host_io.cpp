@@ -207,11 +207,22 @@ int batotp_read_traj_bin(const char *path, int n_joints, int n_cart, double *tre
   float *th = nullptr, *ca = nullptr;
   if (isTheta == 1) {
     th = (float *)malloc((size_t)n_joints * n * 4 + 4);
+    if (!th) {  // a corrupt header can name any size
+      printf("\nError! Cannot allocate %d x %d points for '%s'\n", n_joints, n, path);
+      fclose(fid);
+      return -1;
+    }
     got += fread(th, 4, (size_t)n_joints * n, fid);
   }
   got += fread(&isCart, 4, 1, fid);
   if (isCart == 1) {
     ca = (float *)malloc((size_t)n_cart * n * 4 + 4);
+    if (!ca) {
+      printf("\nError! Cannot allocate %d x %d points for '%s'\n", n_cart, n, path);
+      free(th);
+      fclose(fid);
+      return -1;
+    }
     got += fread(ca, 4, (size_t)n_cart * n, fid);
   }
   fclose(fid);

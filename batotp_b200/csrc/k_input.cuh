@@ -188,7 +188,7 @@ struct ViewSites {
 // ----------------------------------------------------------------------------- load (TP)
 // trajReadBIN / trajReadCSV payload -> FP64 rows (ba.cpp:2283-2299, 2417-2437)
 template <typename T>
-__global__ void k_in_load(Ws w, const T *theta, const T *cart, const int *n0, const double *tres,
+__global__ void k_in_load(WSP, const T *theta, const T *cart, const int *n0, const double *tres,
                           int n0max, int nb) {
   TP_DECOMP(nb);
   const int b = bl;
@@ -245,7 +245,7 @@ __host__ __device__ inline void traj_linear_to4(const Ws &w, double *base, int b
 // ----------------------------------------------------------------------------- prepare (T)
 // ba.cpp:98-183: timestamp de-duplication, length guards, remClosePts (util.cpp:452-524).
 // `ts` (optional) [B][n0max] timestamps of a CSV path; scratch lives in w.sC / w.nrm.
-__global__ void k_in_prepare(Ws w, const double *ts, int n0max, int hasTheta, int hasCart) {
+__global__ void k_in_prepare(WSP, const double *ts, int n0max, int hasTheta, int hasCart) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= w.B) return;
   TrajState &s = w.st[b];
@@ -379,7 +379,7 @@ __host__ __device__ inline void smooth_row(const RV &x, const RV &x2, int n, int
   for (int i = 0; i < n; ++i) x[i] = x2[i];
 }
 
-__global__ void k_in_smooth_decimate(Ws w) {
+__global__ void k_in_smooth_decimate(WSP) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = t / CFG.R, row = t % CFG.R;
   if (b >= w.B) return;
@@ -402,7 +402,7 @@ __global__ void k_in_smooth_decimate(Ws w) {
   if (CFG.c.smooth_window > 1) smooth_row(x, tmp, n, df);
 }
 // after k_in_smooth_decimate: nPts, tresInput, sres bookkeeping (ba.cpp:207-223) (T)
-__global__ void k_in_decim_fix(Ws w) {
+__global__ void k_in_decim_fix(WSP) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= w.B) return;
   TrajState &s = w.st[b];
@@ -470,7 +470,7 @@ __host__ __device__ inline void ik_cspr_point(const Pmat &pm, const double *xyz,
   }
 }
 
-__global__ void k_pointfn(Ws w, double *base, int b0, int mode, int useOver, Pmat pm, int npts, int nb) {
+__global__ void k_pointfn(WSP, double *base, int b0, int mode, int useOver, Pmat pm, int npts, int nb) {
   TP_DECOMP(nb);
   if (i >= npts) return;
   const TrajState &s = w.st[b0 + bl];
@@ -514,7 +514,7 @@ __host__ __device__ inline void aa2q_dev(const double aa[3], double q[4]) {
     for (int i = 0; i < 3; ++i) q[i + 1] = aa[i] * sh / theta;
   }
 }
-__global__ void k_aa2q(Ws w) {
+__global__ void k_aa2q(WSP) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= w.B) return;
   TrajState &s = w.st[b];
@@ -545,7 +545,7 @@ __global__ void k_aa2q(Ws w) {
 // ba.cpp:412-590: cumulative norms, optional automatic integration resolution, scale selection,
 // the weighted arc-length sites sC, and (regular pass) the resample plan of evalSplineFullTraj
 // (ba.cpp:794-819).  ptsOrig is an iota at both call sites (ba.cpp:283, 778) so ptsOrig[i] == i.
-__global__ void k_adjust_s(Ws w, int special) {
+__global__ void k_adjust_s(WSP, int special) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= w.B) return;
   TrajState &s = w.st[b];
@@ -694,7 +694,7 @@ __global__ void k_adjust_s(Ws w, int special) {
 // Spline::getSplineCoeffs on `rows` of the `rowsPerTraj` rows each of nb trajectories holds in the
 // point-major array `src` -> solution rows in `dst`.  b0 = chunk index of the first trajectory.
 // n source: 0 = st.nPts, 1 = st.nOver, 2 = st.nSm
-__global__ void k_thomas_rows(Ws w, double *src, double *dst, int nb, int b0, int rows, int rowsPerTraj,
+__global__ void k_thomas_rows(WSP, double *src, double *dst, int nb, int b0, int rows, int rowsPerTraj,
                               int nsel, int clamped, ThomasTabs tabs) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int bl = t / rows, row = t % rows;
@@ -717,7 +717,7 @@ __global__ void k_thomas_rows(Ws w, double *src, double *dst, int nb, int b0, in
 // JT / CT: joints and Cartesian rows as compile-time constants (0 = take them from the configuration), so that
 // the joint loops unroll and `last` / `cartpt` stay in registers instead of local memory.
 template <int JT, int CT>
-__global__ void k_march(Ws w) {
+__global__ void k_march(WSP) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= w.B) return;
   TrajState &s = w.st[b];
@@ -858,7 +858,7 @@ __global__ void k_march(Ws w) {
 // ----------------------------------------------------------------------------- resample (TP)
 // evalSplineFullTraj, regular pass (ba.cpp:835-859): sites sMVC[i] = sScale*i located in the
 // non-uniform sC by findInterpSegs, values by interp1spline.  Source P/M/sC -> Q.
-__global__ void k_resample(Ws w, int npts, int nb) {
+__global__ void k_resample(WSP, int npts, int nb) {
   TP_DECOMP(nb);
   if (i >= npts) return;
   const int b = bl;
@@ -891,7 +891,7 @@ __global__ void k_resample(Ws w, int npts, int nb) {
   }
 }
 // spline.cpp:78-87: a zero-length input segment aborts findInterpSegs (status only) (T)
-__global__ void k_resample_commit(Ws w) {
+__global__ void k_resample_commit(WSP) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= w.B) return;
   TrajState &s = w.st[b];
@@ -910,7 +910,7 @@ __global__ void k_resample_commit(Ws w) {
 }
 
 // ba.cpp:155-157 after the interpolation-only resample: the result IS the output (sres = outRes)  (T)
-__global__ void k_interp_only_finish(Ws w) {
+__global__ void k_interp_only_finish(WSP) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= w.B) return;
   TrajState &s = w.st[b];
@@ -927,7 +927,7 @@ __global__ void k_interp_only_finish(Ws w) {
 
 // ----------------------------------------------------------------------------- final grid (T + TP)
 // ba.cpp:297-300: sC.clear(); evalSplineFullTraj(traj, sres, sres) -> uniform sites sres*k.
-__global__ void k_final_plan(Ws w) {
+__global__ void k_final_plan(WSP) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= w.B) return;
   TrajState &s = w.st[b];
@@ -954,7 +954,7 @@ __global__ void k_final_plan(Ws w) {
 // and, with torque limits, of the dynamics rows a1..a4 (ba.cpp:1387-1405).  The sweep forms the products
 // evalSplinePartials starts from (3*c3, 2*c2, 6*c3; ba.cpp:1359-1360) when it loads a segment; the output
 // phase evaluates theta(t) from the same rows, so no consumer repeats the /6 divisions.
-__global__ void k_build_table(Ws w, int npts, int nb) {
+__global__ void k_build_table(WSP, int npts, int nb) {
   TP_DECOMP(nb);
   if (i >= npts) return;
   const int b = bl;
@@ -990,7 +990,7 @@ __global__ void k_build_table(Ws w, int npts, int nb) {
 #define BT_TRAJ 8
 #define BT_SEGS 16
 #define BT_ROWS 10
-__global__ void k_build_table_tile(Ws w, int npts, int nb) {
+__global__ void k_build_table_tile(WSP, int npts, int nb) {
   EMU_SHARED double tile[BT_TRAJ][BT_SEGS][BT_ROWS * 4];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int b0 = (int)blockIdx.x * BT_TRAJ, i0 = (int)(blockIdx.z * gridDim.y + blockIdx.y) * BT_SEGS;
@@ -1027,7 +1027,7 @@ __global__ void k_build_table_tile(Ws w, int npts, int nb) {
 
 // Values and s-derivatives on the final grid (ba.cpp:840-855), needed by the dynamic model
 // (findDynModel, ba.cpp:905-938).  Source P/M -> Q (values), GD, GD2.   (TP)
-__global__ void k_eval_grid(Ws w, int npts, int nb) {
+__global__ void k_eval_grid(WSP, int npts, int nb) {
   TP_DECOMP(nb);
   if (i >= npts) return;
   const int b = bl;

@@ -8,7 +8,7 @@
 #include "k_sweep.cuh"
 
 template <int J, bool CART, bool TRQ>
-__global__ void k_mvc(Ws w, double sdotStart, double *out, int cap, int npts, int nb) {
+__global__ void k_mvc(WSP, double sdotStart, double *out, int cap, int npts, int nb) {
   TP_DECOMP(nb);
   if (i >= npts) return;
   const int b = bl;
@@ -20,7 +20,7 @@ __global__ void k_mvc(Ws w, double sdotStart, double *out, int cap, int npts, in
   const double absh = s.integRes;
   const double sBack = s.sresC * (double)(s.nPtsC - 1);
   TrajConsts C;
-  traj_consts(C, s, sBack, absh);
+  traj_consts(C, CFG, s, sBack, absh);
   int seg = imin_(i, s.nPtsC - 2);
   const double sCur = s.sresC * (double)i;
   double sSeg;
@@ -35,7 +35,7 @@ __global__ void k_mvc(Ws w, double sdotStart, double *out, int cap, int npts, in
   };
   const KGlobal K{w.tab + ((size_t)b * w.Nc + seg) * (size_t)RT * 4};
   PointVals<J, CART, TRQ> P;
-  eval_point<J, CART, TRQ>(P, K, tau, C);
+  eval_point<J, CART, TRQ>(P, K, tau, C, CFG);
   // sdotLim without the MVC term and with _sdotMin = 0
   double sd = sdotStart;
   sd = dmin_(sd, sBack / absh);
@@ -45,7 +45,7 @@ __global__ void k_mvc(Ws w, double sdotStart, double *out, int cap, int npts, in
   bis.begin(sd);
   double Lo, Hi;
   for (;;) {
-    const bool viol = verify_point<J, CART, TRQ>(P, C, bis.sdotCur, Lo, Hi);
+    const bool viol = verify_point<J, CART, TRQ>(P, C, CFG, bis.sdotCur, Lo, Hi);
     if (bis.step(viol) != 0) break;
   }
   out[(size_t)b * cap + i] = bis.sdotIn;

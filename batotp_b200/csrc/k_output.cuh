@@ -75,7 +75,7 @@ __host__ __device__ inline void dyn_rr_point(const double th[2], const double th
 }
 
 // findDynModel on the grid (TP): values in Q, s-derivatives in GD/GD2 -> A rows (+Par2Ser)
-__global__ void k_dyn_grid(Ws w, Pmat pm, int npts, int nb) {
+__global__ void k_dyn_grid(WSP, Pmat pm, int npts, int nb) {
   TP_DECOMP(nb);
   if (i >= npts) return;
   const int b = bl;
@@ -125,7 +125,7 @@ __global__ void k_dyn_grid(Ws w, Pmat pm, int npts, int nb) {
 // ----------------------------------------------------------------------------- output plan (T)
 // ba.cpp:1664-1706: output resolution bookkeeping, oversampled size, natural spline of sMVC(t).
 // Output kernels work on the sub-chunk [w.b0, w.b0 + w.Bo) of the resident chunk.
-__global__ void k_out_plan(Ws w, ThomasTabs tabs) {
+__global__ void k_out_plan(WSP, ThomasTabs tabs) {
   const int bl = blockIdx.x * blockDim.x + threadIdx.x;
   if (bl >= w.Bo) return;
   const int b = w.b0 + bl;
@@ -174,7 +174,7 @@ __host__ __device__ __forceinline__ double tmvc_out(int i, int n, double tLast) 
   return (tLast / last) * v;
 }
 
-__global__ void k_out_s(Ws w, int npts, int nb) {
+__global__ void k_out_s(WSP, int npts, int nb) {
   TP_DECOMP(nb);
   if (i >= npts) return;
   const int b = w.b0 + bl;
@@ -205,7 +205,7 @@ __host__ __device__ __forceinline__ int first_seg_uniform(double res, int nIn, d
   while (k < last && !(a < res * (double)(k + 1))) k++;
   return k;
 }
-__global__ void k_out_segs_par(Ws w, int npts, int nb) {
+__global__ void k_out_segs_par(WSP, int npts, int nb) {
   TP_DECOMP(nb);
   if (i >= npts) return;
   TrajState &s = w.st[w.b0 + bl];
@@ -224,7 +224,7 @@ __global__ void k_out_segs_par(Ws w, int npts, int nb) {
   const double lo = res * (double)k, hiEdge = res * (double)(k + 1);
   w.tauO[at] = (a - lo) / (hiEdge - lo);
 }
-__global__ void k_out_segs(Ws w) {
+__global__ void k_out_segs(WSP) {
   const int bl = blockIdx.x * blockDim.x + threadIdx.x;
   if (bl >= w.Bo) return;
   TrajState &s = w.st[w.b0 + bl];
@@ -253,7 +253,7 @@ __global__ void k_out_segs(Ws w) {
 // one or two segments of that row); the tile is turned in shared memory and written with trajectories
 // fastest, the order the point-major consumers read.  The monotonicity test compares with the lane to the
 // left (the site before the tile is recomputed).  Block (32, 8).
-__global__ void k_out_s_segs(Ws w, int npts, int nb) {
+__global__ void k_out_s_segs(WSP, int npts, int nb) {
   EMU_SHARED double tS[32][33], tTau[32][33];
   EMU_SHARED int tSeg[32][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -314,7 +314,7 @@ __global__ void k_out_s_segs(Ws w, int npts, int nb) {
 // theta(t) / cart(t) at the oversampled sites (ba.cpp:1713-1742).  One thread per (point, trajectory, row),
 // rows fastest: the four knot gathers and the store of a point are contiguous R*8-byte runs.  Rows that are
 // not path-driven are filled by the kinematics kernel afterwards (or are the generic robot's zeros).
-__global__ void k_out_eval(Ws w, int npts, int nb) {
+__global__ void k_out_eval(WSP, int npts, int nb) {
   // x covers (trajectory, row) pairs, rows fastest; nb = Bo * R
   const int R = w.R;
   const int xr = (int)(blockIdx.x * blockDim.x + threadIdx.x);
@@ -351,7 +351,7 @@ __global__ void k_out_eval(Ws w, int npts, int nb) {
 // Torque branch, part 1 (ba.cpp:1746-1765 / 1807-1812): values and time derivatives of the
 // re-splined rows at their own knots (seg=i-1, tau=1; i=0: seg=0, tau=0).  O5/OM -> OA, OD, OD2.  (TP)
 // (torque runs use Os == Oc, so OA/OM share O5's pitch)
-__global__ void k_out_knot_eval(Ws w, int npts, int nb) {
+__global__ void k_out_knot_eval(WSP, int npts, int nb) {
   TP_DECOMP(nb);
   if (i >= npts) return;
   const TrajState &s = w.st[w.b0 + bl];
@@ -377,7 +377,7 @@ __global__ void k_out_knot_eval(Ws w, int npts, int nb) {
 }
 
 // Torque branch, part 2 (ba.cpp:1770-1803 / 1815-1825): generalized forces at the output sites (TP)
-__global__ void k_out_trq(Ws w, Pmat pm, int npts, int nb) {
+__global__ void k_out_trq(WSP, Pmat pm, int npts, int nb) {
   TP_DECOMP(nb);
   if (i >= npts) return;
   const TrajState &s = w.st[w.b0 + bl];
@@ -439,7 +439,7 @@ __host__ __device__ __forceinline__ double smooth_at(V &&x, int n, int wIn, int 
 }
 
 // ba.cpp:1838-1871 plan (T): nSm
-__global__ void k_out_smooth_plan(Ws w) {
+__global__ void k_out_smooth_plan(WSP) {
   const int bl = blockIdx.x * blockDim.x + threadIdx.x;
   if (bl >= w.Bo) return;
   TrajState &s = w.st[w.b0 + bl];
@@ -457,7 +457,7 @@ __global__ void k_out_smooth_plan(Ws w) {
 // smooth + linear decimation of every row (src -> dst) and of the torque rows (TP over nSm).
 // Trajectories whose smoothing factor is <= 1.5 (ba.cpp:1838) are copied through unchanged.
 // src/dst are point-major sub-chunk arrays [.][Bo][R].
-__global__ void k_out_smooth(Ws w, double *src, double *dst, int npts, int nb) {
+__global__ void k_out_smooth(WSP, double *src, double *dst, int npts, int nb) {
   TP_DECOMP(nb);
   if (i >= npts) return;
   const TrajState &s = w.st[w.b0 + bl];
@@ -527,7 +527,7 @@ struct OverEval {  // x[j]: row r of trajectory b at oversampled site j; caches 
 };
 // WM = wMid of smooth() (util.cpp:262): the window is 2*WM+1 points
 template <int WM>
-__global__ void k_out_eval_smooth(Ws w, double *dst, int npts, int nb) {
+__global__ void k_out_eval_smooth(WSP, double *dst, int npts, int nb) {
   // x covers (trajectory, row) pairs, rows fastest (nb = Bo * R); y/z the decimated points
   const int R = w.R;
   const int xr = (int)(blockIdx.x * blockDim.x + threadIdx.x);
@@ -580,7 +580,7 @@ __global__ void k_out_eval_smooth(Ws w, double *dst, int npts, int nb) {
 // rows share the site lookups (segO/tauO are read once instead of once per row) and give the thread NR
 // independent chains.  Rows NR..R-1 are the generic robot's zeros.  (TP)
 template <int WM, int NR>
-__global__ void k_out_eval_smooth_rows(Ws w, double *dst, int npts, int nb) {
+__global__ void k_out_eval_smooth_rows(WSP, double *dst, int npts, int nb) {
   TP_DECOMP(nb);
   if (i >= npts) return;
   const int b = w.b0 + bl;
@@ -669,7 +669,7 @@ __global__ void k_out_eval_smooth_rows(Ws w, double *dst, int npts, int nb) {
 
 // ----------------------------------------------------------------------------- final (T + TP)
 // ba.cpp:1873-1921: final sizes
-__global__ void k_out_final_plan(Ws w) {
+__global__ void k_out_final_plan(WSP) {
   const int bl = blockIdx.x * blockDim.x + threadIdx.x;
   if (bl >= w.Bo) return;
   TrajState &s = w.st[w.b0 + bl];
@@ -702,24 +702,27 @@ __host__ __device__ inline void q2aa_dev(const double q[4], double aa[3]) {
 // row order.  src rows hold nSm points, srcM their natural-spline solutions (point-major sub-chunk
 // arrays); outputs are trajectory-major [Bo][row][OutC] as the caller's buffers.  (TP over OutC,
 // points fastest so that the float rows are written coalesced)
-__global__ void k_out_pack(Ws w, double *src, double *srcM, double *trqSrc, double *trqM, float *thetaOut,
-                           float *cartOut, float *trqOut, double *cartOutD, double *outD, int npts, int nb) {
+// `pitch` = row stride (points) of the float32 outputs: the caller's out_cap when the rows travel on, so that a
+// sub-chunk leaves in one contiguous copy; the FP64 side outputs (cartOutD, outD) keep the capacity w.OutC.
+__global__ void k_out_pack(WSP, double *src, double *srcM, double *trqSrc, double *trqM, float *thetaOut,
+                           float *cartOut, float *trqOut, double *cartOutD, double *outD, int pitch, int npts, int nb) {
   PT_DECOMP(npts);
   if (bl >= nb) return;
   const TrajState &s = w.st[w.b0 + bl];
   const int J = CFG.J, C = CFG.C, Cin = CFG.Cin;
-  if (i >= w.OutC) return;
+  const bool inF = i < pitch, inD = i < w.OutC;
+  if (!inF && !inD) return;
   const bool fatal = (s.status & ST_FATAL_MASK) != 0;
   // rows are zero beyond their length (and for trajectories that were not optimised)
-  if (fatal || i >= s.nOut) {
-    for (int r = 0; r < J; ++r) thetaOut[((size_t)bl * J + r) * w.OutC + i] = 0.f;
+  if ((fatal || i >= s.nOut) && inF) {
+    for (int r = 0; r < J; ++r) thetaOut[((size_t)bl * J + r) * pitch + i] = 0.f;
     if (trqOut && CFG.trqOn)
-      for (int r = 0; r < J; ++r) trqOut[((size_t)bl * J + r) * w.OutC + i] = 0.f;
+      for (int r = 0; r < J; ++r) trqOut[((size_t)bl * J + r) * pitch + i] = 0.f;
   }
   if (fatal || i >= s.nCartOut) {
-    if (cartOut)
-      for (int r = 0; r < Cin; ++r) cartOut[((size_t)bl * Cin + r) * w.OutC + i] = 0.f;
-    if (cartOutD && C == 7)
+    if (cartOut && inF)
+      for (int r = 0; r < Cin; ++r) cartOut[((size_t)bl * Cin + r) * pitch + i] = 0.f;
+    if (cartOutD && C == 7 && inD)
       for (int r = 0; r < 7; ++r) cartOutD[((size_t)bl * 7 + r) * w.OutC + i] = 0.0;
   }
   if (fatal) return;
@@ -742,7 +745,7 @@ __global__ void k_out_pack(Ws w, double *src, double *srcM, double *trqSrc, doub
         v = seg_value(seg_coef(orowv(src, w, bl, r), orowv(srcM, w, bl, r), seg), tau, tau2, tau3);
       else
         v = orowv(src, w, bl, r)[i];
-      thetaOut[((size_t)bl * J + r) * w.OutC + i] = (float)v;
+      if (inF) thetaOut[((size_t)bl * J + r) * pitch + i] = (float)v;
       if (outD) outD[((size_t)bl * (CFG.R + J) + r) * w.OutC + i] = v;
     }
     if (trqOut && CFG.trqOn)
@@ -752,7 +755,7 @@ __global__ void k_out_pack(Ws w, double *src, double *srcM, double *trqSrc, doub
           v = seg_value(seg_coef(trqv(trqSrc, w, bl, r), trqv(trqM, w, bl, r), seg), tau, tau2, tau3);
         else
           v = trqv(trqSrc, w, bl, r)[i];
-        trqOut[((size_t)bl * J + r) * w.OutC + i] = (float)v;
+        if (inF) trqOut[((size_t)bl * J + r) * pitch + i] = (float)v;
         if (outD) outD[((size_t)bl * (CFG.R + J) + CFG.R + r) * w.OutC + i] = v;
       }
   }
@@ -775,8 +778,8 @@ __global__ void k_out_pack(Ws w, double *src, double *srcM, double *trqSrc, doub
         for (int r = 0; r < 3; ++r) cv[3 + r] = aa[r];
       }
     }
-    if (cartOut && !(C == 7 && cartOutD))
-      for (int r = 0; r < Cin; ++r) cartOut[((size_t)bl * Cin + r) * w.OutC + i] = (float)cv[r];
+    if (cartOut && inF && !(C == 7 && cartOutD))
+      for (int r = 0; r < Cin; ++r) cartOut[((size_t)bl * Cin + r) * pitch + i] = (float)cv[r];
   }
 }
 
@@ -796,7 +799,8 @@ struct SView {
   int st;
   __host__ __device__ __forceinline__ double operator[](int i) const { return p[i * st]; }
 };
-__global__ void k_out_pack_rows(Ws w, double *src, double *srcM, float *thetaOut, float *cartOut, int npts, int nb) {
+__global__ void k_out_pack_rows(WSP, double *src, double *srcM, float *thetaOut, float *cartOut, int pitch, int npts,
+                                int nb) {
   EMU_SHARED double sY[OP_WARPS][OP_CAP * MAXD];
   EMU_SHARED double sM[OP_WARPS][OP_CAP * MAXD];
   const int lane = threadIdx.x, wy = threadIdx.y;
@@ -846,7 +850,7 @@ __global__ void k_out_pack_rows(Ws w, double *src, double *srcM, float *thetaOut
             v = seg_value(seg_coef(SView{&sY[wy][o + r], J}, SView{&sM[wy][o + r], J}, 0), tau, tau2, tau3);
           else
             v = sY[wy][o + r];
-          thetaOut[((size_t)bl * J + r) * w.OutC + i] = (float)v;
+          thetaOut[((size_t)bl * J + r) * pitch + i] = (float)v;
         }
       }
       __syncwarp();  // the staging buffer is reused below
@@ -857,12 +861,12 @@ __global__ void k_out_pack_rows(Ws w, double *src, double *srcM, float *thetaOut
           v = seg_value(seg_coef(orowv(src, w, bl, r), orowv(srcM, w, bl, r), seg), tau, tau2, tau3);
         else
           v = orowv(src, w, bl, r)[i];
-        thetaOut[((size_t)bl * J + r) * w.OutC + i] = (float)v;
+        thetaOut[((size_t)bl * J + r) * pitch + i] = (float)v;
       }
     }
   }
   if (!live && inRange)  // rows are zero beyond their length (and for trajectories that were not optimised)
-    for (int r = 0; r < J; ++r) thetaOut[((size_t)bl * J + r) * w.OutC + i] = 0.f;
+    for (int r = 0; r < J; ++r) thetaOut[((size_t)bl * J + r) * pitch + i] = 0.f;
   // ---------------- Cartesian rows (generic robot: the source rows J.. at the same index, no re-interpolation)
   if (Cin > 0 && cartOut) {
     const int nC = fatal ? 0 : imin_(s.nCartOut, npts);
@@ -876,40 +880,73 @@ __global__ void k_out_pack_rows(Ws w, double *src, double *srcM, float *thetaOut
       }
       __syncwarp();
       if (liveC)
-        for (int r = 0; r < Cin; ++r) cartOut[((size_t)bl * Cin + r) * w.OutC + i] = (float)sY[wy][lane * Cin + r];
+        for (int r = 0; r < Cin; ++r) cartOut[((size_t)bl * Cin + r) * pitch + i] = (float)sY[wy][lane * Cin + r];
     }
     if (!liveC && inRange)
-      for (int r = 0; r < Cin; ++r) cartOut[((size_t)bl * Cin + r) * w.OutC + i] = 0.f;
+      for (int r = 0; r < Cin; ++r) cartOut[((size_t)bl * Cin + r) * pitch + i] = 0.f;
   }
 }
 
 // s-sdot histories in sdotWrite order (ascending s for the reverse sweep) as float32 (TP over Sc,
 // points fastest); also clears the switching flags beyond the recorded steps.
-__global__ void k_pack_hist(Ws w, float *histOut, int npts, int nb) {
+// `pitch` = row stride (points) of histOut (the caller's hist_cap, or w.Sc); npts covers max(pitch, w.Sc).
+__global__ void k_pack_hist(WSP, float *histOut, int pitch, int npts, int nb) {
   PT_DECOMP(npts);
   if (bl >= nb) return;
-  if (i >= w.Sc) return;
   const int b = w.b0 + bl;
   const TrajState &s = w.st[b];
   const bool fatal = (s.status & ST_FATAL_MASK) != 0;
   const int nRev = fatal ? 0 : s.nRev, nFwd = fatal ? 0 : s.nFwd;
   const double *hb = w.hist + (size_t)b * 4 * w.Sc;
-  float *o = histOut + (size_t)bl * 4 * w.Sc;
+  float *o = histOut + (size_t)bl * 4 * pitch;
   unsigned char *fl = w.flags + (size_t)b * 2 * w.Sc;
+  const bool inF = i < pitch, inS = i < w.Sc;
   if (i < nRev) {
-    o[i] = (float)hb[(w.Sc - nRev) + i];
-    o[(size_t)w.Sc + i] = (float)hb[(size_t)w.Sc + (w.Sc - nRev) + i];
+    if (inF) {
+      o[i] = (float)hb[(w.Sc - nRev) + i];
+      o[(size_t)pitch + i] = (float)hb[(size_t)w.Sc + (w.Sc - nRev) + i];
+    }
   } else {
-    o[i] = 0.f;
-    o[(size_t)w.Sc + i] = 0.f;
-    fl[i] = 0;
+    if (inF) {
+      o[i] = 0.f;
+      o[(size_t)pitch + i] = 0.f;
+    }
+    if (inS) fl[i] = 0;
   }
   if (i < nFwd) {
-    o[2 * (size_t)w.Sc + i] = (float)hb[2 * (size_t)w.Sc + i];
-    o[3 * (size_t)w.Sc + i] = (float)hb[3 * (size_t)w.Sc + i];
+    if (inF) {
+      o[2 * (size_t)pitch + i] = (float)hb[2 * (size_t)w.Sc + i];
+      o[3 * (size_t)pitch + i] = (float)hb[3 * (size_t)w.Sc + i];
+    }
   } else {
-    o[2 * (size_t)w.Sc + i] = 0.f;
-    o[3 * (size_t)w.Sc + i] = 0.f;
-    fl[(size_t)w.Sc + i] = 0;
+    if (inF) {
+      o[2 * (size_t)pitch + i] = 0.f;
+      o[3 * (size_t)pitch + i] = 0.f;
+    }
+    if (inS) fl[(size_t)w.Sc + i] = 0;
   }
+}
+
+// per-trajectory scalars of the output sub-chunk -> the caller's arrays when those live on the device
+// (batotp_batch_out.on_device); `first` = index of the resident chunk's first trajectory in the caller's batch (T)
+struct ScalarOut {
+  int *status, *n_rev, *n_fwd, *n_out, *n_cart_out, *n_grid;
+  double *t_total, *t_rev, *s_last_sec, *out_sres;
+};
+__global__ void k_fetch_scalars(WSP, ScalarOut o, int first, int b0, int nb) {
+  const int bl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bl >= nb) return;
+  const TrajState &s = w.st[b0 + bl];
+  const int g = first + b0 + bl;
+  const bool fatal = (s.status & ST_FATAL_MASK) != 0;
+  if (o.status) o.status[g] = s.status;
+  if (o.n_rev) o.n_rev[g] = s.nRev;
+  if (o.n_fwd) o.n_fwd[g] = s.nFwd;
+  if (o.n_out) o.n_out[g] = fatal ? 0 : s.nOut;
+  if (o.n_cart_out) o.n_cart_out[g] = fatal ? 0 : s.nCartOut;
+  if (o.n_grid) o.n_grid[g] = s.nPtsC;
+  if (o.t_total) o.t_total[g] = s.tFwd;
+  if (o.t_rev) o.t_rev[g] = s.tRev;
+  if (o.s_last_sec) o.s_last_sec[g] = s.sLastSec;
+  if (o.out_sres) o.out_sres[g] = s.sresOut;
 }

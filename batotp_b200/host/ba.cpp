@@ -269,7 +269,10 @@ int BA::sweep(Traj &traj) {
     return -1;
   }
   const int nPts = (int)s.size();
-  const double absh = _cfg.integ_res;
+  // the step the device integrated with: _integRes, or the automatically chosen one (ba.cpp:493-556, 631)
+  double absh = _cfg.integ_res;
+  std::vector<double> one;
+  if (pull("integ_res", 0, one) == 1) absh = one[0];
   const double tElapsed = absh * (nPts - 1);
   printf("%s integ.: %4d steps; %5d ODE evals; %3d failed steps; traj time. %.3f sec.; avg. step size %f sec.\n",
          fwd ? "fwd." : "rev.", nPts, 4 * (nPts - 1), 0, tElapsed, tElapsed / nPts);

@@ -65,6 +65,7 @@ def load(path: Optional[str] = None):
     L.batotp_cuda_set_out_chunk.argtypes = [C.c_void_p, C.c_int]
     L.batotp_cuda_set_max_steps.argtypes = [C.c_void_p, C.c_int]
     L.batotp_cuda_set_tail_overlap.argtypes = [C.c_void_p, C.c_int]
+    L.batotp_cuda_set_step_hint.argtypes = [C.c_void_p, C.c_int]
     L.batotp_cuda_launch_count.argtypes = [C.c_void_p]
     L.batotp_cuda_launch_count.restype = C.c_long
     L.batotp_cuda_stats.argtypes = [C.c_void_p, _dp, C.c_int]
@@ -211,6 +212,9 @@ class Context:
 
     def set_max_steps(self, n: int):
         self.L.batotp_cuda_set_max_steps(self.h, n)
+
+    def set_step_hint(self, n: int):
+        self.L.batotp_cuda_set_step_hint(self.h, n)
 
     def set_tail_overlap(self, on: bool):
         self.L.batotp_cuda_set_tail_overlap(self.h, 1 if on else 0)

@@ -49,6 +49,11 @@ int batotp_cuda_set_out_chunk(batotp_handle h, int n);
  * trajectory that needs more steps (the reference would run it until maxIntegTime, ba.cpp:1117-1122) keeps
  * BATOTP_ST_STEP_CAP and is reported as not optimised; n >= 1024 */
 int batotp_cuda_set_max_steps(batotp_handle h, int n);
+/* Runge-Kutta step capacity (per sweep) a chunk starts with; 0 (default) = automatic: max(1024, 2 x grid points),
+ * then what earlier chunks of the same configuration needed.  Inside batotp_cuda_optimize_batch the few trajectories
+ * of a chunk that outgrow the capacity ("stragglers", at most max(8, chunk/64)) are re-run together with a
+ * larger one after the chunks of the batch; when more do, the chunk is redone with twice the capacity. */
+int batotp_cuda_set_step_hint(batotp_handle h, int n);
 /* tail overlap of batotp_cuda_optimize_batch (default on): when the last chunk of a batch fills at most one sweep
  * CTA per SM (<= SMs x 128 trajectories) it runs on a second context inside the library (own streams and
  * workspaces, one host thread), beside the output / input phases of the full chunks instead of after them.
@@ -145,7 +150,9 @@ int batotp_cuda_mvc_per_sample(batotp_handle h, double sdot_start, double *sdot_
 /* FP64 inspection of the resident chunk (tests, and Traj filling by the facade).
  * name: "theta","cart" (grid/out rows), "thetaC_y","thetaC_m","cartC_y","cartC_m" (spline knots /
  * second-derivative solution), "a1".."a4","a1C_m".."a4C_m", "s_rev","sdot_rev","s_fwd","sdot_fwd",
- * "theta_out","cart_out","trq_out" (FP64 before the float cast).  Returns the length or -1. */
+ * "theta_out","cart_out","trq_out" (FP64 before the float cast); scalars (length 1): "integ_res" (the step the
+ * sweeps used: _integRes or the automatic one, ba.cpp:493-556), "t_step", "t_total", "t_rev".
+ * Returns the length, or -1 for an unknown name / a row the configuration does not have. */
 int batotp_cuda_get_f64(batotp_handle h, const char *name, int traj, int row, double *buf, int cap);
 
 /* keep FP64 copies of the final rows on the device so that batotp_cuda_get_f64 can return

@@ -23,25 +23,36 @@ def main():
     ap.add_argument("--out-chunk", type=int, default=8192)
     ap.add_argument("--lib", default=None)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--workload", default="GEN7DOF", choices=["GEN7DOF", "KUKA", "CSPR3DOF"])
+    ap.add_argument("--trig", type=int, default=1)
+    ap.add_argument("--max-steps", type=int, default=0)
+    ap.add_argument("--skip-host", action="store_true")
     a = ap.parse_args()
     import torch
     from batotp_b200 import native, synth
     from batotp_b200.config import read_config
-    cfg, _ = read_config(os.path.join(ROOT, "tests", "golden", "synthetic", "GEN7DOF_config.dat"))
+    cfg, _ = read_config(os.path.join(ROOT, "tests", "golden", "synthetic", a.workload.replace("KUKA", "KUKA") + "_config.dat"))
+    cfg.trig_mode = a.trig
     B = a.batch
+    gen = {"GEN7DOF": synth.gen7dof_paths, "KUKA": synth.kuka_paths, "CSPR3DOF": synth.cspr_paths}[a.workload]
     parts = []
-    for at in range(0, B, 16384):
-        tres, p = synth.gen7dof_paths(at, min(16384, B - at))
+    for at in range(0, B, 4096):
+        tres, p = gen(at, min(4096, B - at))
         parts.append(p)
     theta = np.concatenate(parts, axis=0)
+    is_cart = a.workload == "CSPR3DOF"
     h_theta = torch.from_numpy(theta).pin_memory()
     d_theta = h_theta.cuda()
     ctx = native.Context(0, a.lib)
-    ctx.set_chunk(a.chunk or B)
+    if a.chunk:
+        ctx.set_chunk(a.chunk)
+    if a.max_steps:
+        ctx.set_max_steps(a.max_steps)
     ctx.set_out_chunk(a.out_chunk)
     J = cfg.n_joints
-    bi_dev = ctx.make_in(tres=tres, device_ptrs=dict(theta=d_theta.data_ptr(), cart=None, B=B, n0_max=theta.shape[2]))
-    res = native.BatchResult(B, J, 0, 0, 0, False, want_rows=False, want_hist=False)
+    bi_dev = ctx.make_in(tres=tres, device_ptrs=dict(theta=None if is_cart else d_theta.data_ptr(),
+                                                     cart=d_theta.data_ptr() if is_cart else None, B=B, n0_max=theta.shape[2]))
+    res = native.BatchResult(B, J, cfg.n_cart, 0, 0, bool(cfg.is_trq_on), want_rows=False, want_hist=False)
     for _ in range(2):
         ctx.optimize_batch(cfg, bi_dev, res)
     torch.cuda.synchronize()
@@ -55,22 +66,25 @@ def main():
     print("resident step: device ms %s  wall ms %s  -> %.0f traj/s" % (
         [round(x[0], 1) for x in ts], [round(x[1], 1) for x in ts], B / (min(x[0] for x in ts) * 1e-3)))
     ref_t = res.t_total.copy()
-    print("sum t_total %.6f  ok %d  mean nfwd %.1f" % (ref_t.sum(), int((res.status & native.ST_FATAL_MASK == 0).sum()),
-                                                       res.n_fwd.mean()))
+    print("sum t_total %.6f  ok %d  mean nfwd %.1f  max nfwd %d  mean ngrid %.0f max ngrid %d" % (
+        ref_t.sum(), int((res.status & native.ST_FATAL_MASK == 0).sum()), res.n_fwd.mean(), res.n_fwd.max(),
+        res.n_grid.mean(), res.n_grid.max()))
+    print("status histogram:", {int(k): int(v) for k, v in zip(*np.unique(res.status, return_counts=True))})
     # host-buffer leg
-    out_cap = int(res.n_out.max()) + 64
-    res_e = native.BatchResult(B, J, 0, out_cap, 0, False, want_rows=True, want_hist=False, pinned=True)
-    bi = ctx.make_in(theta=h_theta.numpy(), tres=tres)
-    ctx.optimize_batch(cfg, bi, res_e)
-    ts = []
-    for _ in range(a.reps):
-        t0 = time.perf_counter()
+    if not a.skip_host:
+        out_cap = int(res.n_out.max()) + 64
+        res_e = native.BatchResult(B, J, cfg.n_cart, out_cap, 0, bool(cfg.is_trq_on), want_rows=True, want_hist=False, pinned=True)
+        bi = ctx.make_in(theta=None if is_cart else h_theta.numpy(), cart=h_theta.numpy() if is_cart else None, tres=tres)
         ctx.optimize_batch(cfg, bi, res_e)
-        torch.cuda.synchronize()
-        ts.append((time.perf_counter() - t0) * 1e3)
-    print("host-buffer step: wall ms %s -> %.0f traj/s; identical t_total: %s; rows nonzero: %s" % (
-        [round(x, 1) for x in ts], B / (min(ts) * 1e-3), bool(np.array_equal(ref_t, res_e.t_total)),
-        bool(np.abs(res_e.theta_out).sum() > 0)))
+        ts = []
+        for _ in range(a.reps):
+            t0 = time.perf_counter()
+            ctx.optimize_batch(cfg, bi, res_e)
+            torch.cuda.synchronize()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        print("host-buffer step: wall ms %s -> %.0f traj/s; identical t_total: %s; rows nonzero: %s" % (
+            [round(x, 1) for x in ts], B / (min(ts) * 1e-3), bool(np.array_equal(ref_t, res_e.t_total)),
+            bool(np.abs(res_e.theta_out).sum() > 0)))
     # profiled resident step
     ctx.set_profile(True)
     ctx.optimize_batch(cfg, bi_dev, res)

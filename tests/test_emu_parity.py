@@ -280,3 +280,103 @@ def test_batch_writer_files_are_the_reference_formats(ctx, tmp_path):
             continue
         assert open(f, "rb").read() == P.device_traj_out_bytes(cfg2, res2, b)
         assert open(os.path.join(str(tmp_path), "s-sdot_%07d.dat" % b), "rb").read() == P.device_s_sdot_bytes(res2, b)
+
+
+def test_two_contexts_with_different_configs_do_not_disturb_each_other():
+    """The run options travel with every launch (Ws is a kernel parameter), so contexts that hold different
+    configurations can be driven phase by phase in any interleaving (round-1 advisor finding: a process-global
+    config made context A compute with B's limits)."""
+    import __graft_entry__ as g
+    lib = g.build_emu()
+    a, b = native.Context(0, lib), native.Context(0, lib)
+    try:
+        cfgA, tresA, thA, _ = P.load_synth("GEN7DOF", 0, 2)
+        cfgB, tresB, thB, _ = P.load_synth("KUKA", 0, 1)
+        a.load(cfgA, a.make_in(thA, None, tresA))
+        a.interp_input()
+        b.load(cfgB, b.make_in(thB, None, tresB))
+        b.interp_input()
+        a.sweeps()
+        b.sweeps()
+        a.interp_output()
+        b.interp_output()
+        ra = a.fetch(native.BatchResult(2, cfgA.n_joints, cfgA.n_cart, 8192, 8192, False))
+        rb = b.fetch(native.BatchResult(1, cfgB.n_joints, cfgB.n_cart, 32768, 32768, False))
+        for k in range(2):
+            assert P.compare(cfgA, ra, k, P.OracleRun(cfgA, tresA, thA[k], None)) == []
+        assert P.compare(cfgB, rb, 0, P.OracleRun(cfgB, tresB, thB[0], None)) == []
+    finally:
+        a.close()
+        b.close()
+
+
+def test_context_reuse_across_robots_and_path_lengths(ctx):
+    """One context, robots with different row counts and path lengths one after the other: the input staging
+    sets keep separate capacities for the joint and the Cartesian block (round-1 advisor finding: RR stock twice,
+    then GEN7DOF, wrote past the staging buffer)."""
+    for name in ("RR", "RR", "GEN7DOF", "CSPR3DOF", "UR5", "RR"):
+        cfg, tres, th, ca, ts = P.load_stock(name)
+        res = P.run_device(ctx, cfg, tres, th, ca, ts)
+        d = P.GOLD + "/stock/" + name
+        assert P.device_traj_out_bytes(cfg, res, 0) == open(d + "/ref_traj_out.dat", "rb").read(), name
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 0, 3)
+    res = P.run_device(ctx, cfg, tres, th, None)
+    assert P.compare(cfg, res, 2, P.OracleRun(cfg, tres, th[2], None)) == []
+
+
+def test_phase_api_load_leaves_the_chunk_setting_alone(ctx):
+    """batotp_cuda_load sizes the resident workspace from its own batch and must not turn the automatic
+    chunking (0) into `chunk = B of the last phase-wise load` (round-1 advisor finding)."""
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 0, 5)
+    ctx.set_chunk(0)
+    ctx.load(cfg, ctx.make_in(th[:1], None, tres))
+    ctx.interp_input()
+    ctx.stats_reset()
+    P.run_device(ctx, cfg, tres, th, None)
+    assert ctx.stats()["sweep_launches"] == 1  # one chunk of 5, not five chunks of 1
+    ctx.set_chunk(16384)
+
+
+def test_stragglers_are_rerun_with_a_larger_step_capacity(ctx):
+    """A few trajectories that outgrow the step capacity of their chunk do not make the whole chunk run again:
+    they are re-run together after the batch (batotp_cuda.cu run_stragglers).  Same results as a run whose
+    capacity served everybody; the sweep kernel is launched once per chunk plus once for the stragglers."""
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 100, 20)
+    ctx.set_chunk(10)  # two chunks
+    try:
+        ctx.set_step_hint(0)
+        a = P.run_device(ctx, cfg, tres, th, None)
+        steps = np.sort(np.maximum(a.n_rev, a.n_fwd))
+        hint = int(steps[-4])  # three trajectories need more steps than this capacity
+        assert steps[-3] > hint >= steps[-5]
+        ctx.set_step_hint(hint)
+        ctx.stats_reset()
+        b = P.run_device(ctx, cfg, tres, th, None)
+        st = ctx.stats()
+    finally:
+        ctx.set_step_hint(0)
+        ctx.set_chunk(16384)
+    assert (b.status & native.ST_FATAL_MASK == 0).all()
+    for nm in ("status", "n_rev", "n_fwd", "n_out", "n_grid", "t_total", "t_rev", "s_last_sec", "out_sres",
+               "theta_out", "hist", "flags"):
+        assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
+    assert st["sweep_launches"] == 3 and st["trajectories"] == 20
+
+
+def test_results_into_device_resident_buffers(ctx):
+    """batotp_batch_out.on_device: every pointer of the result is device memory (here, under the emulation, plain
+    memory): scalars arrive through k_fetch_scalars, rows through the same packed staging sets."""
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 30, 7)
+    ctx.set_chunk(4)
+    ctx.set_out_chunk(3)
+    try:
+        a = P.run_device(ctx, cfg, tres, th, None, out_cap=4096, hist_cap=4096)
+        b = native.BatchResult(7, cfg.n_joints, cfg.n_cart, 4096, 4096, False)
+        b.c.on_device = 1
+        ctx.optimize_batch(cfg, ctx.make_in(th, None, tres), b)
+    finally:
+        ctx.set_chunk(16384)
+        ctx.set_out_chunk(8192)
+    for nm in ("status", "n_rev", "n_fwd", "n_out", "n_cart_out", "n_grid", "t_total", "t_rev", "s_last_sec",
+               "out_sres", "theta_out", "hist", "flags"):
+        assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
