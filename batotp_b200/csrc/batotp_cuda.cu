@@ -395,6 +395,26 @@ inline ThomasTabs thomas_tabs(const batotp_ctx *h) {
   return ThomasTabs{p, p + n, p + 2 * n, p + 3 * n, p + 4 * n, p + 5 * n};
 }
 
+// glibc's x86-64 sin/cos come in two arithmetics, selected at load time: with fused multiply-adds on a CPU that
+// has FMA and AVX2, without otherwise (sysdeps/x86_64/fpu/multiarch/ifunc-avx-fma4.h; the FMA4 variant of old AMD
+// parts contracts the same expressions)
+bool host_libm_uses_fma() {
+#if defined(__x86_64__) && (defined(__GNUC__) || defined(__clang__))
+  static const bool v = [] {
+    // BATOTP_TRIG_VARIANT=1|3 overrides the detection (a process started with GLIBC_TUNABLES=glibc.cpu.hwcaps=-FMA
+    // runs the plain variant on an FMA machine: that is how the test suite checks both)
+    if (const char *e = getenv("BATOTP_TRIG_VARIANT")) {
+      if (e[0] == '1') return false;
+      if (e[0] == '3') return true;
+    }
+    return (__builtin_cpu_supports("fma") && __builtin_cpu_supports("avx2")) || __builtin_cpu_supports("fma4");
+  }();
+  return v;
+#else
+  return false;
+#endif
+}
+
 int oversample_cap(const batotp_ctx *h, int Sc) {
   // nPtsMVCout bound for nFwd <= Sc (ba.cpp:1667-1685)
   const batotp_cfg &c = h->cfg.c;
@@ -461,7 +481,9 @@ size_t out_bytes_per_traj(const batotp_ctx *h, int Sc) {
 void ensure_ws(batotp_ctx *h, int B, int Nc, int Sc) {
   const DevCfg &c = h->cfg;
   const bool trq = c.trqOn != 0;
-  if (B <= h->capB && Nc <= h->capNc && Sc <= h->capSc && c.R == h->capR && c.RT == h->capRT && trq == h->capTrq) {
+  // (with a step hint the capacity asked for is taken literally, not "at least")
+  const bool scOk = h->stepHint > 0 ? (Sc == h->capSc) : (Sc <= h->capSc);
+  if (B <= h->capB && Nc <= h->capNc && scOk && c.R == h->capR && c.RT == h->capRT && trq == h->capTrq) {
     h->w.B = B;
     return;
   }
@@ -616,6 +638,8 @@ void set_cfg(batotp_ctx *h, const batotp_cfg *cfg) {
   d.R = d.J + d.C;
   d.RT = d.J + (d.cartOn ? 3 : 0) + (d.trqOn ? 4 * d.J : 0);
   d.quadThresh = cfg->cart_thresh * cfg->cart_thresh;
+  // strict trig on the device: the arithmetic variant of the host libm this process runs against (k_trig.cuh)
+  d.trigDev = (cfg->trig_mode == 1) ? (host_libm_uses_fma() ? 3 : 1) : 0;
   const double Bt[6][6] = {{1. / 5, 3. / 40, 44. / 45, 19372. / 6561, 9017. / 3168, 35. / 384},
                            {0, 9. / 40, -56. / 15, -25360. / 2187, -355. / 33, 0},
                            {0, 0, 32. / 9, 64448. / 6561, 46732. / 5247, 500. / 1113},
@@ -695,23 +719,23 @@ void host_rows_apply(batotp_ctx *h, double *base, int npts, int nb, int b0, bool
           double *p = r0 + (size_t)i * pst;
           double xyz[3];
           if (c.c.robot_type == BATOTP_KUKA) {
-            fk_kuka_point(p, xyz);
+            fk_kuka_point(Trig{0}, p, xyz);
             for (int q = 0; q < 3; ++q) p[J + q] = xyz[q];
           } else if (c.c.robot_type == BATOTP_RR) {
-            fk_rr_point(p, xyz);
+            fk_rr_point(Trig{0}, p, xyz);
             p[J] = xyz[0];
             p[J + 1] = xyz[1];
           }
         }
       } else if (kind == 2) {
         double aa[3] = {r0[J + 3], r0[J + 4], r0[J + 5]}, q[4], qprev[4];
-        aa2q_dev(aa, qprev);
+        aa2q_dev(Trig{0}, aa, qprev);
         for (int i = 0; i < n; ++i) {
           double *p = r0 + (size_t)i * pst;
           aa[0] = p[J + 3];
           aa[1] = p[J + 4];
           aa[2] = p[J + 5];
-          aa2q_dev(aa, q);
+          aa2q_dev(Trig{0}, aa, q);
           double qdir = 0;
           for (int j = 0; j < 4; ++j) qdir += q[j] * qprev[j];
           if (qdir < 0.0)
@@ -763,7 +787,7 @@ void apply_kinematics(batotp_ctx *h, int where) {
   const int b0 = over ? h->w.b0 : 0;
   const int mode = kin_mode(h, where);
   if (mode == 0) return;
-  if (mode == 1 && c.c.trig_mode == 1) {
+  if (mode == 1 && c.c.trig_mode == 2) {
     host_rows_apply(h, base, npts, nb, b0, over, 1);
     return;
   }
@@ -971,7 +995,7 @@ int do_interp_input(batotp_ctx *h, bool haveN0, bool planSync) {
   run_load_prepare(h, haveN0);
   const int pt = c.c.path_type;
   if ((pt == BATOTP_CART || pt == BATOTP_BOTH) && c.Cin == 6) {  // ba.cpp:185-192
-    if (c.c.trig_mode == 1)
+    if (c.c.trig_mode == 2)
       host_rows_apply(h, w.P, w.Nc, B, 0, false, 2);
     else
       LAUNCH_T(h, k_aa2q, B, w);
@@ -1013,7 +1037,7 @@ int do_interp_input(batotp_ctx *h, bool haveN0, bool planSync) {
   LAUNCH_T(h, k_final_plan, B, w);
   if (c.trqOn) {
     LAUNCH_TP(h, k_eval_grid, w.Nc, B, w);
-    if (!c.c.is_parallel && c.c.trig_mode == 1)
+    if (!c.c.is_parallel && c.c.trig_mode == 2)
       host_dyn_rr_grid(h);
     else
       LAUNCH_TP(h, k_dyn_grid, w.Nc, B, w, h->pm);
@@ -1060,7 +1084,7 @@ int do_interp_only(batotp_ctx *h, bool haveN0) {
     }
     const int pt = c.c.path_type;
     if ((pt == BATOTP_CART || pt == BATOTP_BOTH) && c.Cin == 6) {  // ba.cpp:145-148
-      if (c.c.trig_mode == 1)
+      if (c.c.trig_mode == 2)
         host_rows_apply(h, w.P, w.Nc, h->B, 0, false, 2);
       else
         LAUNCH_T(h, k_aa2q, h->B, w);
@@ -1074,7 +1098,7 @@ int do_interp_only(batotp_ctx *h, bool haveN0) {
     w.Bo = h->B;
     LAUNCH_T(h, k_interp_only_finish, h->B, w);
     select_out_set(h, 0);
-    const bool strictQuat = (c.C == 7 && c.c.trig_mode == 1);
+    const bool strictQuat = (c.C == 7 && c.c.trig_mode != 0);
     const int rp = row_pitch(h), hp = hist_pitch(h);
     if (h->d_trqOut) g_zero(h->d_trqOut, (size_t)h->B * c.J * rp * sizeof(float), h->stream);  // no torque rows here
     LAUNCH_PT(h, k_out_pack, std::max(w.OutC, rp), h->B, w, w.P, w.M, (double *)nullptr, (double *)nullptr, h->d_thetaOut,
@@ -1147,7 +1171,7 @@ void do_interp_output(batotp_ctx *h, int b0, int Bo) {
       // re-spline theta(t) (and cart(t) for the parallel robot) to get time derivatives
       thomas_rows(h, w.O5, w.OM, Bo, b0, c.c.is_parallel ? c.R : c.J, c.R, 1, c.c.is_parallel ? 0 : 1);
       LAUNCH_TP(h, k_out_knot_eval, lOc, Bo, w);
-      if (!c.c.is_parallel && c.c.trig_mode == 1)
+      if (!c.c.is_parallel && c.c.trig_mode == 2)
         host_dyn_rr_out(h);
       else
         LAUNCH_TP(h, k_out_trq, lOc, Bo, w, h->pm);
@@ -1171,7 +1195,7 @@ void do_interp_output(batotp_ctx *h, int b0, int Bo) {
     thomas_rows(h, cur, w.OM, Bo, b0, c.R, c.R, 2, 0);
     if (c.trqOn) thomas_rows(h, trqCur, w.TrqM, Bo, b0, c.J, MAXD, 2, 0);
   }
-  const bool strictQuat = (c.C == 7 && c.c.trig_mode == 1);
+  const bool strictQuat = (c.C == 7 && c.c.trig_mode != 0);
   const int rp = row_pitch(h), hp = hist_pitch(h);
   if (c.c.robot_type == BATOTP_GENJNT && c.C != 7 && c.Cin <= MAXD && !c.trqOn && !h->d_outD && rp > 0 && Bo > 0) {
     // generic robot, float rows only: warp-per-tile staging through shared memory (k_out_pack_rows)
@@ -1276,6 +1300,97 @@ __global__ void k_selftest_div(unsigned long long seed, int perThread, unsigned 
   atomicAdd(fastTaken, fast);
 }
 #endif
+
+// Self-test of the strict trigonometry (k_trig.cuh) against the libm of the host this process runs on: the device
+// evaluates sin / cos at pseudo-random arguments (several magnitudes: the working range of joint angles in radians,
+// the Taylor and table branches, the pi/2 reductions, tiny arguments), the host repeats them with its own sin / cos.
+__host__ __device__ inline unsigned long long tt_mix(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__host__ __device__ inline double tt_arg(unsigned long long seed, long long i) {
+  const unsigned long long a = tt_mix(seed ^ ((unsigned long long)i * 0xD1342543DE82EF95ull)), b = tt_mix(a);
+  const double u = (double)(a >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;  // [-1, 1)
+  switch ((unsigned)(b & 15u)) {
+    case 0: return u * 0.13;        // TAYLOR_SIN
+    case 1: case 2: case 3: return u * 0.86;   // table branch
+    case 4: case 5: case 6: return u * 2.43;   // pi/2 - |x|
+    case 7: case 8: case 9: case 10: return u * 3.4;  // +-195 degrees: every joint range of the shipped robots
+    case 11: case 12: return u * 13.0;         // reduce_sincos, a few turns
+    case 13: return u * 1.0e4;
+    case 14: return u * 1.0e8;                 // up to the end of the ported range
+    default: {                                 // tiny and subnormal-adjacent magnitudes
+      const int e = (int)((b >> 8) % 60);
+      return ldexp(u, -e);
+    }
+  }
+}
+__global__ void k_selftest_trig(unsigned long long seed, long long first, int n, int mode, double *xs, double *ss,
+                                double *cs) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const double x = tt_arg(seed, first + t);
+  const Trig tg{mode};
+  xs[t] = x;
+  ss[t] = tg.s(x);
+  cs[t] = tg.c(x);
+}
+
+// Self-test of the branch-free bracket update of the sweep kernel (Bisect::step_any) against the reference-shaped
+// one (Bisect::step, ba.cpp:1270-1321) on random problems "feasible iff sdot^2 <= T": same result code and same next
+// candidate after every verification, same settled value and iteration count.  kinds: thresholds all over the
+// range, at / next to a candidate, zero, negative start.  One problem per call; runs as a device kernel in the
+// product build and sequentially in the host emulation.
+__host__ __device__ inline bool bisect_problem_differs(unsigned long long seed, long long k) {
+  unsigned long long z = tt_mix(seed ^ ((unsigned long long)k * 0xD1342543DE82EF95ull));
+  auto rnd = [&]() {
+    z = tt_mix(z);
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+  };
+  const int kind = (int)(rnd() * 8);
+  double start = exp((rnd() - 0.5) * 40.0);
+  if (kind == 5) start = -start;
+  if (kind == 6) start = 0.0;
+  double T = start * start * exp(-rnd() * (kind == 1 ? 60.0 : 6.0));
+  if (kind == 2) T = 0.0;                          // nothing but sdot = 0 is feasible
+  if (kind == 3) T = -1.0;                         // nothing is feasible: the bracket collapses or 100 passes
+  if (kind == 4) T = start * start * (1.0 + 1e-3);  // feasible at once
+  if (kind == 7) {                                 // threshold exactly at a candidate of the sequence
+    Bisect p;
+    p.begin(start);
+    const int stop = 1 + (int)(rnd() * 12);
+    for (int it = 0; it < stop; ++it)
+      if (p.step(true) != 0) break;
+    T = p.sdotCur * p.sdotCur;
+  }
+  Bisect a, b;
+  a.begin(start);
+  b.begin(start);
+  int ra = 0, rb = 0, guard = 0;
+  while (ra == 0 && rb == 0 && guard++ < 300) {
+    const bool va = !(a.sdotCur * a.sdotCur <= T), vb = !(b.sdotCur * b.sdotCur <= T);
+    ra = a.step(va);
+    rb = b.step_any(vb);
+    if (ra != rb) return true;
+    if (ra == 0 && a.sdotCur != b.sdotCur && !(a.sdotCur != a.sdotCur && b.sdotCur != b.sdotCur)) return true;
+  }
+  const double inB = (rb == 2) ? start : b.sdotCur;  // what the sweep kernel forms after the loop
+  if (ra != rb || a.nIter != b.nIter) return true;
+  return a.sdotIn != inB && !(a.sdotIn != a.sdotIn && inB != inB);
+}
+__global__ void k_selftest_bisect(unsigned long long seed, long long first, int n, unsigned long long *bad) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  if (bisect_problem_differs(seed, first + t)) {
+#ifdef BATOTP_HOST_EMU
+    (*bad)++;
+#else
+    atomicAdd(bad, 1ull);
+#endif
+  }
+}
 
 // ----------------------------------------------------------------------------- C ABI
 extern "C" {
@@ -1436,6 +1551,51 @@ int batotp_cuda_selftest_div(batotp_handle h, unsigned long long seed, long long
 #endif
 }
 
+int batotp_cuda_selftest_trig(batotp_handle h, unsigned long long seed, long long n, long long *mismatches,
+                              int *variant) {
+  if (!h || n < 0) return -1;
+  try {
+#ifndef BATOTP_HOST_EMU
+    CU_CHECK(cudaSetDevice(h->device));
+#endif
+    const int mode = host_libm_uses_fma() ? 3 : 1;
+    if (variant) *variant = mode;
+    const int M = 1 << 22;
+    double *d = (double *)g_alloc((size_t)3 * M * 8);
+    std::vector<double> hb((size_t)3 * M);
+    long long bad = 0;
+    const unsigned nth = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+    for (long long at = 0; at < n; at += M) {
+      const int m = (int)std::min<long long>(M, n - at);
+      LAUNCH_T(h, k_selftest_trig, m, seed, at, m, mode, d, d + M, d + 2 * (size_t)M);
+      g_d2h(hb.data(), d, (size_t)3 * M * 8, h->stream);
+      g_sync(h->stream);
+      std::vector<long long> part(nth, 0);
+      auto work = [&](unsigned tid) {
+        long long b = 0;
+        for (int i = (int)tid; i < m; i += (int)nth) {
+          const double x = hb[i];
+          const double sr = sin(x), cr = cos(x);  // the host libm: what the reference calls
+          if (memcmp(&sr, &hb[(size_t)M + i], 8) != 0) b++;
+          if (memcmp(&cr, &hb[2 * (size_t)M + i], 8) != 0) b++;
+        }
+        part[tid] = b;
+      };
+      std::vector<std::thread> th;
+      for (unsigned t = 1; t < nth; ++t) th.emplace_back(work, t);
+      work(0);
+      for (auto &x : th) x.join();
+      for (long long v : part) bad += v;
+    }
+    g_free(d);
+    if (mismatches) *mismatches = bad;
+    return 0;
+  } catch (const Err &e) {
+    h->err = e.msg;
+    return -1;
+  }
+}
+
 int batotp_cuda_set_keep_f64(batotp_handle h, int on) {
   if (!h) return -1;
   h->keepF64 = on != 0;
@@ -1488,58 +1648,32 @@ int batotp_emu_set_rcp_ulps(int k) {
   g_emu_rcp_ulps = k;
   return 0;
 }
-// TEST-ONLY: the branch-free bracket update of the sweep kernel (Bisect::step_any) against the reference-shaped
-// one (Bisect::step, ba.cpp:1270-1321) on n random problems "feasible iff sdot^2 <= T": same result code and
-// same next candidate after every verification, same settled value and iteration count.  Returns the number of
-// problems that differ.  kinds: thresholds all over the range, at / next to a candidate, zero, negative start.
-long long batotp_emu_bisect_selftest(unsigned long long seed, long long n) {
-  auto rnd = [&]() {
-    seed += 0x9E3779B97F4A7C15ull;
-    unsigned long long z = seed;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return (double)((z ^ (z >> 31)) >> 11) * (1.0 / 9007199254740992.0);
-  };
-  long long bad = 0;
-  for (long long k = 0; k < n; ++k) {
-    const int kind = (int)(rnd() * 8);
-    double start = std::exp((rnd() - 0.5) * 40.0);
-    if (kind == 5) start = -start;
-    if (kind == 6) start = 0.0;
-    double T = start * start * std::exp(-rnd() * (kind == 1 ? 60.0 : 6.0));
-    if (kind == 2) T = 0.0;                          // nothing but sdot = 0 is feasible
-    if (kind == 3) T = -1.0;                         // nothing is feasible: the bracket collapses or 100 passes
-    if (kind == 4) T = start * start * (1.0 + 1e-3);  // feasible at once
-    if (kind == 7) {                                 // threshold exactly at a candidate of the sequence
-      Bisect p;
-      p.begin(start);
-      const int stop = 1 + (int)(rnd() * 12);
-      for (int it = 0; it < stop; ++it)
-        if (p.step(true) != 0) break;
-      T = p.sdotCur * p.sdotCur;
-    }
-    Bisect a, b;
-    a.begin(start);
-    b.begin(start);
-    int ra = 0, rb = 0, guard = 0;
-    bool same = true;
-    while (ra == 0 && rb == 0 && guard++ < 300) {
-      const bool va = !(a.sdotCur * a.sdotCur <= T), vb = !(b.sdotCur * b.sdotCur <= T);
-      ra = a.step(va);
-      rb = b.step_any(vb);
-      if (ra != rb) same = false;
-      if (ra == 0 && memcmp(&a.sdotCur, &b.sdotCur, sizeof(double)) != 0) same = false;
-      if (!same) break;
-    }
-    if (same) {
-      const double inB = (rb == 2) ? start : b.sdotCur;  // what the sweep kernel forms after the loop
-      if (ra != rb || memcmp(&a.sdotIn, &inB, sizeof(double)) != 0 || a.nIter != b.nIter) same = false;
-    }
-    if (!same) bad++;
-  }
-  return bad;
-}
 #endif
+int batotp_cuda_selftest_bisect(batotp_handle h, unsigned long long seed, long long n, long long *mismatches) {
+  if (!h || n < 0) return -1;
+  try {
+#ifndef BATOTP_HOST_EMU
+    CU_CHECK(cudaSetDevice(h->device));
+#endif
+    unsigned long long *d = (unsigned long long *)g_alloc(8);
+    g_zero(d, 8, h->stream);
+    const int M = 1 << 24;
+    for (long long at = 0; at < n; at += M) {
+      const int m = (int)std::min<long long>(M, n - at);
+      LAUNCH_T(h, k_selftest_bisect, m, seed, at, m, d);
+    }
+    unsigned long long bad = 0;
+    g_d2h(&bad, d, 8, h->stream);
+    g_sync(h->stream);
+    g_free(d);
+    if (mismatches) *mismatches = (long long)bad;
+    return 0;
+  } catch (const Err &e) {
+    h->err = e.msg;
+    return -1;
+  }
+}
+
 int batotp_cuda_timer(batotp_handle h, int which, double *elapsed_ms) {
 #ifndef BATOTP_HOST_EMU
   if (!h || which < 0 || which > 1) return -1;
@@ -1818,7 +1952,7 @@ static void fetch_rows(batotp_handle h, batotp_batch_out *out, int first, cudaSt
     copy_rows(out->theta_out + (size_t)g0 * c.J * oc, oc, h->d_thetaOut, rp, (size_t)Bo * c.J, 4, cs);
   if (out->trq_out && oc > 0 && c.trqOn)
     copy_rows(out->trq_out + (size_t)g0 * c.J * oc, oc, h->d_trqOut, rp, (size_t)Bo * c.J, 4, cs);
-  if (out->cart_out && oc > 0 && c.Cin > 0 && !(c.C == 7 && c.c.trig_mode == 1))
+  if (out->cart_out && oc > 0 && c.Cin > 0 && !(c.C == 7 && c.c.trig_mode != 0))
     copy_rows(out->cart_out + (size_t)g0 * c.Cin * oc, oc, h->d_cartOut, rp, (size_t)Bo * c.Cin, 4, cs);
   const size_t hc = (size_t)out->hist_cap, hp = (size_t)hist_pitch(h);
   if (out->hist && hc > 0) copy_rows(out->hist + (size_t)g0 * 4 * hc, hc, h->d_histOut, hp, (size_t)Bo * 4, 4, cs);
@@ -1832,7 +1966,7 @@ static void fetch_sub(batotp_handle h, batotp_batch_out *out, int first) {
   const DevCfg &c = h->cfg;
   const Ws &w = h->w;
   ProfScope ps_(h, "copy_d2h(fetch)");
-  const bool strictQuatOut = out->cart_out && out->out_cap > 0 && c.Cin > 0 && c.C == 7 && c.c.trig_mode == 1;
+  const bool strictQuatOut = out->cart_out && out->out_cap > 0 && c.Cin > 0 && c.C == 7 && c.c.trig_mode != 0;
   if (out->on_device && strictQuatOut)
     throw Err{"batotp_batch_out.on_device: axis-angle rows in strict-trig mode are finished on the host; use trig_mode 0"};
   fetch_scalars(h, out, first, w.b0, w.Bo);
@@ -1887,7 +2021,7 @@ static void process_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_b
   if (h->onSweepsDone) h->onSweepsDone();
   {
       const DevCfg &c = h->cfg;
-      const bool strictQuatOut = out->cart_out && out->out_cap > 0 && c.Cin > 0 && c.C == 7 && c.c.trig_mode == 1;
+      const bool strictQuatOut = out->cart_out && out->out_cap > 0 && c.Cin > 0 && c.C == 7 && c.c.trig_mode != 0;
       if (strictQuatOut || h->profile) {  // host post-processing per sub-chunk / serialised measurement
         for (int b0 = 0; b0 < B; b0 += h->outChunk) {
           do_interp_output(h, b0, std::min(h->outChunk, B - b0));

@@ -1,12 +1,13 @@
-// host_strict.inl — strict-parity trig (cfg.trig_mode == 1), included by batotp_cuda.cu.
+// host_strict.inl — trig evaluated by the host (cfg.trig_mode == 2), included by batotp_cuda.cu.
 //
 // batotp's kinematics/dynamics call sin/cos/atan2 of the host libm (robot.cpp:130-136,
-// 196-199, 408-419; util.cpp:544-549, 574).  CUDA's FP64 sin/cos are accurate to 1-2 ulp but
-// not bit-identical to glibc, and the algorithm amplifies a 1-ulp table difference into a
-// different integer step count.  So in strict mode the trig-bearing POINT
-// functions are evaluated by this host layer with the host libm — exactly what the reference
-// does — between device stages; everything else (splines, sweeps, interpolation) stays on the
-// device.  trig_mode == 0 keeps these on the device (CUDA sincos) for throughput.
+// 196-199, 408-419; util.cpp:544-549, 574).  The strict mode of this library (trig_mode 1) runs a
+// bit-identical port of that libm's sin/cos on the device (k_trig.cuh).  On a host whose libm is NOT
+// the one ported (batotp_cuda_selftest_trig reports mismatches) trig_mode 2 keeps bit parity with
+// that host's reference build the slow way: the trig-bearing POINT functions are evaluated by this
+// host layer with the host libm between device stages; everything else (splines, sweeps,
+// interpolation) stays on the device.  In trig_mode 1 and 2 alike the atan2 of q2aa (util.cpp:574; the
+// axis-angle output rows of a UR-type robot) is applied here, to the final rows on their way out.
 namespace {
 
 // dynRR on the final grid (findDynModel, ba.cpp:905-914): Q/GD/GD2 rows -> A rows (point-major)
@@ -33,7 +34,7 @@ void host_dyn_rr_grid(batotp_ctx *h) {
     for (int i = 0; i < s.nPts; ++i) {
       const size_t off = ((size_t)i * B + b) * R;
       double a1[2], a2[2], a3[2], a4[2];
-      dyn_rr_point(&q[off], &d1[off], &d2[off], a1, a2, a3, a4);
+      dyn_rr_point(Trig{0}, &q[off], &d1[off], &d2[off], a1, a2, a3, a4);
       const double *aa[4] = {a1, a2, a3, a4};
       double *Ab = &A[((size_t)i * B + b) * 4 * MAXD];
       for (int k = 0; k < 4; ++k)
@@ -68,7 +69,7 @@ void host_dyn_rr_out(batotp_ctx *h) {
     for (int i = 0; i < s.nOver; ++i) {
       const size_t off = ((size_t)i * Bo + bl) * R;
       double a1[2], a2[2], a3[2], a4[2];
-      dyn_rr_point(&q[off], &d1[off], &d2[off], a1, a2, a3, a4);
+      dyn_rr_point(Trig{0}, &q[off], &d1[off], &d2[off], a1, a2, a3, a4);
       for (int j = 0; j < 2; ++j) T[((size_t)i * Bo + bl) * MAXD + j] = a2[j] + a3[j] + a4[j];
     }
   }

@@ -7,6 +7,7 @@
 // All row arrays are point-major [point][trajectory][row] (ba_dev.cuh), accessed through RV views.
 #pragma once
 #include "ba_dev.cuh"
+#include "k_trig.cuh"
 
 // ----------------------------------------------------------------------------- spline primitives
 // Thomas elimination factors depend only on the row index, so they are tabulated once on the
@@ -424,13 +425,13 @@ __global__ void k_in_decim_fix(WSP) {
 struct Pmat {
   double p[3][3];
 };
-__host__ __device__ inline void fk_kuka_point(const double *th, double *xyz) {
+__host__ __device__ inline void fk_kuka_point(const Trig &tg, const double *th, double *xyz) {
   const double D2R = 3.14159265358979323846 / 180.0;
   double c[7], s[7];
   for (int k = 0; k < 7; ++k) {
     const double tk = D2R * th[k];
-    c[k] = cos(tk);
-    s[k] = sin(tk);
+    c[k] = tg.c(tk);
+    s[k] = tg.s(tk);
   }
   const double c1 = c[0], c2 = c[1], c3 = c[2], c4 = c[3], c5 = c[4], c6 = c[5], c7 = c[6];
   const double s1 = s[0], s2 = s[1], s3 = s[2], s4 = s[3], s5 = s[4], s6 = s[5], s7 = s[6];
@@ -454,12 +455,12 @@ __host__ __device__ inline void fk_kuka_point(const double *th, double *xyz) {
   xyz[1] = y2 + (Q[1][0] * tool[0] + Q[1][1] * tool[1] + Q[1][2] * tool[2]);
   xyz[2] = z2 + (Q[2][0] * tool[0] + Q[2][1] * tool[1] + Q[2][2] * tool[2]);
 }
-__host__ __device__ inline void fk_rr_point(const double *th, double *xy) {
+__host__ __device__ inline void fk_rr_point(const Trig &tg, const double *th, double *xy) {
   const double D2R = 3.14159265358979323846 / 180.0;
   const double a1 = .4, a2 = .6;
   const double th1 = D2R * th[0], th2 = D2R * th[1];
-  xy[0] = a1 * cos(th1) + a2 * cos(th1 + th2);
-  xy[1] = a1 * sin(th1) + a2 * sin(th1 + th2);
+  xy[0] = a1 * tg.c(th1) + a2 * tg.c(th1 + th2);
+  xy[1] = a1 * tg.s(th1) + a2 * tg.s(th1 + th2);
 }
 __host__ __device__ inline void ik_cspr_point(const Pmat &pm, const double *xyz, double *rho) {
   for (int k = 0; k < 3; ++k) {
@@ -483,10 +484,10 @@ __global__ void k_pointfn(WSP, double *base, int b0, int mode, int useOver, Pmat
     double th[MAXD], xyz[3];
     for (int j = 0; j < J; ++j) th[j] = r0[j];
     if (CFG.c.robot_type == BATOTP_KUKA) {
-      fk_kuka_point(th, xyz);
+      fk_kuka_point(Trig{CFG.trigDev}, th, xyz);
       for (int q = 0; q < 3; ++q) r0[J + q] = xyz[q];
     } else if (CFG.c.robot_type == BATOTP_RR) {
-      fk_rr_point(th, xyz);
+      fk_rr_point(Trig{CFG.trigDev}, th, xyz);
       r0[J + 0] = xyz[0];
       r0[J + 1] = xyz[1];
     }
@@ -503,14 +504,14 @@ __global__ void k_pointfn(WSP, double *base, int b0, int mode, int useOver, Pmat
 }
 
 // ba.cpp:327-368 aa2qVect (sequential sign continuity) (T);  util.cpp:534-554 aa2q
-__host__ __device__ inline void aa2q_dev(const double aa[3], double q[4]) {
+__host__ __device__ inline void aa2q_dev(const Trig &tg, const double aa[3], double q[4]) {
   const double theta = sqrt(aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2]);
   if (theta < 1e-6) {
     q[0] = 1.0;
     q[1] = q[2] = q[3] = 0.0;
   } else {
-    const double sh = sin(0.5 * theta);
-    q[0] = cos(0.5 * theta);
+    const double sh = tg.s(0.5 * theta);
+    q[0] = tg.c(0.5 * theta);
     for (int i = 0; i < 3; ++i) q[i + 1] = aa[i] * sh / theta;
   }
 }
@@ -522,13 +523,14 @@ __global__ void k_aa2q(WSP) {
   const int J = CFG.J;
   const RV r3 = rowv(w.P, w, b, J + 3), r4 = rowv(w.P, w, b, J + 4), r5 = rowv(w.P, w, b, J + 5),
            r6 = rowv(w.P, w, b, J + 6);
+  const Trig tg{CFG.trigDev};
   double aa[3] = {r3[0], r4[0], r5[0]}, q[4], qprev[4];
-  aa2q_dev(aa, qprev);
+  aa2q_dev(tg, aa, qprev);
   for (int i = 0; i < s.nPts; ++i) {
     aa[0] = r3[i];
     aa[1] = r4[i];
     aa[2] = r5[i];
-    aa2q_dev(aa, q);
+    aa2q_dev(tg, aa, q);
     double qdir = 0;
     for (int j = 0; j < 4; ++j) qdir += q[j] * qprev[j];
     if (qdir < 0.0)

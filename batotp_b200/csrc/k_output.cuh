@@ -52,20 +52,21 @@ __host__ __device__ inline void lu3_solve(const double A[3][3], const double b[3
 }
 
 // robot.cpp:377-431 at one point (theta in degrees; thetaD/thetaD2 are s- or t-derivatives)
-__host__ __device__ inline void dyn_rr_point(const double th[2], const double thD[2], const double thD2[2],
-                                             double a1[2], double a2[2], double a3[2], double a4[2]) {
+__host__ __device__ inline void dyn_rr_point(const Trig &tg, const double th[2], const double thD[2],
+                                             const double thD2[2], double a1[2], double a2[2], double a3[2],
+                                             double a4[2]) {
   const double D2R = 3.14159265358979323846 / 180.0, g = 9.81;
   const double A1 = .4, A2 = .6, m1 = 4, m2 = 8;
   const double th1 = D2R * th[0], th2 = D2R * th[1];
   const double dth1 = D2R * thD[0], dth2 = D2R * thD[1];
   const double ddth1 = D2R * thD2[0], ddth2 = D2R * thD2[1];
-  const double c1 = cos(th1), c2 = cos(th2), c12 = cos(th1 + th2);
+  const double c1 = tg.c(th1), c2 = tg.c(th2), c12 = tg.c(th1 + th2);
   const double A11 = .25 * m1 * A1 * A1 + m2 * (A1 * A1 + .25 * A2 * A2 + A1 * A2 * c2);
   const double A12 = .5 * m2 * (.5 * A2 * A2 + A1 * A2 * c2);
   const double A22 = .25 * m2 * A2 * A2;
   a1[0] = A11 * dth1 + A12 * dth2;
   a1[1] = A12 * dth1 + A22 * dth2;
-  const double ccFact = m2 * A1 * A2 * sin(th2);
+  const double ccFact = m2 * A1 * A2 * tg.s(th2);
   a2[0] = A11 * ddth1 + A12 * ddth2 - ccFact * dth2 * (dth1 + .5 * dth2);
   a2[1] = A12 * ddth1 + A22 * ddth2 - .5 * ccFact * dth1 * dth1;
   a3[0] = 10 * dth1;
@@ -115,7 +116,7 @@ __global__ void k_dyn_grid(WSP, Pmat pm, int npts, int nb) {
       d1[q] = g1[q];
       d2[q] = g2[q];
     }
-    dyn_rr_point(th, d1, d2, a[0], a[1], a[2], a[3]);
+    dyn_rr_point(Trig{CFG.trigDev}, th, d1, d2, a[0], a[1], a[2], a[3]);
   }
   double *Ab = w.A + ((size_t)i * w.B + b) * 4 * MAXD;
   for (int k = 0; k < 4; ++k)
@@ -406,7 +407,7 @@ __global__ void k_out_trq(WSP, Pmat pm, int npts, int nb) {
       d1[q] = od[q];
       d2[q] = od2[q];
     }
-    dyn_rr_point(th, d1, d2, a1, a2, a3, a4);
+    dyn_rr_point(Trig{CFG.trigDev}, th, d1, d2, a1, a2, a3, a4);
     for (int q = 0; q < 2; ++q) trq[q] = a2[q] + a3[q] + a4[q];
   }
 }

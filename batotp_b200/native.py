@@ -73,6 +73,9 @@ def load(path: Optional[str] = None):
     L.batotp_cuda_fp64_peak.argtypes = [C.c_void_p, _dp, _dp]
     L.batotp_cuda_selftest_div.argtypes = [C.c_void_p, C.c_ulonglong, C.c_longlong, C.POINTER(C.c_longlong),
                                            C.POINTER(C.c_longlong)]
+    L.batotp_cuda_selftest_trig.argtypes = [C.c_void_p, C.c_ulonglong, C.c_longlong, C.POINTER(C.c_longlong),
+                                            C.POINTER(C.c_int)]
+    L.batotp_cuda_selftest_bisect.argtypes = [C.c_void_p, C.c_ulonglong, C.c_longlong, C.POINTER(C.c_longlong)]
     L.batotp_cuda_stats_reset.argtypes = [C.c_void_p]
     L.batotp_cuda_timer.argtypes = [C.c_void_p, C.c_int, _dp]
     L.batotp_cuda_set_profile.argtypes = [C.c_void_p, C.c_int]
@@ -241,6 +244,19 @@ class Context:
         if self.L.batotp_cuda_selftest_div(self.h, seed, n, C.byref(bad), C.byref(fast)) != 0:
             self._err('batotp_cuda_selftest_div')
         return bad.value, fast.value
+
+    def selftest_bisect(self, seed: int, n: int) -> int:
+        bad = C.c_longlong(0)
+        if self.L.batotp_cuda_selftest_bisect(self.h, seed, n, C.byref(bad)) != 0:
+            self._err('batotp_cuda_selftest_bisect')
+        return bad.value
+
+    def selftest_trig(self, seed: int, n: int):
+        """-> (mismatches against the host libm's sin/cos, arithmetic variant: 1 plain, 3 fused multiply-adds)"""
+        bad, var = C.c_longlong(0), C.c_int(0)
+        if self.L.batotp_cuda_selftest_trig(self.h, seed, n, C.byref(bad), C.byref(var)) != 0:
+            self._err('batotp_cuda_selftest_trig')
+        return bad.value, var.value
 
     def set_profile(self, on: bool):
         self.L.batotp_cuda_set_profile(self.h, int(on))

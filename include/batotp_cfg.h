@@ -47,9 +47,15 @@ typedef struct batotp_cfg {
   int is_par2ser;        /* _isPar2Ser           ba.h:302 */
   int is_interp_only;    /* _isInterpOnly        ba.h:306 (re-sample the path at outRes only, ba.cpp:139-159; needs joint rows) */
   int is_auto_integ_res; /* _isAutoIntegRes      ba.h:309 (batest forces 0, test/main.cpp:53) */
-  int trig_mode;         /* 0: kinematics/dynamics trig evaluated on the device (CUDA sincos);
-                            1: strict parity — the host layer evaluates the trig-bearing point
-                               functions with the host libm, as the reference does */
+  int trig_mode;         /* sin/cos of the kinematics / dynamics point functions (robot.cpp:130-136, 196-199, 408-419,
+                            util.cpp:544-549), all evaluated on the device unless 2:
+                            0: CUDA's sin/cos (1-2 ulp: results within the bisection tolerance, not bit-identical);
+                            1: strict parity — a bit-identical device port of the host libm's sin/cos
+                               (glibc 2.39 x86-64; batotp_cuda_selftest_trig verifies it against the running host);
+                            2: strict parity the slow way — the host evaluates those point functions with its own
+                               libm between device stages (for a host whose libm is not the one ported).
+                            In modes 1 and 2 the atan2 of the axis-angle output rows (util.cpp:574) is applied by
+                            the host to the final rows */
   int reserved_i[11];
   /* ---- doubles ---- */
   double jnt_vel_max[BATOTP_MAX_DOF]; /* _JntVelMax */

@@ -83,6 +83,17 @@ int batotp_cuda_fp64_peak(batotp_handle h, double *tflops_fma, double *tflops_no
 int batotp_cuda_selftest_div(batotp_handle h, unsigned long long seed, long long n, long long *mismatches,
                              long long *fast_path_taken);
 
+/* device self-test of the sweep kernel's branch-free bisection step (Bisect::step_any, k_sweep.cuh) against the
+ * reference-shaped control flow of ba.cpp:1270-1321 on n random feasibility thresholds; mismatches must be 0 */
+int batotp_cuda_selftest_bisect(batotp_handle h, unsigned long long seed, long long n, long long *mismatches);
+/* device self-test of the strict trigonometry (cfg.trig_mode 1): the device port of the host libm's sin / cos
+ * (robot.cpp:130-136, 196-199, 408-419 and util.cpp:544-549 call them) against the libm of the host this process
+ * runs on, at n pseudo-random arguments over the working range and beyond; reports bitwise mismatches (must be 0
+ * for trig_mode 1 to reproduce the reference on this host; otherwise use trig_mode 2) and the arithmetic variant
+ * in use (1: products and sums rounded separately, 3: fused multiply-adds, as glibc selects on an FMA+AVX2 CPU) */
+int batotp_cuda_selftest_trig(batotp_handle h, unsigned long long seed, long long n, long long *mismatches,
+                              int *variant);
+
 /* ---- batch input: what BA::loadTrajectoryData leaves in Traj (ba.cpp:2206-2461) -------- */
 typedef struct batotp_batch_in {
   int B;                  /* trajectories */

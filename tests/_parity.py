@@ -42,6 +42,31 @@ def load_stock(name):
     return cfg, tres, th, ca, ts
 
 
+def variant_config(name, dst_dir, **lines):
+    """Writes a copy of a stock config.dat with some option lines replaced (the option name as it appears in the
+    file's comment, e.g. inputDecimFact=3) into dst_dir and returns its path; the path file stays in the stock
+    folder (pass that as the input folder)."""
+    src = os.path.join(GOLD, "stock", name, "config.dat")
+    out = []
+    left = dict(lines)
+    for ln in open(src).read().splitlines():
+        for k in list(left):
+            if "// " + k in ln:
+                ln = "%s // %s" % (left.pop(k), k)
+        out.append(ln)
+    assert not left, "options not found: %s" % list(left)
+    dst = os.path.join(str(dst_dir), "config_%s.dat" % name)
+    open(dst, "w").write("\n".join(out) + "\n")
+    return dst
+
+
+def load_stock_variant(name, dst_dir, **lines):
+    """load_stock with some options of the stock config replaced."""
+    cfg, tres, th, ca, ts = load_stock(name)
+    cfg2, _ = read_config(variant_config(name, dst_dir, **lines))
+    return cfg2, tres, th, ca, ts
+
+
 def load_synth(name, first, count):
     """-> (cfg, tres, theta or None, cart or None)"""
     cfg, _ = read_config(os.path.join(GOLD, "synthetic", name + "_config.dat"))
@@ -77,6 +102,7 @@ class OracleRun:
         self.J = cfg.n_joints
         self.n_rev, self.n_fwd = int(o.scalar("nRev")), int(o.scalar("nFwd"))
         self.t_total = o.scalar("tTotalTraj")
+        self.s_last_sec = o.scalar("sLastSec")
         self.ok = self.rc == 0
         if self.ok:
             self.n_out = int(o.scalar("nPts"))
@@ -117,6 +143,8 @@ def compare(cfg, res, b, orc: OracleRun, check_hist=True):
         msgs.append("steps rev %d/%d fwd %d/%d" % (res.n_rev[b], orc.n_rev, res.n_fwd[b], orc.n_fwd))
     if res.t_total[b] != orc.t_total:
         msgs.append("tTotalTraj %r vs %r" % (res.t_total[b], orc.t_total))
+    if res.s_last_sec[b] != orc.s_last_sec:
+        msgs.append("sLastSec %r vs %r" % (res.s_last_sec[b], orc.s_last_sec))
     if res.n_out[b] != orc.n_out:
         msgs.append("n_out %d vs %d" % (res.n_out[b], orc.n_out))
         return msgs

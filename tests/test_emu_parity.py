@@ -186,11 +186,7 @@ def test_branch_free_bracket_update_equals_the_reference_shaped_one(ctx):
     """Bisect::step_any (one straight-line pass for every verification of the sweep kernel) against Bisect::step
     (the shape of ba.cpp:1270-1321) on random feasibility thresholds, including thresholds exactly at a
     candidate, zero / negative thresholds (bracket collapse, 100-pass limit) and non-positive start values."""
-    import ctypes as C
-    f = ctx.L.batotp_emu_bisect_selftest
-    f.argtypes = [C.c_ulonglong, C.c_longlong]
-    f.restype = C.c_longlong
-    assert f(12345, 400000) == 0
+    assert ctx.selftest_bisect(12345, 400000) == 0
 
 
 def test_step_capacity_is_bounded(ctx):
@@ -380,3 +376,51 @@ def test_results_into_device_resident_buffers(ctx):
     for nm in ("status", "n_rev", "n_fwd", "n_out", "n_cart_out", "n_grid", "t_total", "t_rev", "s_last_sec",
                "out_sres", "theta_out", "hist", "flags"):
         assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
+
+
+@pytest.mark.parametrize("name,decim,window", [("GEN7DOF", 3, 1), ("GEN7DOF", 2, 4), ("RR", 3, 3), ("UR5", 1, 3),
+                                               ("UR5", 3, 3), ("CSPR3DOF", 3, 3), ("KUKA-LWR-IV", 2, 4)])
+def test_input_decimation_and_smoothing(ctx, name, decim, window, tmp_path):
+    """inputDecimFact / smoothWindow (ba.cpp:195-242, quirk Q6) on the device: k_in_smooth_decimate + k_in_decim_fix
+    against the oracle (which tests/test_oracle_vs_reference.py pins to the unmodified reference for these options)."""
+    cfg, tres, th, ca, ts = P.load_stock_variant(name, tmp_path, inputDecimFact=decim, smoothWindow=window)
+    res = P.run_device(ctx, cfg, tres, th, ca, ts)
+    orc = P.OracleRun(cfg, tres, None if th is None else th[0], None if ca is None else ca[0],
+                      None if ts is None else ts[0])
+    assert orc.ok and res.status[0] & native.ST_FATAL_MASK == 0
+    assert P.compare(cfg, res, 0, orc) == []
+
+
+def test_strict_trig_port_reproduces_the_host_libm(ctx):
+    """cfg.trig_mode 1: sin / cos of the point functions are a port of the host libm's algorithm (k_trig.cuh).
+    The host build of the same functions against this machine's libm, in the arithmetic glibc selected here;
+    the other arithmetic is checked in a child process started with glibc's FMA variants switched off."""
+    import os
+    import subprocess
+    import sys
+    bad, variant = ctx.selftest_trig(2026, 3_000_000)
+    assert bad == 0 and variant in (1, 3)
+    code = ("import sys; sys.path.insert(0, %r); import __graft_entry__ as g; from batotp_b200 import native; "
+            "c = native.Context(0, g.build_emu()); print(c.selftest_trig(11, 1500000))" % P.HERE.rsplit("/", 1)[0])
+    env = dict(os.environ, GLIBC_TUNABLES="glibc.cpu.hwcaps=-FMA,-AVX2", BATOTP_TRIG_VARIANT="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.strip().splitlines()[-1] == "(0, 1)"
+    if variant == 3:  # the check bites: the fused port against the unfused libm differs
+        env["BATOTP_TRIG_VARIANT"] = "3"
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and out.stdout.strip().splitlines()[-1] != "(0, 3)"
+
+
+@pytest.mark.parametrize("name", ["RR", "KUKA-LWR-IV", "UR5"])
+def test_host_evaluated_trig_mode_gives_the_same_bytes(ctx, name):
+    """trig_mode 2 (the host evaluates the trig-bearing point functions with its libm between device stages) and
+    trig_mode 1 (the device port) are both strict: same files as the reference."""
+    cfg, tres, th, ca, ts = P.load_stock(name)
+    d = P.GOLD + "/stock/" + name
+    for mode in (1, 2):
+        c2 = cfg.copy()
+        c2.trig_mode = mode
+        res = P.run_device(ctx, c2, tres, th, ca, ts)
+        assert P.device_traj_out_bytes(c2, res, 0) == open(d + "/ref_traj_out.dat", "rb").read(), mode
+        assert P.device_s_sdot_bytes(res, 0) == open(d + "/ref_s-sdot.dat", "rb").read(), mode

@@ -257,3 +257,210 @@ def test_limit_regimes_match_oracle(ctx, acc, vel, integ):
     for b in range(0, B, 3):
         orc = P.OracleRun(cfg, tres, th[b], None)
         assert P.compare(cfg, res, b, orc) == [], b
+
+
+# ----------------------------------------------------------------------------- round 2
+def _oracle_batch(cfg, tres, th, ca, out_cap):
+    """orc_batch_run on all host cores -> (t_total, n_rev, n_fwd, n_out, status, theta_out[B,J,out_cap])."""
+    import ctypes as C
+    import os
+    from _oracle import orc_lib
+    ref = th if th is not None else ca
+    B = ref.shape[0]
+    tt = np.zeros(B)
+    nr, nf, no, st = (np.zeros(B, np.int32) for _ in range(4))
+    rows = np.zeros((B, cfg.n_joints, out_cap), np.float32)
+    fp, dp, ip = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int)
+    orc_lib().orc_batch_run(C.byref(cfg), B, ref.shape[2], tres, None if th is None else th.ctypes.data_as(fp),
+                            None if ca is None else ca.ctypes.data_as(fp), os.cpu_count() or 1,
+                            tt.ctypes.data_as(dp), nr.ctypes.data_as(ip), nf.ctypes.data_as(ip),
+                            no.ctypes.data_as(ip), st.ctypes.data_as(ip), rows.ctypes.data_as(fp), out_cap)
+    return tt, nr, nf, no, st, rows
+
+
+def test_strict_trig_port_reproduces_the_host_libm_on_1e9_arguments(ctx):
+    """cfg.trig_mode 1: the device's sin / cos (k_trig.cuh, a port of the host libm's algorithm in the arithmetic
+    glibc selected on this machine) against this host's sin / cos: 10^9 arguments = 2*10^9 values, bit for bit."""
+    bad, variant = ctx.selftest_trig(20261017, 1_000_000_000)
+    assert variant in (1, 3)
+    assert bad == 0
+
+
+def test_branch_free_bracket_update_on_the_device(ctx):
+    assert ctx.selftest_bisect(99, 50_000_000) == 0
+
+
+def test_kuka_4096_matches_oracle_bit_for_bit(ctx):
+    """BASELINE configs[2] at its stated size: 4096 synthetic KUKA-LWR-IV paths (Cartesian velocity / acceleration
+    limits through the forward kinematics, ~18 600 RK steps per sweep), strict trigonometry ON THE DEVICE, against
+    the oracle restatement on the host cores: switching counts, total time and every float32 output sample."""
+    B, slab = 4096, 1024
+    cfg, tres, th, _ = P.load_synth("KUKA", 0, B)
+    assert cfg.trig_mode == 1
+    scal = native.BatchResult(B, cfg.n_joints, cfg.n_cart, 0, 0, False, want_rows=False, want_hist=False)
+    ctx.optimize_batch(cfg, ctx.make_in(theta=th, tres=tres), scal)
+    assert (scal.status & native.ST_FATAL_MASK == 0).all()
+    out_cap = int(scal.n_out.max()) + 8
+    for at in range(0, B, slab):
+        res = native.BatchResult(slab, cfg.n_joints, cfg.n_cart, out_cap, 0, False, want_rows=True, want_hist=False)
+        ctx.optimize_batch(cfg, ctx.make_in(theta=th[at:at + slab], tres=tres), res)
+        tt, nr, nf, no, st, rows = _oracle_batch(cfg, tres, th[at:at + slab], None, out_cap)
+        assert (st == 0).all()
+        assert np.array_equal(res.n_rev, nr) and np.array_equal(res.n_fwd, nf) and np.array_equal(res.n_out, no)
+        assert np.array_equal(res.t_total, tt) and np.array_equal(res.t_total, scal.t_total[at:at + slab])
+        assert np.array_equal(res.theta_out, rows)
+
+
+def test_cspr_8192_matches_oracle_bit_for_bit(ctx):
+    """BASELINE configs[3] (an eighth of its stated size; bench.py --workload cspr runs all 65 536): 8192 synthetic
+    CSPR3DOF paths inside the static workspace (cable-tension limits through dynCSPR3DOF + setA + Par2Ser LU,
+    Cartesian-driven, ~4300-knot grids) against the oracle on the host cores, bit for bit; plus the raw candidate
+    family, where some paths leave the workspace (failed bisections, crawling sweeps): same statuses / counts for
+    everything the step ceiling lets finish."""
+    B = 8192
+    cfg, tres, _, ca = P.load_synth("CSPR3DOF", 100000, B)
+    scal = native.BatchResult(B, cfg.n_joints, cfg.n_cart, 0, 0, True, want_rows=False, want_hist=False)
+    ctx.optimize_batch(cfg, ctx.make_in(cart=ca, tres=tres), scal)
+    assert (scal.status & native.ST_FATAL_MASK == 0).all()
+    assert (scal.status & native.ST_BISECT_FAIL == 0).all()  # inside the static workspace no bisection fails
+    out_cap = int(scal.n_out.max()) + 8
+    res = native.BatchResult(B, cfg.n_joints, cfg.n_cart, out_cap, 0, True, want_rows=True, want_hist=False)
+    ctx.optimize_batch(cfg, ctx.make_in(cart=ca, tres=tres), res)
+    tt, nr, nf, no, st, rows = _oracle_batch(cfg, tres, None, ca, out_cap)
+    assert (st == 0).all()
+    assert np.array_equal(res.n_rev, nr) and np.array_equal(res.n_fwd, nf) and np.array_equal(res.n_out, no)
+    assert np.array_equal(res.t_total, tt)
+    assert np.array_equal(res.theta_out, rows)
+    # tensions within the limits of the config ([1, 12] N, with the float32 cast's slack)
+    live = np.arange(out_cap)[None, None, :] < res.n_out[:, None, None]
+    assert res.trq_out[live.repeat(3, 1)].min() > 0.99 and res.trq_out[live.repeat(3, 1)].max() < 12.01
+
+
+def test_ur5_fine_discretisation(ctx):
+    """BASELINE configs[1]: the UR5 path at fine discretisation (integRes 0.008 -> 0.001, norm resolutions / 10,
+    outRes 0.001: ten times the grid and the steps), joint + Cartesian limits, axis-angle rows: bit for bit."""
+    cfg, tres, th, ca, ts = P.load_stock("UR5")
+    cfg = cfg.copy()
+    cfg.integ_res = 0.001
+    cfg.theta_norm_res, cfg.theta_norm_res2 = cfg.theta_norm_res / 10, cfg.theta_norm_res2 / 10
+    cfg.cart_norm_res, cfg.cart_norm_res2 = cfg.cart_norm_res / 10, cfg.cart_norm_res2 / 10
+    cfg.out_res = 0.001
+    res = P.run_device(ctx, cfg, tres, th, ca, ts, out_cap=65536, hist_cap=65536)
+    assert res.status[0] & native.ST_FATAL_MASK == 0 and res.n_fwd[0] > 5000
+    orc = P.OracleRun(cfg, tres, th[0], ca[0], ts[0])
+    assert orc.ok and P.compare(cfg, res, 0, orc) == []
+
+
+@pytest.mark.parametrize("name,max_step_diff,max_deg", [("RR", 8, 2.0), ("UR5", 8, 2.0)])
+def test_cuda_trig_mode_on_rr_and_ur5(ctx, name, max_step_diff, max_deg):
+    """trig_mode 0: CUDA's own sin / cos in fwdKinRR + dynRR (RR) and aa2q / q2aa (UR5).  Not bit-identical to
+    the reference; stated tolerance: switching counts within 8 RK steps, total time within 2e-3 relative,
+    theta(t) within 2 degrees at a fixed output index (a shift of a few steps at some tens of deg/s)."""
+    cfg, tres, th, ca, ts = P.load_stock(name)
+    strict = P.run_device(ctx, cfg, tres, th, ca, ts)
+    c0 = cfg.copy()
+    c0.trig_mode = 0
+    fast = P.run_device(ctx, c0, tres, th, ca, ts)
+    assert fast.status[0] & native.ST_FATAL_MASK == 0
+    assert abs(int(fast.n_fwd[0]) - int(strict.n_fwd[0])) <= max_step_diff
+    assert abs(int(fast.n_rev[0]) - int(strict.n_rev[0])) <= max_step_diff
+    assert abs(fast.t_total[0] - strict.t_total[0]) / strict.t_total[0] < 2e-3
+    n = min(int(fast.n_out[0]), int(strict.n_out[0]))
+    assert np.abs(fast.theta_out[0, :, :n] - strict.theta_out[0, :, :n]).max() < max_deg
+    if fast.cart_out is not None:
+        nc = min(int(fast.n_cart_out[0]), int(strict.n_cart_out[0]))
+        assert np.abs(fast.cart_out[0, :3, :nc] - strict.cart_out[0, :3, :nc]).max() < 0.02  # metres
+
+
+@pytest.mark.parametrize("name", ["RR", "KUKA-LWR-IV", "UR5"])
+def test_host_evaluated_trig_mode_gives_the_same_bytes(ctx, name):
+    cfg, tres, th, ca, ts = P.load_stock(name)
+    d = P.GOLD + "/stock/" + name
+    c2 = cfg.copy()
+    c2.trig_mode = 2
+    res = P.run_device(ctx, c2, tres, th, ca, ts)
+    assert P.device_traj_out_bytes(c2, res, 0) == open(d + "/ref_traj_out.dat", "rb").read()
+    assert P.device_s_sdot_bytes(res, 0) == open(d + "/ref_s-sdot.dat", "rb").read()
+
+
+@pytest.mark.parametrize("name,decim,window", [("GEN7DOF", 3, 1), ("GEN7DOF", 2, 4), ("RR", 3, 3), ("UR5", 1, 3),
+                                               ("UR5", 3, 3), ("CSPR3DOF", 3, 3), ("KUKA-LWR-IV", 2, 4)])
+def test_input_decimation_and_smoothing(ctx, name, decim, window, tmp_path):
+    cfg, tres, th, ca, ts = P.load_stock_variant(name, tmp_path, inputDecimFact=decim, smoothWindow=window)
+    res = P.run_device(ctx, cfg, tres, th, ca, ts)
+    orc = P.OracleRun(cfg, tres, None if th is None else th[0], None if ca is None else ca[0],
+                      None if ts is None else ts[0])
+    assert orc.ok and res.status[0] & native.ST_FATAL_MASK == 0
+    assert P.compare(cfg, res, 0, orc) == []
+
+
+def test_results_into_device_resident_buffers(ctx):
+    """batotp_batch_out.on_device: scalars, rows, histories and flags land in caller-owned HBM."""
+    import torch
+    B, cap = 700, 4096
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 7000, B)
+    ctx.set_chunk(256)
+    ctx.set_out_chunk(100)
+    try:
+        a = P.run_device(ctx, cfg, tres, th, None, out_cap=cap, hist_cap=cap)
+        dev = {}
+        b = native.BatchResult(B, cfg.n_joints, cfg.n_cart, cap, cap, False)
+        for nm in ("status", "n_rev", "n_fwd", "n_out", "n_cart_out", "n_grid", "t_total", "t_rev", "s_last_sec",
+                   "out_sres", "theta_out", "hist", "flags"):
+            host = getattr(b, nm)
+            dev[nm] = torch.zeros(host.shape, dtype={"int32": torch.int32, "float64": torch.float64,
+                                                     "float32": torch.float32, "uint8": torch.uint8}[str(host.dtype)],
+                                  device="cuda:0")
+            ptr = dev[nm].data_ptr()
+            if nm in ("theta_out", "hist", "flags"):
+                setattr(b.c, nm, ptr)
+            else:
+                import ctypes as C
+                setattr(b.c, nm, C.cast(ptr, type(getattr(b.c, nm))))
+        b.c.cart_out = None
+        b.c.on_device = 1
+        ctx.optimize_batch(cfg, ctx.make_in(th, None, tres), b)
+        torch.cuda.synchronize()
+    finally:
+        ctx.set_chunk(16384)
+        ctx.set_out_chunk(8192)
+    for nm, t in dev.items():
+        assert np.array_equal(getattr(a, nm), t.cpu().numpy()), nm
+
+
+def test_stragglers_and_two_contexts(ctx):
+    """Stragglers (a few trajectories outgrowing the step capacity are re-run after the batch) and two contexts
+    with different configurations driven in an interleaved order, on the device."""
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 100, 300)
+    ctx.set_step_hint(0)
+    a = P.run_device(ctx, cfg, tres, th, None, out_cap=4096, hist_cap=4096)
+    steps = np.sort(np.maximum(a.n_rev, a.n_fwd))
+    try:
+        ctx.set_step_hint(int(steps[-4]))
+        ctx.stats_reset()
+        b = P.run_device(ctx, cfg, tres, th, None, out_cap=4096, hist_cap=4096)
+        st = ctx.stats()
+    finally:
+        ctx.set_step_hint(0)
+    assert st["sweep_launches"] == 2 and st["trajectories"] == 300
+    for nm in ("status", "n_rev", "n_fwd", "n_out", "t_total", "s_last_sec", "theta_out", "hist", "flags"):
+        assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
+    other = native.Context(0)
+    try:
+        cfgB, tresB, thB, _ = P.load_synth("KUKA", 0, 2)
+        ctx.load(cfg, ctx.make_in(th[:4], None, tres))
+        ctx.interp_input()
+        other.load(cfgB, other.make_in(thB, None, tresB))
+        other.interp_input()
+        ctx.sweeps()
+        other.sweeps()
+        ctx.interp_output()
+        other.interp_output()
+        ra = ctx.fetch(native.BatchResult(4, cfg.n_joints, cfg.n_cart, 8192, 8192, False))
+        rb = other.fetch(native.BatchResult(2, cfgB.n_joints, cfgB.n_cart, 32768, 32768, False))
+        for k in range(4):
+            assert P.compare(cfg, ra, k, P.OracleRun(cfg, tres, th[k], None)) == []
+        for k in range(2):
+            assert P.compare(cfgB, rb, k, P.OracleRun(cfgB, tresB, thB[k], None)) == []
+    finally:
+        other.close()
