@@ -21,6 +21,7 @@
 #include "../../include/batotp_cuda.h"
 #include "k_output.cuh"
 #include "k_sweep.cuh"
+#include "k_sweep_group.cuh"
 #include "k_mvc.cuh"
 
 #ifndef BATOTP_HOST_EMU
@@ -116,6 +117,9 @@ inline void g_check_launch() {}
 #endif
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+#ifndef SWEEP_GROUP_MAX_B
+#define SWEEP_GROUP_MAX_B 16384  // chunks up to this size take the group-per-trajectory sweep kernel (automatic mode)
+#endif
 // bytes the device can still hand out (host emulation: "plenty")
 inline size_t g_free_bytes() {
 #ifndef BATOTP_HOST_EMU
@@ -176,6 +180,7 @@ struct batotp_ctx {
   // batotp_cuda_optimize_batch (a sub-chunk then leaves in one contiguous copy), 0 = the device capacities
   int rowPitch = 0, histPitch = 0, capRowPitch = 0, capHistPitch = 0;
   int maxSteps = 65536;           // largest RK-step capacity the automatic retries grow to (per sweep)
+  int sweepKernel = 0;            // 0 automatic (by chunk size), 1 one trajectory per lane (k_sweep), 2 a group of lanes per trajectory (k_sweep_group)
   int stepHint = 0;               // RK-step capacity a chunk starts with (0 = automatic: max(1024, 2 x grid points))
   // Thomas factor tables
   double *d_cN = nullptr;  // Thomas tables (ensure_tabs)
@@ -835,9 +840,65 @@ void launch_sweep(batotp_ctx *h) {
   h->sweepLaunches++;
 }
 
+template <int J, bool CART, bool TRQ>
+void launch_sweep_group(batotp_ctx *h) {
+  g_zero(h->w.queue, sizeof(int) * 4, h->stream);
+  constexpr int G = GroupShape<J, CART>::G;
+#ifndef BATOTP_HOST_EMU
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int perSm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_sweep_group<J, CART, TRQ>, SWG_NT, 0);
+  if (perSm < 1) perSm = 1;
+  int blocks = (int)std::min<long long>((long long)sms * perSm, ((long long)h->B * G + SWG_NT - 1) / SWG_NT);
+  if (blocks < 1) blocks = 1;
+  if (!h->evS0) {
+    CU_CHECK(cudaEventCreate(&h->evS0));
+    CU_CHECK(cudaEventCreate(&h->evS1));
+  }
+  CU_CHECK(cudaEventRecord(h->evS0, h->stream));
+#else
+  int blocks = 1;
+#endif
+  {
+    ProfScope ps_(h, "k_sweep_group");
+    BATOTP_LAUNCH_WARP((k_sweep_group<J, CART, TRQ>), dim3(blocks), dim3(SWG_NT), 0, h->stream, h->w);
+    g_check_launch();
+  }
+#ifndef BATOTP_HOST_EMU
+  CU_CHECK(cudaEventRecord(h->evS1, h->stream));
+  h->sweepPending = true;
+#endif
+  h->launches++;
+  h->sweepLaunches++;
+}
+
+// Which sweep kernel serves a chunk: one trajectory per lane (k_sweep.cuh: the fewest issue slots per trajectory,
+// the choice when the chunk fills the machine) or a group of lanes per trajectory (k_sweep_group.cuh: a quarter of the
+// latency per point, the choice when the latency of one trajectory bounds the launch).
+bool use_group_kernel(const batotp_ctx *h) {
+  if (h->sweepKernel == 1) return false;
+  if (h->sweepKernel == 2) return true;
+  return h->B <= SWEEP_GROUP_MAX_B;
+}
+
 int dispatch_sweep(batotp_ctx *h) {
   const DevCfg &c = h->cfg;
   const int key = c.J * 4 + (c.cartOn ? 2 : 0) + (c.trqOn ? 1 : 0);
+  if (use_group_kernel(h)) {
+    switch (key) {
+      case 7 * 4 + 0: launch_sweep_group<7, false, false>(h); return 0;
+      case 7 * 4 + 2: launch_sweep_group<7, true, false>(h); return 0;
+      case 6 * 4 + 2: launch_sweep_group<6, true, false>(h); return 0;
+      case 6 * 4 + 0: launch_sweep_group<6, false, false>(h); return 0;
+      case 2 * 4 + 3: launch_sweep_group<2, true, true>(h); return 0;
+      case 3 * 4 + 3: launch_sweep_group<3, true, true>(h); return 0;
+      case 3 * 4 + 2: launch_sweep_group<3, true, false>(h); return 0;
+      case 2 * 4 + 2: launch_sweep_group<2, true, false>(h); return 0;
+      default: break;  // no group instantiation: the per-lane kernel below reports what is missing
+    }
+  }
   switch (key) {
     case 7 * 4 + 0: launch_sweep<7, false, false>(h); return 0;  // GEN7DOF
     case 7 * 4 + 2: launch_sweep<7, true, false>(h); return 0;   // KUKA-LWR-IV
@@ -2289,6 +2350,7 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
           if (hp->stepHint != h->stepHint) hp->hwSc = 0;
           hp->stepHint = h->stepHint;
           hp->keepF64 = h->keepF64;
+          hp->sweepKernel = h->sweepKernel;
           hp->stragglers.clear();
           hp->stragglerSc = 0;
           hp->collectStragglers = true;
@@ -2460,6 +2522,13 @@ int batotp_cuda_get_f64(batotp_handle h, const char *name, int traj, int row, do
 int batotp_cuda_set_max_steps(batotp_handle h, int n) {
   if (!h || n < 1024) return -1;
   h->maxSteps = n;
+  return 0;
+}
+
+int batotp_cuda_set_sweep_kernel(batotp_handle h, int mode) {
+  if (!h || mode < 0 || mode > 2) return -1;
+  h->sweepKernel = mode;
+  if (h->helper) h->helper->sweepKernel = mode;
   return 0;
 }
 

@@ -66,6 +66,7 @@ def load(path: Optional[str] = None):
     L.batotp_cuda_set_max_steps.argtypes = [C.c_void_p, C.c_int]
     L.batotp_cuda_set_tail_overlap.argtypes = [C.c_void_p, C.c_int]
     L.batotp_cuda_set_step_hint.argtypes = [C.c_void_p, C.c_int]
+    L.batotp_cuda_set_sweep_kernel.argtypes = [C.c_void_p, C.c_int]
     L.batotp_cuda_launch_count.argtypes = [C.c_void_p]
     L.batotp_cuda_launch_count.restype = C.c_long
     L.batotp_cuda_stats.argtypes = [C.c_void_p, _dp, C.c_int]
@@ -215,6 +216,10 @@ class Context:
 
     def set_max_steps(self, n: int):
         self.L.batotp_cuda_set_max_steps(self.h, n)
+
+    def set_sweep_kernel(self, mode: int):
+        """0 automatic, 1 one trajectory per lane, 2 a group of lanes per trajectory."""
+        self.L.batotp_cuda_set_sweep_kernel(self.h, mode)
 
     def set_step_hint(self, n: int):
         self.L.batotp_cuda_set_step_hint(self.h, n)

@@ -49,6 +49,11 @@ int batotp_cuda_set_out_chunk(batotp_handle h, int n);
  * trajectory that needs more steps (the reference would run it until maxIntegTime, ba.cpp:1117-1122) keeps
  * BATOTP_ST_STEP_CAP and is reported as not optimised; n >= 1024 */
 int batotp_cuda_set_max_steps(batotp_handle h, int n);
+/* which sweep kernel serves a chunk.  0 (default) = by chunk size; 1 = one trajectory per lane (k_sweep.cuh: fewest
+ * issue slots per trajectory, for chunks that fill the device); 2 = a group of 8 (or 4) lanes per trajectory
+ * (k_sweep_group.cuh: a fraction of the latency per Runge-Kutta stage, for small batches and single paths).  Both
+ * produce the same bits. */
+int batotp_cuda_set_sweep_kernel(batotp_handle h, int mode);
 /* Runge-Kutta step capacity (per sweep) a chunk starts with; 0 (default) = automatic: max(1024, 2 x grid points),
  * then what earlier chunks of the same configuration needed.  Inside batotp_cuda_optimize_batch the few trajectories
  * of a chunk that outgrow the capacity ("stragglers", at most max(8, chunk/64)) are re-run together with a

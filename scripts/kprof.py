@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--trig", type=int, default=1)
     ap.add_argument("--max-steps", type=int, default=0)
     ap.add_argument("--skip-host", action="store_true")
+    ap.add_argument("--sweep-kernel", type=int, default=0, help="0 automatic, 1 lane per trajectory, 2 group per trajectory")
     a = ap.parse_args()
     import torch
     from batotp_b200 import native, synth
@@ -49,6 +50,7 @@ def main():
     if a.max_steps:
         ctx.set_max_steps(a.max_steps)
     ctx.set_out_chunk(a.out_chunk)
+    ctx.set_sweep_kernel(a.sweep_kernel)
     J = cfg.n_joints
     bi_dev = ctx.make_in(tres=tres, device_ptrs=dict(theta=None if is_cart else d_theta.data_ptr(),
                                                      cart=d_theta.data_ptr() if is_cart else None, B=B, n0_max=theta.shape[2]))

@@ -15,6 +15,10 @@ from batotp_b200 import native
 def ctx():
     import __graft_entry__ as g
     c = native.Context(0, g.build_emu())
+    # The library would pick the group-per-trajectory sweep kernel for batches this small; under the emulation its
+    # many shuffles cost a fibre switch each, so the suite runs the one-trajectory-per-lane kernel unless a test
+    # asks for the other one (test_group_sweep_kernel_*).
+    c.set_sweep_kernel(1)
     yield c
     c.close()
 
@@ -424,3 +428,41 @@ def test_host_evaluated_trig_mode_gives_the_same_bytes(ctx, name):
         res = P.run_device(ctx, c2, tres, th, ca, ts)
         assert P.device_traj_out_bytes(c2, res, 0) == open(d + "/ref_traj_out.dat", "rb").read(), mode
         assert P.device_s_sdot_bytes(res, 0) == open(d + "/ref_s-sdot.dat", "rb").read(), mode
+
+
+@pytest.mark.parametrize("name", ["GEN7DOF", "RR", "UR5", "CSPR3DOF"])
+def test_group_sweep_kernel_on_stock_folders(ctx, name):
+    """k_sweep_group.cuh (a group of 8 / 4 lanes per trajectory, per-joint work spread over the lanes, shuffle
+    reductions) gives the reference's files byte for byte, like the one-trajectory-per-lane kernel: joint limits
+    only (GEN7DOF), serial torque + Cartesian (RR, 4 lanes), Cartesian with quaternions (UR5), Par2Ser torque (CSPR)."""
+    cfg, tres, th, ca, ts = P.load_stock(name)
+    ctx.set_sweep_kernel(2)
+    try:
+        res = P.run_device(ctx, cfg, tres, th, ca, ts)
+    finally:
+        ctx.set_sweep_kernel(1)
+    d = P.GOLD + "/stock/" + name
+    assert P.device_traj_out_bytes(cfg, res, 0) == open(d + "/ref_traj_out.dat", "rb").read()
+    assert P.device_s_sdot_bytes(res, 0) == open(d + "/ref_s-sdot.dat", "rb").read()
+    orc = P.OracleRun(cfg, tres, None if th is None else th[0], None if ca is None else ca[0],
+                      None if ts is None else ts[0])
+    assert P.compare(cfg, res, 0, orc) == []  # switching flags and sLastSec included
+
+
+def test_group_sweep_kernel_on_a_ragged_batch(ctx):
+    """Several groups per warp, trajectories of different lengths, refills from the queue, a degenerate path."""
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 300, 9)
+    th = th.copy()
+    n0 = np.array([400, 400, 57, 400, 3, 400, 1, 400, 400], dtype=np.int32)
+    ctx.set_sweep_kernel(1)
+    a = P.run_device(ctx, cfg, tres, th, None, n0=n0, out_cap=4096, hist_cap=4096)
+    ctx.set_sweep_kernel(2)
+    try:
+        ctx.stats_reset()
+        b = P.run_device(ctx, cfg, tres, th, None, n0=n0, out_cap=4096, hist_cap=4096)
+        sb = ctx.stats()
+    finally:
+        ctx.set_sweep_kernel(1)
+    for nm in ("status", "n_rev", "n_fwd", "n_out", "t_total", "s_last_sec", "theta_out", "hist", "flags"):
+        assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
+    assert sb["verifies"] > 0 and P.compare(cfg, b, 3, P.OracleRun(cfg, tres, th[3], None)) == []
