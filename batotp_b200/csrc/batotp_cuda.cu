@@ -127,6 +127,9 @@ inline size_t g_free_bytes() {
   if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return (size_t)1 << 62;
   return fr;
 #else
+  // TEST-ONLY (host emulation): BATOTP_EMU_FREE_MB pretends the device has that much memory left, so that the
+  // CPU suite can walk the "chunk does not fit" paths
+  if (const char *e = getenv("BATOTP_EMU_FREE_MB")) return (size_t)atoll(e) << 20;
   return (size_t)1 << 62;
 #endif
 }
@@ -236,6 +239,13 @@ struct batotp_ctx {
   // measurement (bench.py): device time of the sweep kernel and whole-context event timer
   double sweepMs = 0;
   long sweepLaunches = 0;
+  // one record per sweep launch since the last reset: device ms, trajectories of the chunk, kernel (1 lane, 2 group)
+  struct SweepRec {
+    double ms;
+    int B, kernel;
+  };
+  std::vector<SweepRec> sweepLog;
+  int lastSweepKernel = 1;
   long long cntVerify = 0, cntSteps = 0, cntTraj = 0;
   // optional per-kernel device timing (batotp_cuda_set_profile): serialises every launch
   bool profile = false;
@@ -886,6 +896,7 @@ bool use_group_kernel(const batotp_ctx *h) {
 int dispatch_sweep(batotp_ctx *h) {
   const DevCfg &c = h->cfg;
   const int key = c.J * 4 + (c.cartOn ? 2 : 0) + (c.trqOn ? 1 : 0);
+  h->lastSweepKernel = use_group_kernel(h) ? 2 : 1;
   if (use_group_kernel(h)) {
     switch (key) {
       case 7 * 4 + 0: launch_sweep_group<7, false, false>(h); return 0;
@@ -1126,7 +1137,7 @@ int do_interp_only(batotp_ctx *h, bool haveN0) {
   const DevCfg &c = h->cfg;
   for (int attempt = 0; attempt < 4; ++attempt) {
     int Nc = std::max(std::max(h->hwNc, h->n0max + 8), h->w.Nc);
-    ensure_ws(h, std::max(h->B, h->capB), Nc, std::max(h->hwSc, 1024));
+    ensure_ws(h, h->B, Nc, std::max(h->hwSc, 1024));
     Ws &w = h->w;
     w.B = h->B;
     run_load_prepare(h, haveN0);
@@ -1154,7 +1165,7 @@ int do_interp_only(batotp_ctx *h, bool haveN0) {
     LAUNCH_TP(h, k_resample, w.Nc, h->B, w);
     LAUNCH_T(h, k_resample_commit, h->B, w);
     std::swap(w.P, w.Q);
-    ensure_out(h, std::max(h->B, h->capBo), mx + 8);
+    ensure_out(h, h->B, mx + 8);
     w.b0 = 0;
     w.Bo = h->B;
     LAUNCH_T(h, k_interp_only_finish, h->B, w);
@@ -1181,7 +1192,7 @@ int do_sweeps(batotp_ctx *h) {
 // interpOutputData for the sub-chunk [b0, b0+Bo) of the resident chunk
 void do_interp_output(batotp_ctx *h, int b0, int Bo) {
   const DevCfg &c = h->cfg;
-  ensure_out(h, std::max(Bo, h->capBo));
+  ensure_out(h, Bo);
   Ws &w = h->w;
   w.b0 = b0;
   w.Bo = Bo;
@@ -1670,10 +1681,21 @@ int batotp_cuda_stats(batotp_handle h, double *out, int n) {
   for (int i = 0; i < n && i < 6; ++i) out[i] = v[i];
   return 0;
 }
+int batotp_cuda_sweep_log(batotp_handle h, double *ms, int *n_traj, int *kernel, int cap) {
+  if (!h) return -1;
+  const int n = (int)h->sweepLog.size();
+  for (int i = 0; i < n && i < cap; ++i) {
+    if (ms) ms[i] = h->sweepLog[i].ms;
+    if (n_traj) n_traj[i] = h->sweepLog[i].B;
+    if (kernel) kernel[i] = h->sweepLog[i].kernel;
+  }
+  return n;
+}
 int batotp_cuda_stats_reset(batotp_handle h) {
   if (!h) return -1;
   h->sweepMs = 0;
   h->sweepLaunches = 0;
+  h->sweepLog.clear();
   h->cntVerify = h->cntSteps = h->cntTraj = 0;
   h->launches = 0;
   return 0;
@@ -1820,10 +1842,12 @@ static int load_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_batch
 // one chunk through interpInputData with capacity planning / retry
 static int chunk_interp_input(batotp_handle h, bool haveN0) {
   int Nc = std::max(h->hwNc, h->n0max + 8);
-  int Sc = std::max(h->hwSc, h->stepHint > 0 ? h->stepHint : std::max(1024, 2 * Nc));
   bool plan = (h->hwNc == 0);
   for (int attempt = 0; attempt < 8; ++attempt) {
-    ensure_ws(h, std::max(h->B, h->capB), Nc, Sc);
+    // the step capacity follows the grid the planning pass finds (a sweep takes about as many steps as the
+    // grid has points; twice that leaves room), or what earlier chunks needed
+    const int Sc = std::max(h->hwSc, h->stepHint > 0 ? h->stepHint : std::max(1024, 2 * Nc));
+    ensure_ws(h, h->B, Nc, Sc);
     h->w.B = h->B;
     const int need = do_interp_input(h, haveN0, plan);
     if (need > 0) {  // planning pass asked for more room
@@ -1856,6 +1880,7 @@ static int chunk_sweeps_output(batotp_handle h, bool haveN0) {
       float ms = 0;
       CU_CHECK(cudaEventElapsedTime(&ms, h->evS0, h->evS1));
       h->sweepMs += ms;
+      if (h->sweepLog.size() < 4096) h->sweepLog.push_back({(double)ms, h->B, h->lastSweepKernel});
       h->sweepPending = false;
     }
 #endif
@@ -1907,7 +1932,7 @@ static int chunk_sweeps_output(batotp_handle h, bool haveN0) {
     // grow the step capacity and redo the chunk from the start (the status word is sticky)
     const int Sc = h->w.Sc * 2;
     const int Nc = h->w.Nc;
-    ensure_ws(h, h->capB, Nc, Sc);
+    ensure_ws(h, h->B, Nc, Sc);
     h->w.B = h->B;
     const int need = do_interp_input(h, haveN0, false);
     (void)need;
@@ -2094,7 +2119,7 @@ static void process_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_b
         int k = 0;
         for (int b0 = 0; b0 < B; b0 += h->outChunk, ++k) {
           const int q = k & 1;
-          ensure_out(h, std::max(std::min(h->outChunk, B - b0), h->capBo));
+          ensure_out(h, std::min(h->outChunk, B - b0));
           if (k >= 2) g_stream_wait(h->stream, h->evCopied[q]);  // set q has reached the host
           select_out_set(h, q);
           do_interp_output(h, b0, std::min(h->outChunk, B - b0));
@@ -2133,20 +2158,21 @@ static void run_chunks(batotp_handle h, const batotp_cfg *cfg, const batotp_batc
       process_chunk(h, first ? cfg : nullptr, in, out, at, B, std::min(chunk, mainB - at - B));
     } catch (const Err &e) {
       // a workspace did not fit (long paths, many rows): release everything and go on with smaller chunks
-      if (!e.oom || (chunk <= 256 && h->outChunk <= 256)) throw;
+      if (!e.oom) throw;
       g_sync(h->stream);
       g_sync(h->copyStream);
       h->copiesPending = false;
       h->inSet[0].src = h->inSet[1].src = nullptr;
       free_ws(h);
       free_out(h);
-      if (e.fitB > 0 && e.fitB < chunk)  // the workspace planner knows what fits
-        chunk = std::max(256, e.fitB / SW_NT * SW_NT);
-      else if (h->allocPhase == 1 && std::min(h->outChunk, chunk) > 256)
-        h->outChunk = std::max(256, std::min(h->outChunk, chunk) / 2);
+      const int chunk0 = chunk, out0 = h->outChunk;
+      if (e.fitB > 0 && e.fitB < B)  // the workspace planner knows what fits
+        chunk = std::max(1, e.fitB >= SW_NT ? e.fitB / SW_NT * SW_NT : e.fitB);
+      else if (h->allocPhase == 1 && std::min(h->outChunk, B) > 1)
+        h->outChunk = std::max(1, std::min(h->outChunk, B) / 2);
       else
-        chunk = std::max(256, (chunk / 2 + SW_NT - 1) / SW_NT * SW_NT);
-      h->capB = 0;
+        chunk = std::max(1, B > 2 * SW_NT ? (B / 2 + SW_NT - 1) / SW_NT * SW_NT : B / 2);
+      if ((chunk >= chunk0 || chunk >= B) && h->outChunk >= std::min(out0, B)) throw;  // nothing left to shrink
       continue;
     }
     first = false;
@@ -2259,7 +2285,9 @@ static void run_stragglers(batotp_handle h, const batotp_cfg *cfg, const batotp_
   h->copiesPending = false;
   h->inSet[0].src = h->inSet[1].src = nullptr;
   try {
-    process_chunk(h, cfg, &in2, &o2, 0, n, 0);
+    int chunk2 = n;
+    bool first2 = true;
+    run_chunks(h, cfg, &in2, &o2, 0, n, chunk2, first2);  // (with its out-of-memory retries)
     g_sync(h->copyStream);
     g_sync(h->stream);
     h->copiesPending = false;
@@ -2392,6 +2420,7 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
       batotp_ctx *hp = h->helper;
       h->sweepMs += hp->sweepMs;
       h->sweepLaunches += hp->sweepLaunches;
+      h->sweepLog.insert(h->sweepLog.end(), hp->sweepLog.begin(), hp->sweepLog.end());
       h->cntVerify += hp->cntVerify;
       h->cntSteps += hp->cntSteps;
       h->cntTraj += hp->cntTraj;

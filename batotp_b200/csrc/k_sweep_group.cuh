@@ -109,7 +109,10 @@ __global__ void __launch_bounds__(SWG_NT) k_sweep_group(WSP) {
   bis.begin(0.0);
   bool have = false, needPro = false, drained = false;
   // ---- per-lane rows: cached segment coefficients and the values at the current point
-  double kr0 = 0, kr1 = 0, kr2 = 0;  // own joint row {3c3, 2c2, c1}
+  // own joint row {3c3, 2c2, c1}; a lane without a joint keeps theta' = (tau + 1) vFact, theta'' = aFact: its
+  // results are masked out everywhere, but the compiler evaluates some quotients of theta', theta'' ahead of
+  // their conditions, and zeros there would send every such division down the slow path
+  double kr0 = 0, kr1 = 1, kr2 = 1;
   double cr0 = 0, cr1 = 0, cr2 = 0;  // own Cartesian row (lanes 0..2)
   double dr[TRQ ? 4 : 1][4];          // own dynamics rows a1..a4 {c3,c2,c1,c0}
   double thD = 0, thDD = 0;
@@ -257,9 +260,15 @@ __global__ void __launch_bounds__(SWG_NT) k_sweep_group(WSP) {
     }
     if (accOn && jointLane) {  // ba.cpp:1514-1533
       const double v = thD;
-      if (fabs(v) < C.thrV) {
-        if (!(fabs(thDD) < C.thrA))
-          if (sq > accMax / fabs(thDD)) viol = true;
+      if (fabs(v) < C.thrV) {  // rare: the joint (nearly) stands still, only the curvature bounds sdot
+        if (!(fabs(thDD) < C.thrA)) {
+          double den = fabs(thDD);
+#ifdef __CUDA_ARCH__
+          asm volatile("" : "+d"(den));  // keeps the division inside its condition (it is loop-invariant and pure,
+                                         // so it would be hoisted to every point otherwise)
+#endif
+          if (sq > accMax / den) viol = true;
+        }
       } else {
         const int sg = (0.0 < v) - (v < 0.0);
         const double vT = thDD * sq;
@@ -303,9 +312,13 @@ __global__ void __launch_bounds__(SWG_NT) k_sweep_group(WSP) {
           viol |= (L > H);
         }
       } else {
-        const double Cq = Q2;
-        if (!(Cq < C.thrQ2))
+        double Cq = Q2;
+        if (!(Cq < C.thrQ2)) {
+#ifdef __CUDA_ARCH__
+          asm volatile("" : "+d"(Cq));  // as above: not ahead of its condition
+#endif
           if (sq * sq > C.amaxSQ / Cq) viol = true;
+        }
       }
     }
     Lo = L;

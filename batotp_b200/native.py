@@ -70,6 +70,7 @@ def load(path: Optional[str] = None):
     L.batotp_cuda_launch_count.argtypes = [C.c_void_p]
     L.batotp_cuda_launch_count.restype = C.c_long
     L.batotp_cuda_stats.argtypes = [C.c_void_p, _dp, C.c_int]
+    L.batotp_cuda_sweep_log.argtypes = [C.c_void_p, _dp, _ip, _ip, C.c_int]
     L.batotp_cuda_set_keep_f64.argtypes = [C.c_void_p, C.c_int]
     L.batotp_cuda_fp64_peak.argtypes = [C.c_void_p, _dp, _dp]
     L.batotp_cuda_selftest_div.argtypes = [C.c_void_p, C.c_ulonglong, C.c_longlong, C.POINTER(C.c_longlong),
@@ -238,6 +239,13 @@ class Context:
         self.L.batotp_cuda_stats(self.h, v, 6)
         return dict(sweep_ms=v[0], sweep_launches=int(v[1]), verifies=int(v[2]), steps=int(v[3]),
                     trajectories=int(v[4]), launches=int(v[5]))
+
+    def sweep_log(self):
+        """[(device ms, trajectories, kernel)] of the sweep launches since the last stats_reset."""
+        cap = 4096
+        ms, nt, kk = (C.c_double * cap)(), (C.c_int * cap)(), (C.c_int * cap)()
+        n = self.L.batotp_cuda_sweep_log(self.h, ms, nt, kk, cap)
+        return [(ms[i], nt[i], kk[i]) for i in range(min(n, cap))]
 
     def fp64_peak(self):
         a, b = C.c_double(0), C.c_double(0)

@@ -73,6 +73,9 @@ long batotp_cuda_launch_count(batotp_handle h);
  * _timer(which=0) records an event on the context's stream, _timer(which=1) records a second one,
  *         waits for it and returns the elapsed device milliseconds between the two. */
 int batotp_cuda_stats(batotp_handle h, double *out, int n);
+/* one record per sweep launch since the last reset (at most 4096 kept): device milliseconds, trajectories of the
+ * chunk, kernel (1 = one trajectory per lane, 2 = a group of lanes per trajectory).  Returns the number of records. */
+int batotp_cuda_sweep_log(batotp_handle h, double *ms, int *n_traj, int *kernel, int cap);
 int batotp_cuda_stats_reset(batotp_handle h);
 int batotp_cuda_timer(batotp_handle h, int which, double *elapsed_ms);
 /* per-kernel device timing for tuning runs: when on, every launch is bracketed by CUDA events and waited

@@ -229,6 +229,39 @@ int ref_sweep_flags(void *p, int dir, double *sOut, double *sdotOut, unsigned ch
   return n;
 }
 
+// SURVEY §8a A10 (derived product: the per-sample maximum-velocity curve) from the REFERENCE's own private
+// per-point functions: evalSplinePartials (ba.cpp:1341), sdotLim (ba.cpp:1204; reverse direction, so no MVC
+// term; _sdotMin = 0) and applyAccelConstraintsBisectionPt (ba.cpp:1248) at every knot of the s-grid, starting
+// from sdot_start.  This is what pins the restatement's orc_mvc_per_sample (and through it the device kernel
+// k_mvc) to the reference.  Call after ref_interp_input.
+int ref_mvc_per_sample(void *p, double sdot_start, double *out, int cap) {
+  Handle *h = (Handle *)p;
+  BA &ba = h->ba;
+  Traj &traj = h->traj;
+  const int n = traj.nPtsC;
+  const int saveDir = ba._integDir;
+  const double saveMin = ba._sdotMin, saveSec = traj.sLastSec;
+  ba._integDir = -1;
+  for (int k = 0; k < n && k < cap; ++k) {
+    traj.sCur = traj.sC[k];
+    traj.curSegC = std::min(k, n - 2);
+    ba._sdotMin = 0.0;
+    ba.evalSplinePartials(traj);  // the velocity limits read the partials of the last evaluation (quirk Q2)
+    double sd = sdot_start;
+    ba.sdotLim(traj, sd, "linear");
+    traj.sdotCur = sd;
+    double sdd = 0;
+    int it = 0;
+    traj.sLastSec = 0;  // keeps the bisection from recording it
+    ba.applyAccelConstraintsBisectionPt(traj, sdd, it);
+    out[k] = traj.sdotCur;
+  }
+  ba._integDir = saveDir;
+  ba._sdotMin = saveMin;
+  traj.sLastSec = saveSec;
+  return n;
+}
+
 int ref_get_vec(void *p, const char *name, int idx, double *buf, int cap) {
   Handle *h = (Handle *)p;
   Traj &t = h->traj;

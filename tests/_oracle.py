@@ -90,6 +90,7 @@ def ref_lib():
         L.ref_sweep.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.ref_sweep_flags.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.POINTER(C.c_ubyte), C.c_int]
         L.ref_get_vec.argtypes = [C.c_void_p, C.c_char_p, C.c_int, _dp, C.c_int]
+        L.ref_mvc_per_sample.argtypes = [C.c_void_p, C.c_double, _dp, C.c_int]
         L.ref_get_scalar.argtypes = [C.c_void_p, C.c_char_p]
         L.ref_get_scalar.restype = C.c_double
         L.ref_get_cfg.argtypes = [C.c_void_p, C.POINTER(BatotpCfg)]
@@ -237,6 +238,12 @@ class Ref(_Base):
 
     def interp_output(self):
         return self._call(self.L.ref_interp_output)
+
+    def mvc_per_sample(self, sdot_start: float) -> np.ndarray:
+        n = int(self.scalar("nPtsC"))
+        out = np.zeros(n, dtype=np.float64)
+        self._call(self.L.ref_mvc_per_sample, sdot_start, out.ctypes.data_as(_dp), n)
+        return out
 
     def write_output(self):
         return self._call(self.L.ref_write_output)

@@ -466,3 +466,49 @@ def test_group_sweep_kernel_on_a_ragged_batch(ctx):
     for nm in ("status", "n_rev", "n_fwd", "n_out", "t_total", "s_last_sec", "theta_out", "hist", "flags"):
         assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
     assert sb["verifies"] > 0 and P.compare(cfg, b, 3, P.OracleRun(cfg, tres, th[3], None)) == []
+
+
+def test_chunks_shrink_until_the_workspace_fits(ctx, monkeypatch):
+    """A chunk whose workspace would not fit the device memory is refused before anything is allocated, with the
+    size that fits; the batch goes on with smaller chunks and gives the same results.  When even one trajectory
+    does not fit the call fails with a message instead of retrying for ever.  (BATOTP_EMU_FREE_MB makes the host
+    emulation report that much free memory; 2 GB of it are the planner's own reserve.)"""
+    import __graft_entry__ as g
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 0, 12)
+    a = P.run_device(ctx, cfg, tres, th, None, out_cap=4096, hist_cap=4096)
+    fresh = native.Context(0, g.build_emu())  # no workspace yet: every size is planned against the "free" memory
+    fresh.set_sweep_kernel(1)
+    try:
+        monkeypatch.setenv("BATOTP_EMU_FREE_MB", str(2048 + 8))  # room for a few trajectories
+        b = P.run_device(fresh, cfg, tres, th, None, out_cap=4096, hist_cap=4096)
+        assert fresh.stats()["sweep_launches"] >= 3
+        for nm in ("status", "n_rev", "n_fwd", "n_out", "t_total", "theta_out", "hist", "flags"):
+            assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
+        cfg2, tres2, th2, ca2, ts2 = P.load_stock("KUKA-LWR-IV")  # another robot: the workspace is planned anew
+        monkeypatch.setenv("BATOTP_EMU_FREE_MB", "2048")
+        with pytest.raises(native.NativeError, match="of workspace"):
+            P.run_device(fresh, cfg2, tres2, th2, ca2, ts2)
+        monkeypatch.delenv("BATOTP_EMU_FREE_MB")
+        c = P.run_device(fresh, cfg, tres, th, None, out_cap=4096, hist_cap=4096)
+        assert np.array_equal(a.theta_out, c.theta_out)
+    finally:
+        fresh.close()
+
+
+@pytest.mark.parametrize("name", ["RR", "UR5", "CSPR3DOF", "KUKA-LWR-IV"])
+def test_per_sample_mvc_on_cartesian_and_torque_robots(ctx, name):
+    """SURVEY 8a A10 on robots with Cartesian limits (UR5, KUKA), serial torque (RR) and Par2Ser torque (CSPR3DOF):
+    k_mvc against the oracle, which tests/test_oracle_vs_reference.py pins to the reference's private per-point
+    functions on the same folders."""
+    from _oracle import Oracle
+    cfg, tres, th, ca, ts = P.load_stock(name)
+    ctx.load(cfg, ctx.make_in(th, ca, tres, timestamp=ts))
+    ctx.interp_input()
+    o = Oracle(cfg)
+    n0 = (th if th is not None else ca).shape[2]
+    o.load_raw(n0, tres, None if th is None else th[0], None if ca is None else ca[0], None if ts is None else ts[0])
+    assert o.interp_input() == 0
+    for start in (1.0e3, 0.5):
+        want = o.mvc_per_sample(start)
+        got = ctx.mvc_per_sample(1, len(want) + 8, start)
+        assert np.array_equal(got[0, :len(want)], want), start

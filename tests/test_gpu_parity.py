@@ -474,3 +474,22 @@ def test_stragglers_and_two_contexts(ctx):
             assert P.compare(cfgB, rb, k, P.OracleRun(cfgB, tresB, thB[k], None)) == []
     finally:
         other.close()
+
+
+@pytest.mark.parametrize("name", ["RR", "UR5", "CSPR3DOF", "KUKA-LWR-IV"])
+def test_per_sample_mvc_on_cartesian_and_torque_robots(ctx, name):
+    """SURVEY 8a A10 on robots with Cartesian limits (UR5, KUKA), serial torque (RR) and Par2Ser torque (CSPR3DOF):
+    k_mvc against the oracle, which tests/test_oracle_vs_reference.py pins to the reference's private per-point
+    functions on the same folders."""
+    from _oracle import Oracle
+    cfg, tres, th, ca, ts = P.load_stock(name)
+    ctx.load(cfg, ctx.make_in(th, ca, tres, timestamp=ts))
+    ctx.interp_input()
+    o = Oracle(cfg)
+    n0 = (th if th is not None else ca).shape[2]
+    o.load_raw(n0, tres, None if th is None else th[0], None if ca is None else ca[0], None if ts is None else ts[0])
+    assert o.interp_input() == 0
+    for start in (1.0e3, 0.5):
+        want = o.mvc_per_sample(start)
+        got = ctx.mvc_per_sample(1, len(want) + 8, start)
+        assert np.array_equal(got[0, :len(want)], want), start

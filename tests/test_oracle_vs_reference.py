@@ -181,3 +181,19 @@ def test_input_decimation_and_smoothing_match(name, decim, window, tmp_path):
         assert np.array_equal(r.vec("theta", j), o.vec("theta", j)), j
     for j in range(int(r.scalar("cartRows"))):
         assert np.array_equal(r.vec("cart", j), o.vec("cart", j)), j
+
+
+@pytest.mark.parametrize("name", P.STOCK)
+@pytest.mark.parametrize("start", [1.0e3, 0.5])
+def test_per_sample_mvc_is_the_reference_functions(name, start, tmp_path):
+    """the per-sample maximum-velocity curve has no reference output of its own; it is DEFINED as
+    the reference's private per-point functions (evalSplinePartials, sdotLim, applyAccelConstraintsBisectionPt)
+    evaluated at every knot.  ref_mvc_per_sample drives exactly those (oracle/ref_harness.cpp); the restatement
+    must agree bit for bit on every robot: joint limits (GEN7DOF), Cartesian (UR5, KUKA), serial torque (RR),
+    Par2Ser torque (CSPR3DOF)."""
+    cfg, r, o = _pair(name, tmp_path)
+    assert r.interp_input() == 0 and o.interp_input() == 0
+    a, b = r.mvc_per_sample(start), o.mvc_per_sample(start)
+    assert len(a) == len(b) == int(o.scalar("nPtsC")) and len(a) > 100
+    assert np.array_equal(a, b)
+    assert np.isfinite(b).all() and b.max() <= start
