@@ -1846,7 +1846,7 @@ static int chunk_interp_input(batotp_handle h, bool haveN0) {
   for (int attempt = 0; attempt < 8; ++attempt) {
     // the step capacity follows the grid the planning pass finds (a sweep takes about as many steps as the
     // grid has points; twice that leaves room), or what earlier chunks needed
-    const int Sc = std::max(h->hwSc, h->stepHint > 0 ? h->stepHint : std::max(1024, 2 * Nc));
+    const int Sc = std::min(h->maxSteps, std::max(h->hwSc, h->stepHint > 0 ? h->stepHint : std::max(1024, 2 * Nc)));
     ensure_ws(h, h->B, Nc, Sc);
     h->w.B = h->B;
     const int need = do_interp_input(h, haveN0, plan);

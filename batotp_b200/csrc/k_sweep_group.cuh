@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(SWG_NT) k_sweep_group(WSP) {
   const int gbase = lane & ~(G - 1);  // first lane of the group
   const bool jointLane = gl < J;
   const bool cartLane = CART && gl < 3;
-  const unsigned gmask = ((G == 32) ? 0xffffffffu : ((1u << G) - 1u)) << gbase;
+  const unsigned gmask = ((G == 32) ? 0xffffffffu : ((1u << G) - 1u)) << gbase;  // (for ballots)
 #define SD(k) sS[(k)][tid]
 #define SDD(k) sS[7 + (k)][tid]
   // this lane's limits
@@ -170,22 +170,30 @@ __global__ void __launch_bounds__(SWG_NT) k_sweep_group(WSP) {
     nLim = nBis = 0;
     needPro = true;
   };
-  auto fetch = [&]() {
-    for (;;) {
+  // Every collective of this kernel is warp-wide and sits in convergent code, the queue fetch included: the groups
+  // that need a trajectory draw one (their leader lane), all lanes take part in the broadcast, and the draw is
+  // repeated while some group drew a trajectory that interpInputData has already rejected.
+  auto fetch_all = [&]() {
+    bool need = !have && !drained;
+    while (__any_sync(0xffffffffu, need)) {
       int bb = 0;
-      if (gl == 0) bb = atomicAdd(w.queue, 1);
-      b = __shfl_sync(gmask, bb, gbase);
-      if (b >= w.B) {
-        drained = true;
-        return;
+      if (need && gl == 0) bb = atomicAdd(w.queue, 1);
+      bb = __shfl_sync(0xffffffffu, bb, gbase);
+      if (need) {
+        b = bb;
+        if (b >= w.B) {
+          drained = true;
+          need = false;
+        } else if (!(w.st[b].status & ST_FATAL_MASK)) {
+          need = false;
+          have = true;
+          status = 0;
+          nVerify = 0;
+          sLastSec = w.st[b].sLastSec;
+          sweep_begin(-1, 0);
+        }
       }
-      if (!(w.st[b].status & ST_FATAL_MASK)) break;
     }
-    have = true;
-    status = 0;
-    nVerify = 0;
-    sLastSec = w.st[b].sLastSec;
-    sweep_begin(-1, 0);
   };
   auto mvc_window = [&]() {
     if (segM != segMLoaded) {
@@ -480,7 +488,7 @@ __global__ void __launch_bounds__(SWG_NT) k_sweep_group(WSP) {
   // ================= persistent warp loop =================
   for (;;) {
     __syncwarp();  // the leader's history stores of the last step are visible to the group (MVC reads)
-    if (!have && !drained) fetch();
+    fetch_all();
     if (!__any_sync(0xffffffffu, have)) break;
     const bool pro = have && needPro;
     for (int p = __any_sync(0xffffffffu, pro) ? -3 : 0; p < 6; ++p)
