@@ -254,6 +254,8 @@ struct batotp_ctx {
   // context (own streams and workspaces, one host thread) next to the output / input phases of the full chunks
   batotp_ctx *helper = nullptr;
   bool tailOverlap = true;
+  int pipeline = 1;  // two-context chunk pipeline of batotp_cuda_optimize_batch: 0 off, 1 automatic (large batches),
+                     // n > 1: chunks of n trajectories whatever the batch size (tuning / tests)
   // stragglers: the few trajectories of a chunk that outgrow the step capacity keep BATOTP_ST_STEP_CAP for the
   // moment and are re-run together, with a larger capacity, after the chunks of the batch (optimize_batch)
   std::vector<int> stragglers;  // indices in the caller's batch
@@ -2140,6 +2142,13 @@ int batotp_cuda_set_tail_overlap(batotp_handle h, int on) {
   return 0;
 }
 
+int batotp_cuda_set_pipeline(batotp_handle h, int on) {
+  if (!h) return -1;
+  if (on < 0) return -1;
+  h->pipeline = on;
+  return 0;
+}
+
 // drain both streams of a context without raising (error paths)
 static void sync_quiet(batotp_handle h) {
 #ifndef BATOTP_HOST_EMU
@@ -2359,6 +2368,109 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
     h->stragglers.clear();
     h->stragglerSc = 0;
     h->collectStragglers = !cfg->is_interp_only;
+    // ---- two-context pipeline: chunks alternate between this context and the helper (own streams and workspaces,
+    // driven by one host thread each).  The sweep kernel is bound by the latency of a trajectory and leaves most of
+    // the issue slots and nearly all of the DRAM bandwidth idle; the input / output phases are bandwidth-bound.  With
+    // chunks of two sweep CTAs per SM the register file has room for the other context's streaming kernels, so the
+    // sweep of chunk k runs beside the output phase of chunk k-1 and the input phase of chunk k+1.  No ordering is
+    // needed between the contexts (trajectories are independent, the result arrays are disjoint); the device
+    // serialises the two sweeps by itself, which is what staggers the pipelines.
+    if (h->pipeline && h->chunk == 0 && !h->profile && !cfg->is_interp_only &&
+        (h->pipeline > 1 || (in->B > SWEEP_GROUP_MAX_B && h->sweepKernel != 2))) {
+      int sms = 148;
+#ifndef BATOTP_HOST_EMU
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+#endif
+      const int chunkP = h->pipeline > 1 ? h->pipeline : sms * 2 * SW_NT;
+      if (in->B > chunkP + chunkP / 4) {
+        if (!h->helper && batotp_cuda_create(h->device, &h->helper) != 0) h->helper = nullptr;
+        if (h->helper) {
+          batotp_ctx *hp = h->helper;
+          hp->tailOverlap = false;
+          hp->pipeline = 0;
+          hp->chunk = 0;
+          hp->outChunk = h->outChunk;
+          hp->maxSteps = h->maxSteps;
+          if (hp->stepHint != h->stepHint) hp->hwSc = 0;
+          hp->stepHint = h->stepHint;
+          hp->keepF64 = h->keepF64;
+          hp->sweepKernel = h->sweepKernel;
+          hp->stragglers.clear();
+          hp->stragglerSc = 0;
+          hp->collectStragglers = true;
+          hp->beforeSweeps = nullptr;
+          h->onSweepsDone = nullptr;
+          // chunk list: full chunks of chunkP, the remainder last; even ones here, odd ones on the helper
+          std::vector<std::pair<int, int>> mine, theirs;
+          int k = 0;
+          for (int at = 0; at < in->B; at += chunkP, ++k)
+            (k % 2 == 0 ? mine : theirs).push_back({at, std::min(chunkP, in->B - at)});
+          struct { bool failed = false, oom = false; std::string msg; } hres;
+          std::vector<std::pair<int, int>> redo;  // chunks the helper could not take (no memory for two workspaces)
+          std::thread worker([&, hp]() {
+            bool firstH = true;
+            size_t done = 0;
+            try {
+              hp->inSet[0].src = hp->inSet[1].src = nullptr;
+              for (; done < theirs.size(); ++done) {
+                int c = theirs[done].second;
+                run_chunks(hp, cfg, in, out, theirs[done].first, theirs[done].first + theirs[done].second, c, firstH);
+              }
+              g_sync(hp->copyStream);
+              hp->copiesPending = false;
+            } catch (const Err &e) {
+              hres.failed = true;
+              hres.oom = e.oom;
+              hres.msg = e.msg;
+              sync_quiet(hp);
+            } catch (...) {
+              hres.failed = true;
+              hres.msg = "unexpected exception in the second pipeline context";
+              sync_quiet(hp);
+            }
+            for (size_t q = done; q < theirs.size(); ++q) redo.push_back(theirs[q]);
+          });
+          std::string myErr;
+          bool myFailed = false;
+          try {
+            for (auto &c : mine) {
+              int cs = c.second;
+              run_chunks(h, cfg, in, out, c.first, c.first + c.second, cs, first);
+            }
+          } catch (const Err &e) {
+            myFailed = true;
+            myErr = e.msg;
+          }
+          worker.join();
+          h->sweepMs += hp->sweepMs;
+          h->sweepLaunches += hp->sweepLaunches;
+          h->sweepLog.insert(h->sweepLog.end(), hp->sweepLog.begin(), hp->sweepLog.end());
+          h->cntVerify += hp->cntVerify;
+          h->cntSteps += hp->cntSteps;
+          h->cntTraj += hp->cntTraj;
+          h->launches += hp->launches;
+          batotp_cuda_stats_reset(hp);
+          h->stragglers.insert(h->stragglers.end(), hp->stragglers.begin(), hp->stragglers.end());
+          h->stragglerSc = std::max(h->stragglerSc, hp->stragglerSc);
+          hp->stragglers.clear();
+          if (myFailed) throw Err{myErr};
+          if (hres.failed) {
+            if (!hres.oom) throw Err{hres.msg};
+            free_ws(hp);  // no room for the second context's workspaces: its chunks run here
+            free_out(hp);
+            for (auto &c : redo) {
+              int cs = c.second;
+              run_chunks(h, cfg, in, out, c.first, c.first + c.second, cs, first);
+            }
+          }
+          g_sync(h->copyStream);
+          h->copiesPending = false;
+          if (!h->stragglers.empty()) run_stragglers(h, cfg, in, out);
+          h->collectStragglers = false;
+          return 0;
+        }
+      }
+    }
     if (h->tailOverlap && !h->profile && !out->on_device && !cfg->is_interp_only && in->B > chunk) {
       int sms = 148;
 #ifndef BATOTP_HOST_EMU

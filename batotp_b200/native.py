@@ -66,6 +66,7 @@ def load(path: Optional[str] = None):
     L.batotp_cuda_set_max_steps.argtypes = [C.c_void_p, C.c_int]
     L.batotp_cuda_set_tail_overlap.argtypes = [C.c_void_p, C.c_int]
     L.batotp_cuda_set_step_hint.argtypes = [C.c_void_p, C.c_int]
+    L.batotp_cuda_set_pipeline.argtypes = [C.c_void_p, C.c_int]
     L.batotp_cuda_set_sweep_kernel.argtypes = [C.c_void_p, C.c_int]
     L.batotp_cuda_launch_count.argtypes = [C.c_void_p]
     L.batotp_cuda_launch_count.restype = C.c_long
@@ -221,6 +222,10 @@ class Context:
     def set_sweep_kernel(self, mode: int):
         """0 automatic, 1 one trajectory per lane, 2 a group of lanes per trajectory."""
         self.L.batotp_cuda_set_sweep_kernel(self.h, mode)
+
+    def set_pipeline(self, on: int):
+        """0 off, 1 automatic, n > 1: two-context pipeline with chunks of n trajectories."""
+        self.L.batotp_cuda_set_pipeline(self.h, int(on))
 
     def set_step_hint(self, n: int):
         self.L.batotp_cuda_set_step_hint(self.h, n)

@@ -82,6 +82,8 @@ def parse():
                     help="paths resident per device pass (input interp + sweeps); 0 = the library's automatic split")
     ap.add_argument("--out-chunk", type=int, default=8192, help="paths per output-interpolation pass")
     ap.add_argument("--sweep-kernel", type=int, default=0, help="0 automatic, 1 lane per trajectory, 2 group per trajectory")
+    ap.add_argument("--pipeline", type=int, default=1,
+                    help="two-context chunk pipeline: 1 automatic, 0 off, n > 1 chunks of n paths (tuning)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-path latency block")
@@ -371,6 +373,7 @@ def main_b200(args):
     ctx.set_chunk(args.chunk)
     ctx.set_out_chunk(args.out_chunk)
     ctx.set_sweep_kernel(args.sweep_kernel)
+    ctx.set_pipeline(args.pipeline)
     peak_fma, peak_nofma = ctx.fp64_peak()
     trig_bad, trig_variant = ctx.selftest_trig(1, 1 << 20)  # the strict trigonometry reproduces this host's libm
 
@@ -456,7 +459,7 @@ def main_b200(args):
     # use the pitch of the longest trajectory (known from the resident leg).
     out_cap = int(res_s.n_out.max()) if ok else 4096
     h_np = h_pay.numpy()
-    want_cart = cfg.n_cart > 0
+    want_cart = cfg.n_cart > 0 and wl != "gen7dof"  # a generic robot has no Cartesian data: its rows are zeros
     sl = B
     res_e = None
     while res_e is None:
@@ -508,6 +511,7 @@ def main_b200(args):
                     dtype="f64", data="synthetic",
                     config=dict(workload=W["text"], paths_per_gpu=B, paths_total=total,
                                 sweep_kernel={0: "automatic", 1: "lane", 2: "group"}[args.sweep_kernel],
+                                pipeline={0: "off", 1: "automatic"}.get(args.pipeline, "chunks of %d" % args.pipeline),
                                 parallelism="independent contiguous slices per GPU, no collective",
                                 l2="inputs (%.0f MB/GPU) and per-chunk tables exceed the 126 MB L2" % (payload.nbytes / 1e6),
                                 optimised=ok, mean_rk_steps=steps_rk / ntraj,
