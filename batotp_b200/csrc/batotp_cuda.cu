@@ -254,7 +254,7 @@ struct batotp_ctx {
   // context (own streams and workspaces, one host thread) next to the output / input phases of the full chunks
   batotp_ctx *helper = nullptr;
   bool tailOverlap = true;
-  int pipeline = 1;  // two-context chunk pipeline of batotp_cuda_optimize_batch: 0 off, 1 automatic (large batches),
+  int pipeline = 0;  // two-context chunk pipeline of batotp_cuda_optimize_batch: 0 off, 1 automatic (large batches),
                      // n > 1: chunks of n trajectories whatever the batch size (tuning / tests)
   // stragglers: the few trajectories of a chunk that outgrow the step capacity keep BATOTP_ST_STEP_CAP for the
   // moment and are re-run together, with a larger capacity, after the chunks of the batch (optimize_batch)

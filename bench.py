@@ -82,8 +82,9 @@ def parse():
                     help="paths resident per device pass (input interp + sweeps); 0 = the library's automatic split")
     ap.add_argument("--out-chunk", type=int, default=8192, help="paths per output-interpolation pass")
     ap.add_argument("--sweep-kernel", type=int, default=0, help="0 automatic, 1 lane per trajectory, 2 group per trajectory")
-    ap.add_argument("--pipeline", type=int, default=1,
-                    help="two-context chunk pipeline: 1 automatic, 0 off, n > 1 chunks of n paths (tuning)")
+    ap.add_argument("--pipeline", type=int, default=0,
+                    help="two-context chunk pipeline: 0 off (default: measured slower, see DESIGN.md), 1 automatic, "
+                         "n > 1 chunks of n paths (tuning)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-path latency block")

@@ -535,7 +535,7 @@ def test_two_context_pipeline_does_not_change_results(ctx):
             runs.append((b, ctx.stats()))
     finally:
         ctx.set_step_hint(0)
-        ctx.set_pipeline(1)
+        ctx.set_pipeline(0)
         ctx.set_chunk(16384)
     for b, sb in runs:
         for nm in ("status", "n_rev", "n_fwd", "n_out", "t_total", "s_last_sec", "theta_out", "hist", "flags"):
