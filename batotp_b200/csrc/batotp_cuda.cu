@@ -164,6 +164,7 @@ Pmat make_pmat() {
 }  // namespace
 
 // ----------------------------------------------------------------------------- context
+#define NSETS 4
 struct batotp_ctx {
   int device = 0;
   cudaStream_t stream = 0;
@@ -217,10 +218,13 @@ struct batotp_ctx {
   int B = 0, n0max = 0;
   // staged outputs
   float *d_thetaOut = nullptr, *d_cartOut = nullptr, *d_trqOut = nullptr, *d_histOut = nullptr;  // current set
-  // two sets of packed-output staging buffers: the rows of sub-chunk k travel to the host on the copy stream
-  // while the kernels of sub-chunk k+1 fill the other set
-  float *o_thetaOut[2] = {nullptr, nullptr}, *o_cartOut[2] = {nullptr, nullptr}, *o_trqOut[2] = {nullptr, nullptr},
-        *o_histOut[2] = {nullptr, nullptr};
+  // NSETS sets of packed-output staging buffers: the rows of sub-chunk k travel to the host on the copy stream
+  // while the kernels of the following sub-chunks fill the other sets - and, since nothing but the output phase
+  // touches a set, while the NEXT chunk's input phase and sweeps run: when the host link is the bottleneck (several
+  // GPUs sharing it) the copy engine then never idles
+  float *o_thetaOut[NSETS] = {}, *o_cartOut[NSETS] = {}, *o_trqOut[NSETS] = {}, *o_histOut[NSETS] = {};
+  bool setBusy[NSETS] = {};  // a copy out of the set has been enqueued since its rows were last awaited (evCopied)
+  int setNext = 0;           // the staging sets rotate across sub-chunks AND chunks
   cudaStream_t copyStream = 0;
   double *d_cartOutD = nullptr;
   double *d_outD = nullptr;  // [Bo][R+J][OutC] FP64 final rows (keepF64)
@@ -266,10 +270,10 @@ struct batotp_ctx {
   std::function<void()> beforeSweeps;  // called after interpInputData of a chunk has been enqueued (may block)
 #ifndef BATOTP_HOST_EMU
   cudaEvent_t evS0 = nullptr, evS1 = nullptr, evT[2] = {nullptr, nullptr}, evP[2] = {nullptr, nullptr};
-  cudaEvent_t evOut[2] = {nullptr, nullptr}, evCopied[2] = {nullptr, nullptr};
+  cudaEvent_t evOut[NSETS] = {}, evCopied[NSETS] = {};
   bool sweepPending = false;
 #else
-  cudaEvent_t evOut[2] = {0, 0}, evCopied[2] = {0, 0};
+  cudaEvent_t evOut[NSETS] = {}, evCopied[NSETS] = {};
 #endif
 };
 
@@ -604,7 +608,8 @@ void ensure_out(batotp_ctx *h, int Bo, int minOutC = 0) {
       h->o_Trq2 = out_alloc<double>(h, b * MAXD * Oc);
       h->o_TrqM = out_alloc<double>(h, b * MAXD * Oc);
     }
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < NSETS; ++q) {
+      h->setBusy[q] = false;  // (free_out has waited for the device)
       h->o_thetaOut[q] = out_alloc<float>(h, b * c.J * rowP);
       h->o_cartOut[q] = out_alloc<float>(h, b * std::max(c.Cin, 1) * rowP);
       h->o_trqOut[q] = trq ? out_alloc<float>(h, b * c.J * rowP) : nullptr;
@@ -1500,7 +1505,7 @@ int batotp_cuda_create(int device, batotp_handle *out) {
     delete h;
     return -1;
   }
-  for (int q = 0; q < 2; ++q)
+  for (int q = 0; q < NSETS; ++q)
     if (cudaEventCreateWithFlags(&h->evOut[q], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->evCopied[q], cudaEventDisableTiming) != cudaSuccess) {
       delete h;
@@ -1528,7 +1533,7 @@ int batotp_cuda_destroy(batotp_handle h) {
 #ifndef BATOTP_HOST_EMU
   cudaStreamDestroy(h->stream);
   cudaStreamDestroy(h->copyStream);
-  for (int q = 0; q < 2; ++q) {
+  for (int q = 0; q < NSETS; ++q) {
     if (h->evOut[q]) cudaEventDestroy(h->evOut[q]);
     if (h->evCopied[q]) cudaEventDestroy(h->evCopied[q]);
   }
@@ -2098,11 +2103,15 @@ static void process_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_b
   }
   if (chunk_interp_input(h, h->lastHaveN0) != 0) throw Err{h->err};
   if (h->beforeSweeps) h->beforeSweeps();
-  if (h->copiesPending) {
-    // the last rows / flags of the previous chunk may still be on their way to the host: the sweeps and the
-    // output phase (which overwrite the flags and the staging sets) queue up behind those copies
-    g_stream_wait(h->stream, h->evCopied[0]);
-    g_stream_wait(h->stream, h->evCopied[1]);
+  if (h->copiesPending && out->flags && out->hist_cap > 0) {
+    // the switching flags travel straight out of the chunk workspace, which the sweeps overwrite: when they were
+    // asked for, the sweeps queue up behind the previous chunk's copies.  (Rows and histories leave from the
+    // staging sets, which only the output phase touches: their copies go on beside the next chunk's sweeps.)
+    for (int q = 0; q < NSETS; ++q)
+      if (h->setBusy[q]) {
+        g_stream_wait(h->stream, h->evCopied[q]);
+        h->setBusy[q] = false;
+      }
     h->copiesPending = false;
   }
   if (chunk_sweeps_output(h, h->lastHaveN0) != 0) throw Err{h->err};
@@ -2118,17 +2127,18 @@ static void process_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_b
       } else {
         // rows of sub-chunk k go to the host on the copy stream while sub-chunk k+1 is computed into the
         // other staging set
-        int k = 0;
-        for (int b0 = 0; b0 < B; b0 += h->outChunk, ++k) {
-          const int q = k & 1;
+        for (int b0 = 0; b0 < B; b0 += h->outChunk) {
           ensure_out(h, std::min(h->outChunk, B - b0));
-          if (k >= 2) g_stream_wait(h->stream, h->evCopied[q]);  // set q has reached the host
+          const int q = h->setNext;
+          h->setNext = (q + 1) % NSETS;
+          if (h->setBusy[q]) g_stream_wait(h->stream, h->evCopied[q]);  // the set's last rows have reached the host
           select_out_set(h, q);
           do_interp_output(h, b0, std::min(h->outChunk, B - b0));
           g_event_record(h->evOut[q], h->stream);
           g_stream_wait(h->copyStream, h->evOut[q]);
           fetch_rows(h, out, at, h->copyStream);
           g_event_record(h->evCopied[q], h->copyStream);
+          h->setBusy[q] = true;
         }
         fetch_scalars(h, out, at, 0, B);
         h->copiesPending = true;  // waited for before the next chunk's sweeps, or before the call returns
