@@ -35,7 +35,7 @@ class BatotpCfg(C.Structure):
         ("is_cart_vel_on", C.c_int), ("is_cart_acc_on", C.c_int), ("input_decim_fact", C.c_int),
         ("smooth_window", C.c_int), ("is_sdot_out", C.c_int), ("scale_type", C.c_int),
         ("is_svd", C.c_int), ("is_par2ser", C.c_int), ("is_interp_only", C.c_int),
-        ("is_auto_integ_res", C.c_int), ("trig_mode", C.c_int), ("reserved_i", C.c_int * 11),
+        ("is_auto_integ_res", C.c_int), ("trig_mode", C.c_int), ("dyn_source", C.c_int), ("reserved_i", C.c_int * 10),
         ("jnt_vel_max", C.c_double * MAX_DOF), ("jnt_acc_max", C.c_double * MAX_DOF),
         ("jnt_trq_max", C.c_double * MAX_DOF), ("jnt_trq_min", C.c_double * MAX_DOF),
         ("cart_vel_max", C.c_double), ("cart_acc_max", C.c_double), ("integ_res", C.c_double),

@@ -184,6 +184,9 @@ struct batotp_ctx {
   // batotp_cuda_optimize_batch (a sub-chunk then leaves in one contiguous copy), 0 = the device capacities
   int rowPitch = 0, histPitch = 0, capRowPitch = 0, capHistPitch = 0;
   int maxSteps = 65536;           // largest RK-step capacity the automatic retries grow to (per sweep)
+  // cfg.dyn_source = 1: the caller's point function for a1..a4 (Robot::call_dynSerial's contract)
+  batotp_dyn_fn dynFn = nullptr;
+  void *dynUser = nullptr;
   int sweepKernel = 0;            // 0 automatic (by chunk size), 1 one trajectory per lane (k_sweep), 2 a group of lanes per trajectory (k_sweep_group)
   int stepHint = 0;               // RK-step capacity a chunk starts with (0 = automatic: max(1024, 2 x grid points))
   // Thomas factor tables
@@ -696,8 +699,17 @@ int check_cfg(batotp_ctx *h) {
     h->err = "parallel-mechanism torque limits without isPar2Ser are outside the accelerated scope (SURVEY §8f rank 3)";
     return -1;
   }
-  if (c.is_trq_on && !((c.robot_type == BATOTP_RR && !c.is_parallel) || (c.robot_type == BATOTP_CSPR3DOF && c.is_parallel))) {
-    h->err = "torque limits need a dynamic model: only RR (serial) and CSPR3DOF (parallel) have one (robot.cpp:349-360, 463-474)";
+  if (c.is_trq_on && c.dyn_source == 1) {
+    if (c.is_parallel) {
+      h->err = "dyn_source = 1 (a caller-supplied dynamic model) serves serial mechanisms only";
+      return -1;
+    }
+    if (!h->dynFn) {
+      h->err = "dyn_source = 1 needs a point function: call batotp_cuda_set_dyn_callback first";
+      return -1;
+    }
+  } else if (c.is_trq_on && !((c.robot_type == BATOTP_RR && !c.is_parallel) || (c.robot_type == BATOTP_CSPR3DOF && c.is_parallel))) {
+    h->err = "torque limits need a dynamic model: batotp has one for RR (serial) and CSPR3DOF (parallel) only (robot.cpp:349-360, 463-474); supply yours with dyn_source = 1 + batotp_cuda_set_dyn_callback";
     return -1;
   }
   if (c.is_interp_only && c.path_type == BATOTP_CART) {
@@ -908,6 +920,9 @@ int dispatch_sweep(batotp_ctx *h) {
     switch (key) {
       case 7 * 4 + 0: launch_sweep_group<7, false, false>(h); return 0;
       case 7 * 4 + 2: launch_sweep_group<7, true, false>(h); return 0;
+      case 7 * 4 + 3: launch_sweep_group<7, true, true>(h); return 0;   // 7 joints, Cartesian + caller-supplied torque model
+      case 7 * 4 + 1: launch_sweep_group<7, false, true>(h); return 0;
+      case 6 * 4 + 3: launch_sweep_group<6, true, true>(h); return 0;
       case 6 * 4 + 2: launch_sweep_group<6, true, false>(h); return 0;
       case 6 * 4 + 0: launch_sweep_group<6, false, false>(h); return 0;
       case 2 * 4 + 3: launch_sweep_group<2, true, true>(h); return 0;
@@ -920,6 +935,9 @@ int dispatch_sweep(batotp_ctx *h) {
   switch (key) {
     case 7 * 4 + 0: launch_sweep<7, false, false>(h); return 0;  // GEN7DOF
     case 7 * 4 + 2: launch_sweep<7, true, false>(h); return 0;   // KUKA-LWR-IV
+    case 7 * 4 + 3: launch_sweep<7, true, true>(h); return 0;    // KUKA-LWR-IV with a caller-supplied torque model
+    case 7 * 4 + 1: launch_sweep<7, false, true>(h); return 0;   // 7 joints, torque model, no Cartesian limits
+    case 6 * 4 + 3: launch_sweep<6, true, true>(h); return 0;
     case 6 * 4 + 2: launch_sweep<6, true, false>(h); return 0;   // UR5
     case 6 * 4 + 0: launch_sweep<6, false, false>(h); return 0;
     case 2 * 4 + 3: launch_sweep<2, true, true>(h); return 0;    // RR
@@ -1116,7 +1134,7 @@ int do_interp_input(batotp_ctx *h, bool haveN0, bool planSync) {
   LAUNCH_T(h, k_final_plan, B, w);
   if (c.trqOn) {
     LAUNCH_TP(h, k_eval_grid, w.Nc, B, w);
-    if (!c.c.is_parallel && c.c.trig_mode == 2)
+    if (!c.c.is_parallel && (c.c.trig_mode == 2 || c.c.dyn_source == 1))
       host_dyn_rr_grid(h);
     else
       LAUNCH_TP(h, k_dyn_grid, w.Nc, B, w, h->pm);
@@ -1250,7 +1268,7 @@ void do_interp_output(batotp_ctx *h, int b0, int Bo) {
       // re-spline theta(t) (and cart(t) for the parallel robot) to get time derivatives
       thomas_rows(h, w.O5, w.OM, Bo, b0, c.c.is_parallel ? c.R : c.J, c.R, 1, c.c.is_parallel ? 0 : 1);
       LAUNCH_TP(h, k_out_knot_eval, lOc, Bo, w);
-      if (!c.c.is_parallel && c.c.trig_mode == 2)
+      if (!c.c.is_parallel && (c.c.trig_mode == 2 || c.c.dyn_source == 1))
         host_dyn_rr_out(h);
       else
         LAUNCH_TP(h, k_out_trq, lOc, Bo, w, h->pm);
@@ -2405,6 +2423,8 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
           hp->stepHint = h->stepHint;
           hp->keepF64 = h->keepF64;
           hp->sweepKernel = h->sweepKernel;
+          hp->dynFn = h->dynFn;
+          hp->dynUser = h->dynUser;
           hp->stragglers.clear();
           hp->stragglerSc = 0;
           hp->collectStragglers = true;
@@ -2501,6 +2521,8 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
           hp->stepHint = h->stepHint;
           hp->keepF64 = h->keepF64;
           hp->sweepKernel = h->sweepKernel;
+          hp->dynFn = h->dynFn;
+          hp->dynUser = h->dynUser;
           hp->stragglers.clear();
           hp->stragglerSc = 0;
           hp->collectStragglers = true;
@@ -2673,6 +2695,17 @@ int batotp_cuda_get_f64(batotp_handle h, const char *name, int traj, int row, do
 int batotp_cuda_set_max_steps(batotp_handle h, int n) {
   if (!h || n < 1024) return -1;
   h->maxSteps = n;
+  return 0;
+}
+
+int batotp_cuda_set_dyn_callback(batotp_handle h, batotp_dyn_fn fn, void *user) {
+  if (!h) return -1;
+  h->dynFn = fn;
+  h->dynUser = user;
+  if (h->helper) {
+    h->helper->dynFn = fn;
+    h->helper->dynUser = user;
+  }
   return 0;
 }
 

@@ -10,7 +10,27 @@
 // axis-angle output rows of a UR-type robot) is applied here, to the final rows on their way out.
 namespace {
 
-// dynRR on the final grid (findDynModel, ba.cpp:905-914): Q/GD/GD2 rows -> A rows (point-major)
+// The serial dynamics evaluated by the host at one point: the caller's point function (cfg.dyn_source = 1,
+// batotp_cuda_set_dyn_callback - the plug-in for robots batotp has no model for) or dynRR with the host libm
+// (trig_mode 2)
+inline void host_dyn_point(const batotp_ctx *h, const double *q, const double *d1, const double *d2, double *a1,
+                           double *a2, double *a3, double *a4) {
+  if (h->cfg.c.dyn_source == 1)
+    h->dynFn(h->dynUser, h->cfg.J, q, d1, d2, a1, a2, a3, a4);
+  else
+    dyn_rr_point(Trig{0}, q, d1, d2, a1, a2, a3, a4);
+}
+// runs f(first, last) over [0, n) on the host's cores
+template <class F>
+void host_parallel_for(int n, F f) {
+  const int nth = std::max(1, std::min<int>((int)std::thread::hardware_concurrency(), std::min(64, n)));
+  std::vector<std::thread> th;
+  for (int t = 1; t < nth; ++t) th.emplace_back([=] { f((int)((long long)n * t / nth), (int)((long long)n * (t + 1) / nth)); });
+  f(0, (int)((long long)n / nth));
+  for (auto &x : th) x.join();
+}
+
+// serial dynamics on the final grid (findDynModel, ba.cpp:905-914): Q/GD/GD2 rows -> A rows (point-major)
 void host_dyn_rr_grid(batotp_ctx *h) {
   const DevCfg &c = h->cfg;
   const Ws &w = h->w;
@@ -28,19 +48,22 @@ void host_dyn_rr_grid(batotp_ctx *h) {
   g_d2h(d1.data(), w.GD, cnt * 8, h->stream);
   g_d2h(d2.data(), w.GD2, cnt * 8, h->stream);
   g_sync(h->stream);
-  for (int b = 0; b < B; ++b) {
-    const TrajState &s = h->hst[b];
-    if (s.status & ST_FATAL_MASK) continue;
-    for (int i = 0; i < s.nPts; ++i) {
-      const size_t off = ((size_t)i * B + b) * R;
-      double a1[2], a2[2], a3[2], a4[2];
-      dyn_rr_point(Trig{0}, &q[off], &d1[off], &d2[off], a1, a2, a3, a4);
-      const double *aa[4] = {a1, a2, a3, a4};
-      double *Ab = &A[((size_t)i * B + b) * 4 * MAXD];
-      for (int k = 0; k < 4; ++k)
-        for (int j = 0; j < 2; ++j) Ab[k * MAXD + j] = aa[k][j];
+  const int J = c.J;
+  host_parallel_for(B, [&](int b0, int b1) {
+    for (int b = b0; b < b1; ++b) {
+      const TrajState &s = h->hst[b];
+      if (s.status & ST_FATAL_MASK) continue;
+      for (int i = 0; i < s.nPts; ++i) {
+        const size_t off = ((size_t)i * B + b) * R;
+        double a1[MAXD] = {0}, a2[MAXD] = {0}, a3[MAXD] = {0}, a4[MAXD] = {0};
+        host_dyn_point(h, &q[off], &d1[off], &d2[off], a1, a2, a3, a4);
+        const double *aa[4] = {a1, a2, a3, a4};
+        double *Ab = &A[((size_t)i * B + b) * 4 * MAXD];
+        for (int k = 0; k < 4; ++k)
+          for (int j = 0; j < J; ++j) Ab[k * MAXD + j] = aa[k][j];
+      }
     }
-  }
+  });
   g_h2d(w.A, A.data(), A.size() * 8, h->stream);
   g_sync(h->stream);
 }
@@ -63,16 +86,19 @@ void host_dyn_rr_out(batotp_ctx *h) {
   g_d2h(d1.data(), w.OD, cnt * 8, h->stream);
   g_d2h(d2.data(), w.OD2, cnt * 8, h->stream);
   g_sync(h->stream);
-  for (int bl = 0; bl < Bo; ++bl) {
-    const TrajState &s = h->hst[b0 + bl];
-    if (s.status & ST_FATAL_MASK) continue;
-    for (int i = 0; i < s.nOver; ++i) {
-      const size_t off = ((size_t)i * Bo + bl) * R;
-      double a1[2], a2[2], a3[2], a4[2];
-      dyn_rr_point(Trig{0}, &q[off], &d1[off], &d2[off], a1, a2, a3, a4);
-      for (int j = 0; j < 2; ++j) T[((size_t)i * Bo + bl) * MAXD + j] = a2[j] + a3[j] + a4[j];
+  const int J = c.J;
+  host_parallel_for(Bo, [&](int l0, int l1) {
+    for (int bl = l0; bl < l1; ++bl) {
+      const TrajState &s = h->hst[b0 + bl];
+      if (s.status & ST_FATAL_MASK) continue;
+      for (int i = 0; i < s.nOver; ++i) {
+        const size_t off = ((size_t)i * Bo + bl) * R;
+        double a1[MAXD] = {0}, a2[MAXD] = {0}, a3[MAXD] = {0}, a4[MAXD] = {0};
+        host_dyn_point(h, &q[off], &d1[off], &d2[off], a1, a2, a3, a4);
+        for (int j = 0; j < J; ++j) T[((size_t)i * Bo + bl) * MAXD + j] = a2[j] + a3[j] + a4[j];  // ba.cpp:1823
+      }
     }
-  }
+  });
   g_h2d(w.Trq, T.data(), T.size() * 8, h->stream);
   g_sync(h->stream);
 }
@@ -113,6 +139,9 @@ int run_mvc_per_sample(batotp_ctx *h, double sdotStart, double *sdot_out, int ca
   switch (key) {
     case 7 * 4 + 0: launch_mvc<7, false, false>(h, sdotStart, d_out, cap); break;
     case 7 * 4 + 2: launch_mvc<7, true, false>(h, sdotStart, d_out, cap); break;
+    case 7 * 4 + 3: launch_mvc<7, true, true>(h, sdotStart, d_out, cap); break;
+    case 7 * 4 + 1: launch_mvc<7, false, true>(h, sdotStart, d_out, cap); break;
+    case 6 * 4 + 3: launch_mvc<6, true, true>(h, sdotStart, d_out, cap); break;
     case 6 * 4 + 2: launch_mvc<6, true, false>(h, sdotStart, d_out, cap); break;
     case 6 * 4 + 0: launch_mvc<6, false, false>(h, sdotStart, d_out, cap); break;
     case 2 * 4 + 3: launch_mvc<2, true, true>(h, sdotStart, d_out, cap); break;

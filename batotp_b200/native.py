@@ -66,6 +66,7 @@ def load(path: Optional[str] = None):
     L.batotp_cuda_set_max_steps.argtypes = [C.c_void_p, C.c_int]
     L.batotp_cuda_set_tail_overlap.argtypes = [C.c_void_p, C.c_int]
     L.batotp_cuda_set_step_hint.argtypes = [C.c_void_p, C.c_int]
+    L.batotp_cuda_set_dyn_callback.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.batotp_cuda_set_pipeline.argtypes = [C.c_void_p, C.c_int]
     L.batotp_cuda_set_sweep_kernel.argtypes = [C.c_void_p, C.c_int]
     L.batotp_cuda_launch_count.argtypes = [C.c_void_p]
@@ -226,6 +227,11 @@ class Context:
     def set_pipeline(self, on: int):
         """0 off, 1 automatic, n > 1: two-context pipeline with chunks of n trajectories."""
         self.L.batotp_cuda_set_pipeline(self.h, int(on))
+
+    def set_dyn_callback(self, fn, user=None):
+        """fn: address of (or ctypes pointer to) a batotp_dyn_fn; None switches it off."""
+        self._dyn = fn
+        self.L.batotp_cuda_set_dyn_callback(self.h, C.cast(fn, C.c_void_p) if fn is not None else None, user)
 
     def set_step_hint(self, n: int):
         self.L.batotp_cuda_set_step_hint(self.h, n)

@@ -56,7 +56,12 @@ typedef struct batotp_cfg {
                                libm between device stages (for a host whose libm is not the one ported).
                             In modes 1 and 2 the atan2 of the axis-angle output rows (util.cpp:574) is applied by
                             the host to the final rows */
-  int reserved_i[11];
+  int dyn_source;        /* torque limits for a robot batotp has no dynamic model for (the reference's
+                            README asks a user to add the model to robot.cpp): 0 = the built-in models (dynRR robot.cpp:377,
+                            dynCSPR3DOF robot.cpp:487); 1 = a1..a4 come from the caller's point function
+                            (batotp_cuda_set_dyn_callback, same contract as Robot::call_dynSerial robot.cpp:349-360);
+                            serial mechanisms only */
+  int reserved_i[10];
   /* ---- doubles ---- */
   double jnt_vel_max[BATOTP_MAX_DOF]; /* _JntVelMax */
   double jnt_acc_max[BATOTP_MAX_DOF]; /* _JntAccMax */

@@ -111,6 +111,18 @@ int batotp_cuda_selftest_bisect(batotp_handle h, unsigned long long seed, long l
 int batotp_cuda_selftest_trig(batotp_handle h, unsigned long long seed, long long n, long long *mismatches,
                               int *variant);
 
+/* ---- dynamic models batotp does not have ----------------------------------
+ * The reference evaluates tau = a1*sddot + a2*sdot^2 + a3*sdot + a4 through Robot::call_dynSerial (robot.cpp:349-360),
+ * which knows the RR robot only; its README asks a user to add other models to robot.cpp.  Here the model is a point
+ * function of the caller: with cfg.dyn_source = 1 and cfg.is_trq_on = 1 the library calls fn for every grid point of
+ * every trajectory (findDynModel, ba.cpp:905-914: joint values and their s-derivatives in, a1..a4 out, n_joints
+ * entries each) and again at the output sites (ba.cpp:1815-1825: time derivatives in; trq = a2 + a3 + a4), on the
+ * host's cores between device stages; splines, sweeps and limits run on the device as for RR.  fn must be
+ * thread-safe.  Serial mechanisms only. */
+typedef void (*batotp_dyn_fn)(void *user, int n_joints, const double *theta, const double *thetaD,
+                              const double *thetaD2, double *a1, double *a2, double *a3, double *a4);
+int batotp_cuda_set_dyn_callback(batotp_handle h, batotp_dyn_fn fn, void *user);
+
 /* ---- batch input: what BA::loadTrajectoryData leaves in Traj (ba.cpp:2206-2461) -------- */
 typedef struct batotp_batch_in {
   int B;                  /* trajectories */

@@ -424,6 +424,8 @@ static void bv_push(bvec *v, unsigned char x) {
 }
 
 struct orc_traj {
+  orc_dyn_fn dynFn; /* cfg.dyn_source = 1: the caller's point function for a1..a4 */
+  void *dynUser;
   batotp_cfg cfg; /* option values as loaded; the mutable ones are copied below (Q9) */
   /* BA private state (ba.h:261-331) that changes during a run */
   int nJoints, nCart;
@@ -720,6 +722,74 @@ static void rb_dyn_rr(orc_traj *t) {
     t->a3[1].p[i] = 10 * dth2;
     t->a4[0].p[i] = .5 * C_G * (m1 * A1 * c1 + m2 * (2.0 * A1 * c1 + A2 * c12));
     t->a4[1].p[i] = .5 * C_G * m2 * A2 * c12;
+  }
+}
+
+/* cfg.dyn_source = 1: Robot::call_dynSerial (robot.cpp:349-360) replaced by the caller's point function */
+static void rb_dyn_callback(orc_traj *t) {
+  int nPts = t->theta[0].n, J = t->nJoints;
+  for (int i = 0; i < J; ++i) {
+    dv_resize(&t->a1[i], nPts);
+    dv_resize(&t->a2[i], nPts);
+    dv_resize(&t->a3[i], nPts);
+    dv_resize(&t->a4[i], nPts);
+  }
+  for (int i = 0; i < nPts; ++i) {
+    double th[MAXD], d1[MAXD], d2[MAXD], a1[MAXD] = {0}, a2[MAXD] = {0}, a3[MAXD] = {0}, a4[MAXD] = {0};
+    for (int j = 0; j < J; ++j) {
+      th[j] = t->theta[j].p[i];
+      d1[j] = t->thetaD[j].p[i];
+      d2[j] = t->thetaD2[j].p[i];
+    }
+    t->dynFn(t->dynUser, J, th, d1, d2, a1, a2, a3, a4);
+    for (int j = 0; j < J; ++j) {
+      t->a1[j].p[i] = a1[j];
+      t->a2[j].p[i] = a2[j];
+      t->a3[j].p[i] = a3[j];
+      t->a4[j].p[i] = a4[j];
+    }
+  }
+}
+void orc_set_dyn_callback(orc_traj *t, orc_dyn_fn fn, void *user) {
+  t->dynFn = fn;
+  t->dynUser = user;
+}
+/* dynRR (robot.cpp:377-431) behind the plug-in signature */
+void orc_demo_dyn_rr(void *user, int n_joints, const double *theta, const double *thetaD, const double *thetaD2,
+                     double *a1, double *a2, double *a3, double *a4) {
+  (void)user;
+  (void)n_joints;
+  double A1 = .4, A2 = .6, m1 = 4, m2 = 8;
+  double th1 = C_DEG2RAD * theta[0], th2 = C_DEG2RAD * theta[1];
+  double dth1 = C_DEG2RAD * thetaD[0], dth2 = C_DEG2RAD * thetaD[1];
+  double ddth1 = C_DEG2RAD * thetaD2[0], ddth2 = C_DEG2RAD * thetaD2[1];
+  double c1 = cos(th1), c2 = cos(th2), c12 = cos(th1 + th2);
+  double A11 = .25 * m1 * A1 * A1 + m2 * (A1 * A1 + .25 * A2 * A2 + A1 * A2 * c2);
+  double A12 = .5 * m2 * (.5 * A2 * A2 + A1 * A2 * c2);
+  double A22 = .25 * m2 * A2 * A2;
+  a1[0] = A11 * dth1 + A12 * dth2;
+  a1[1] = A12 * dth1 + A22 * dth2;
+  double ccFact = m2 * A1 * A2 * sin(th2);
+  a2[0] = A11 * ddth1 + A12 * ddth2 - ccFact * dth2 * (dth1 + .5 * dth2);
+  a2[1] = A12 * ddth1 + A22 * ddth2 - .5 * ccFact * dth1 * dth1;
+  a3[0] = 10 * dth1;
+  a3[1] = 10 * dth2;
+  a4[0] = .5 * C_G * (m1 * A1 * c1 + m2 * (2.0 * A1 * c1 + A2 * c12));
+  a4[1] = .5 * C_G * m2 * A2 * c12;
+}
+/* a decoupled n-joint model (angles in degrees): tau_j = I_j thetaddot_j + b_j thetadot_j + g_j cos(theta_j), i.e.
+ * a1 = I theta', a2 = I theta'', a3 = b theta', a4 = g cos(theta) in the path parameter; inertias and gravity loads
+ * falling from the base to the wrist.  TEST MODEL for robots the reference has no dynamics for. */
+void orc_demo_dyn_serial(void *user, int n_joints, const double *theta, const double *thetaD, const double *thetaD2,
+                         double *a1, double *a2, double *a3, double *a4) {
+  (void)user;
+  for (int j = 0; j < n_joints; ++j) {
+    double I = 2.4 / (1.0 + j), bf = 1.5 / (1.0 + j), g = (j % 2 ? 18.0 : 3.0) / (1.0 + 0.5 * j);
+    double d1 = C_DEG2RAD * thetaD[j], d2 = C_DEG2RAD * thetaD2[j];
+    a1[j] = I * d1;
+    a2[j] = I * d2;
+    a3[j] = bf * d1;
+    a4[j] = g * cos(C_DEG2RAD * theta[j]);
   }
 }
 
@@ -1082,6 +1152,9 @@ static int ba_find_dyn_model(orc_traj *t) {
   if (t->isParallelMechOrig) {
     if (t->cfg.robot_type != BATOTP_CSPR3DOF) return -1;
     rb_dyn_cspr(t);
+  } else if (t->cfg.dyn_source == 1) {
+    if (!t->dynFn) return -1;
+    rb_dyn_callback(t);
   } else {
     if (t->cfg.robot_type != BATOTP_RR) return -1;
     rb_dyn_rr(t);
@@ -1708,7 +1781,10 @@ int orc_interp_output(orc_traj *t) {
         spl_interp_spline(&t->theta[i], &t->thetaD[i], &t->thetaD2[i], &t->thetaC[i], &sg, t->sres / t->outSmoothFact);
       }
       t->nPts = t->theta[0].n;
-      rb_dyn_rr(t);
+      if (t->cfg.dyn_source == 1)
+        rb_dyn_callback(t);
+      else
+        rb_dyn_rr(t);
       t->trqRows = J;
       for (int i = 0; i < J; ++i) {
         dv_resize(&t->trq[i], t->nPts);

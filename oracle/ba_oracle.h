@@ -51,6 +51,20 @@ int orc_optimize(orc_traj *t);                            /* ba.cpp:2538-2573 */
  * Must be called after orc_interp_input and before the sweeps. */
 int orc_mvc_per_sample(orc_traj *t, double sdot_start, double *sdot_out, int cap);
 
+/* cfg.dyn_source = 1: the generalized forces tau = a1*sddot + a2*sdot^2 + a3*sdot + a4 of a serial robot come from
+ * the caller's point function instead of Robot::call_dynSerial (robot.cpp:349-360; same arguments: the joint values
+ * and their first / second derivatives at one point in, a1..a4 out).  orc_demo_dyn_rr restates dynRR (robot.cpp:
+ * 377-431) behind that signature, so that the plug-in path can be pinned to the reference on the RR folder;
+ * orc_demo_dyn_serial is a decoupled n-joint model (inertia, viscous friction, a gravity-like term) for robots the
+ * reference has no model for (the KUKA torque variant of SURVEY 8d C3). */
+typedef void (*orc_dyn_fn)(void *user, int n_joints, const double *theta, const double *thetaD, const double *thetaD2,
+                           double *a1, double *a2, double *a3, double *a4);
+void orc_set_dyn_callback(orc_traj *t, orc_dyn_fn fn, void *user);
+void orc_demo_dyn_rr(void *user, int n_joints, const double *theta, const double *thetaD, const double *thetaD2,
+                     double *a1, double *a2, double *a3, double *a4);
+void orc_demo_dyn_serial(void *user, int n_joints, const double *theta, const double *thetaD, const double *thetaD2,
+                         double *a1, double *a2, double *a3, double *a4);
+
 /* vectors: returns length (copies min(len,cap)); -1 unknown name.
  * names: theta thetaD thetaD2 cart cartD cartD2 trq a1 a2 a3 a4 (idx = coordinate)
  *        sMVC sdot tMVC sC ptsOrig hist_s0 hist_sdot0 hist_s1 hist_sdot1 (idx ignored)

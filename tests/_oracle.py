@@ -53,6 +53,7 @@ def orc_lib():
             getattr(L, f).argtypes = [C.c_void_p]
         L.orc_sweep.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_mvc_per_sample.argtypes = [C.c_void_p, C.c_double, _dp, C.c_int]
+        L.orc_set_dyn_callback.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_get_vec.argtypes = [C.c_void_p, C.c_char_p, C.c_int, _dp, C.c_int]
         L.orc_get_scalar.argtypes = [C.c_void_p, C.c_char_p]
         L.orc_get_scalar.restype = C.c_double
@@ -65,6 +66,12 @@ def orc_lib():
                                     _dp, _ip, _ip, _ip, _ip, _fp, C.c_int]
         _orc = L
     return _orc
+
+
+def dyn_fn_address(name: str) -> int:
+    """Address of one of the oracle library's demonstration dynamics (orc_demo_dyn_rr, orc_demo_dyn_serial): the
+    same host function feeds the oracle and - through batotp_cuda_set_dyn_callback - the device path."""
+    return C.cast(getattr(orc_lib(), name), C.c_void_p).value
 
 
 _ref = None
@@ -143,6 +150,10 @@ class Oracle(_Base):
         ca = None if cart is None else np.ascontiguousarray(cart, dtype=np.float32)
         ts = None if timestamp is None else np.ascontiguousarray(timestamp, dtype=np.float64)
         return self.L.orc_load_raw(self.h, n0, tres, _ptr(th, _fp), _ptr(ca, _fp), _ptr(ts, _dp))
+
+    def set_dyn_callback(self, fn):
+        """fn: address of an orc_dyn_fn (e.g. dyn_fn_address("orc_demo_dyn_serial"))."""
+        self.L.orc_set_dyn_callback(self.h, C.cast(fn, C.c_void_p), None)
 
     def interp_input(self):
         return self.L.orc_interp_input(self.h)

@@ -90,8 +90,10 @@ def run_device(ctx, cfg, tres, th, ca, ts=None, n0=None, out_cap=32768, hist_cap
 
 
 class OracleRun:
-    def __init__(self, cfg, tres, th, ca, ts=None, n0=None):
+    def __init__(self, cfg, tres, th, ca, ts=None, n0=None, dyn_fn=None):
         self.o = Oracle(cfg)
+        if dyn_fn is not None:
+            self.o.set_dyn_callback(dyn_fn)
         ref = th if th is not None else ca
         n = ref.shape[1] if n0 is None else n0
         self.o.load_raw(n, tres, None if th is None else np.ascontiguousarray(th[:, :n]),

@@ -543,3 +543,46 @@ def test_two_context_pipeline_does_not_change_results(ctx):
         for k in ("verifies", "steps", "trajectories"):
             assert sa[k] == sb[k], k
     assert runs[0][1]["sweep_launches"] == 5 and runs[1][1]["sweep_launches"] == 6
+
+
+def _kuka_torque_cfg(cfg):
+    """The KUKA torque variant of SURVEY 8d C3: the stock KUKA options plus torque limits on a caller-supplied model."""
+    c = cfg.copy()
+    c.is_trq_on = 1
+    c.dyn_source = 1
+    for j, v in enumerate((60.0, 60.0, 30.0, 30.0, 15.0, 15.0, 8.0)):
+        c.jnt_trq_max[j] = v
+        c.jnt_trq_min[j] = -v
+    return c
+
+
+def test_caller_supplied_dynamics(ctx):
+    """cfg.dyn_source = 1 (batotp_cuda_set_dyn_callback): (a) dynRR behind the plug-in signature gives the reference's
+    RR files byte for byte; (b) the KUKA-LWR-IV stock path with torque limits on a 7-joint model the reference does
+    not have (k_sweep<7,true,true>): same host point function on both sides, device against the oracle bit for bit
+    - switching flags, torque rows and all - with the limits actually binding."""
+    from _oracle import dyn_fn_address
+    cfg, tres, th, ca, ts = P.load_stock("RR")
+    c1 = cfg.copy()
+    c1.dyn_source = 1
+    try:
+        ctx.set_dyn_callback(dyn_fn_address("orc_demo_dyn_rr"))
+        res = P.run_device(ctx, c1, tres, th, ca, ts)
+        d = P.GOLD + "/stock/RR"
+        assert P.device_traj_out_bytes(c1, res, 0) == open(d + "/ref_traj_out.dat", "rb").read()
+        assert P.device_s_sdot_bytes(res, 0) == open(d + "/ref_s-sdot.dat", "rb").read()
+        cfg, tres, th, ca, ts = P.load_stock("KUKA-LWR-IV")
+        plain = P.run_device(ctx, cfg, tres, th, ca, ts)
+        c2 = _kuka_torque_cfg(cfg)
+        fn = dyn_fn_address("orc_demo_dyn_serial")
+        ctx.set_dyn_callback(fn)
+        res = P.run_device(ctx, c2, tres, th, ca, ts)
+        orc = P.OracleRun(c2, tres, th[0], None, dyn_fn=fn)
+        assert orc.ok and res.status[0] & native.ST_FATAL_MASK == 0
+        assert P.compare(c2, res, 0, orc) == []
+        assert res.t_total[0] > plain.t_total[0]  # the torque limits bind: the move takes longer
+    finally:
+        ctx.set_dyn_callback(None)
+    c3 = _kuka_torque_cfg(cfg)
+    with pytest.raises(native.NativeError, match="dyn_source = 1 needs a point function"):
+        P.run_device(ctx, c3, tres, th, ca, ts)

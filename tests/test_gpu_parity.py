@@ -493,3 +493,65 @@ def test_per_sample_mvc_on_cartesian_and_torque_robots(ctx, name):
         want = o.mvc_per_sample(start)
         got = ctx.mvc_per_sample(1, len(want) + 8, start)
         assert np.array_equal(got[0, :len(want)], want), start
+
+
+def _kuka_torque_cfg(cfg):
+    """The KUKA torque variant of SURVEY 8d C3: the stock KUKA options plus torque limits on a caller-supplied model."""
+    c = cfg.copy()
+    c.is_trq_on = 1
+    c.dyn_source = 1
+    for j, v in enumerate((60.0, 60.0, 30.0, 30.0, 15.0, 15.0, 8.0)):
+        c.jnt_trq_max[j] = v
+        c.jnt_trq_min[j] = -v
+    return c
+
+
+def test_caller_supplied_dynamics(ctx):
+    """cfg.dyn_source = 1 (batotp_cuda_set_dyn_callback): (a) dynRR behind the plug-in signature gives the reference's
+    RR files byte for byte; (b) the KUKA-LWR-IV stock path with torque limits on a 7-joint model the reference does
+    not have (k_sweep<7,true,true>): same host point function on both sides, device against the oracle bit for bit
+    - switching flags, torque rows and all - with the limits actually binding."""
+    from _oracle import dyn_fn_address
+    cfg, tres, th, ca, ts = P.load_stock("RR")
+    c1 = cfg.copy()
+    c1.dyn_source = 1
+    try:
+        ctx.set_dyn_callback(dyn_fn_address("orc_demo_dyn_rr"))
+        res = P.run_device(ctx, c1, tres, th, ca, ts)
+        d = P.GOLD + "/stock/RR"
+        assert P.device_traj_out_bytes(c1, res, 0) == open(d + "/ref_traj_out.dat", "rb").read()
+        assert P.device_s_sdot_bytes(res, 0) == open(d + "/ref_s-sdot.dat", "rb").read()
+        cfg, tres, th, ca, ts = P.load_stock("KUKA-LWR-IV")
+        plain = P.run_device(ctx, cfg, tres, th, ca, ts)
+        c2 = _kuka_torque_cfg(cfg)
+        fn = dyn_fn_address("orc_demo_dyn_serial")
+        ctx.set_dyn_callback(fn)
+        res = P.run_device(ctx, c2, tres, th, ca, ts)
+        orc = P.OracleRun(c2, tres, th[0], None, dyn_fn=fn)
+        assert orc.ok and res.status[0] & native.ST_FATAL_MASK == 0
+        assert P.compare(c2, res, 0, orc) == []
+        assert res.t_total[0] > plain.t_total[0]  # the torque limits bind: the move takes longer
+    finally:
+        ctx.set_dyn_callback(None)
+    c3 = _kuka_torque_cfg(cfg)
+    with pytest.raises(native.NativeError, match="dyn_source = 1 needs a point function"):
+        P.run_device(ctx, c3, tres, th, ca, ts)
+
+
+def test_kuka_torque_variant_batch(ctx, sweep_kernel):
+    """SURVEY 8d C3, torque variant: synthetic KUKA paths with torque limits on a caller-supplied 7-joint model, both
+    sweep kernels (k_sweep<7,true,true> / k_sweep_group<7,true,true>), against the oracle fed the same point function."""
+    from _oracle import dyn_fn_address
+    B = 40
+    cfg, tres, th, _ = P.load_synth("KUKA", 300, B)
+    c2 = _kuka_torque_cfg(cfg)
+    fn = dyn_fn_address("orc_demo_dyn_serial")
+    try:
+        ctx.set_dyn_callback(fn)
+        res = P.run_device(ctx, c2, tres, th, None, out_cap=49152, hist_cap=49152)
+    finally:
+        ctx.set_dyn_callback(None)
+    assert (res.status & native.ST_FATAL_MASK == 0).all()
+    for b in range(0, B, 5):
+        orc = P.OracleRun(c2, tres, th[b], None, dyn_fn=fn)
+        assert orc.ok and P.compare(c2, res, b, orc) == [], b

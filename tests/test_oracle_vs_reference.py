@@ -197,3 +197,32 @@ def test_per_sample_mvc_is_the_reference_functions(name, start, tmp_path):
     assert len(a) == len(b) == int(o.scalar("nPtsC")) and len(a) > 100
     assert np.array_equal(a, b)
     assert np.isfinite(b).all() and b.max() <= start
+
+
+def test_caller_supplied_dynamics_reproduce_the_reference_on_rr(tmp_path):
+    """cfg.dyn_source = 1: a1..a4 come from the caller's point function instead of Robot::call_dynSerial.  With
+    dynRR restated behind that signature (orc_demo_dyn_rr) the plug-in path of the restatement must give what the
+    unmodified reference gives with its built-in model: grid tables, both sweeps, torque rows - bit for bit."""
+    from _oracle import dyn_fn_address
+    cfg, r, o = _pair("RR", tmp_path)
+    cfg2 = cfg.copy()
+    cfg2.dyn_source = 1
+    o = Oracle(cfg2)
+    _, tres, th, ca, ts = P.load_stock("RR")
+    o.load_raw(th.shape[2], tres, th[0], None, None)
+    o.set_dyn_callback(dyn_fn_address("orc_demo_dyn_rr"))
+    assert r.interp_input() == 0 and o.interp_input() == 0
+    for nm in ("a1", "a2", "a3", "a4", "a1C_m", "a4C_m"):
+        for j in range(2):
+            x, y = r.vec(nm, j), o.vec(nm, j)
+            if nm.endswith("_m"):
+                x, y = x[:-1], y[:-1]
+            assert np.array_equal(x, y), (nm, j)
+    for d, last in ((-1, 0), (1, 1)):
+        assert r.sweep(d, last) == 0 and o.sweep(d, last) == 0
+        assert np.array_equal(r.vec("sMVC"), o.vec("sMVC")) and np.array_equal(r.vec("sdot"), o.vec("sdot"))
+    r.interp_output()
+    o.interp_output()
+    for nm in ("theta", "trq"):
+        for j in range(2):
+            assert np.array_equal(r.vec(nm, j), o.vec(nm, j)), (nm, j)
