@@ -6,6 +6,7 @@
 // There is no CPU fallback in that library.  The same file compiles with g++ and
 // -DBATOTP_HOST_EMU into a TEST-ONLY emulation library (see emu.h) used by the CPU CI.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -183,6 +184,15 @@ struct batotp_ctx {
   // row pitch (points) of the packed float32 rows / histories: the caller's out_cap / hist_cap inside
   // batotp_cuda_optimize_batch (a sub-chunk then leaves in one contiguous copy), 0 = the device capacities
   int rowPitch = 0, histPitch = 0, capRowPitch = 0, capHistPitch = 0;
+  // ragged result layout (batotp_batch_out.row_offset): the blocks of a sub-chunk are packed back to back in the
+  // staging set and leave in one copy; where they go in the caller's buffer comes from a counter shared by the
+  // contexts that work on one batch
+  bool ragged = false;
+  std::atomic<long long> *ragNext = nullptr;
+  long long *d_ragOff = nullptr;       // [capBo + 1] prefix sums of the sub-chunk's output lengths (device)
+  std::vector<long long> ragOffHost;  // the same on the host
+  long long ragBase[NSETS] = {}, ragTotal[NSETS] = {};
+  int curSet = 0;
   int maxSteps = 65536;           // largest RK-step capacity the automatic retries grow to (per sweep)
   // cfg.dyn_source = 1: the caller's point function for a1..a4 (Robot::call_dynSerial's contract)
   batotp_dyn_fn dynFn = nullptr;
@@ -572,6 +582,7 @@ inline int row_pitch(const batotp_ctx *h) { return h->rowPitch > 0 ? h->rowPitch
 inline int hist_pitch(const batotp_ctx *h) { return h->histPitch > 0 ? h->histPitch : h->w.Sc; }
 
 void select_out_set(batotp_ctx *h, int q) {
+  h->curSet = q;
   h->d_thetaOut = h->o_thetaOut[q];
   h->d_cartOut = h->o_cartOut[q];
   h->d_trqOut = h->o_trqOut[q];
@@ -621,6 +632,7 @@ void ensure_out(batotp_ctx *h, int Bo, int minOutC = 0) {
     h->capRowPitch = rowP;
     h->capHistPitch = histP;
     select_out_set(h, 0);
+    h->d_ragOff = out_alloc<long long>(h, b + 1);
     h->d_cartOutD = (c.C == 7) ? out_alloc<double>(h, b * 7 * OutC) : nullptr;
     h->d_outD = h->keepF64 ? out_alloc<double>(h, b * (R + c.J) * OutC) : nullptr;
     h->capBo = Bo;
@@ -1199,7 +1211,8 @@ int do_interp_only(batotp_ctx *h, bool haveN0) {
     const int rp = row_pitch(h), hp = hist_pitch(h);
     if (h->d_trqOut) g_zero(h->d_trqOut, (size_t)h->B * c.J * rp * sizeof(float), h->stream);  // no torque rows here
     LAUNCH_PT(h, k_out_pack, std::max(w.OutC, rp), h->B, w, w.P, w.M, (double *)nullptr, (double *)nullptr, h->d_thetaOut,
-              h->d_cartOut, (float *)nullptr, strictQuat ? h->d_cartOutD : (double *)nullptr, h->d_outD, rp);
+              h->d_cartOut, (float *)nullptr, strictQuat ? h->d_cartOutD : (double *)nullptr, h->d_outD, rp,
+              (const long long *)nullptr);
     LAUNCH_PT(h, k_pack_hist, std::max(w.Sc, hp), h->B, w, h->d_histOut, hp);
     h->phase = 4;
     return 0;
@@ -1294,18 +1307,37 @@ void do_interp_output(batotp_ctx *h, int b0, int Bo) {
   }
   const bool strictQuat = (c.C == 7 && c.c.trig_mode != 0);
   const int rp = row_pitch(h), hp = hist_pitch(h);
+  const long long *rag = nullptr;
+  if (h->ragged) {
+    // ragged layout: prefix sums of the output lengths (device), read back so that the host can reserve the
+    // sub-chunk's place in the caller's buffer and size the copy; the blocks are packed back to back
+    {
+      ProfScope ps_(h, "k_rag_scan");
+      BATOTP_LAUNCH_WARP(k_rag_scan, dim3(1), dim3(256), 0, h->stream, w, h->d_ragOff, Bo);
+      g_check_launch();
+      h->launches++;
+    }
+    h->ragOffHost.resize((size_t)Bo + 1);
+    g_d2h(h->ragOffHost.data(), h->d_ragOff, ((size_t)Bo + 1) * sizeof(long long), h->stream);
+    g_sync(h->stream);
+    const long long total = h->ragOffHost[Bo];
+    h->ragTotal[h->curSet] = total;
+    h->ragBase[h->curSet] = h->ragNext->fetch_add(total);
+    rag = h->d_ragOff;
+  }
+  float *cartDst = h->ragged ? (float *)nullptr : h->d_cartOut;
   if (c.c.robot_type == BATOTP_GENJNT && c.C != 7 && c.Cin <= MAXD && !c.trqOn && !h->d_outD && rp > 0 && Bo > 0) {
     // generic robot, float rows only: warp-per-tile staging through shared memory (k_out_pack_rows)
     const long long rows = cdiv(Bo, OP_WARPS);
     const long long gy = std::min<long long>(rows, 32768), gz = (rows + gy - 1) / gy;
     ProfScope ps_(h, "k_out_pack_rows");
     BATOTP_LAUNCH_WARP(k_out_pack_rows, dim3((unsigned)cdiv(rp, 32), (unsigned)gy, (unsigned)gz),
-                       dim3(32, OP_WARPS, 1), 0, h->stream, w, cur, w.OM, h->d_thetaOut, h->d_cartOut, rp, rp, Bo);
+                       dim3(32, OP_WARPS, 1), 0, h->stream, w, cur, w.OM, h->d_thetaOut, cartDst, rp, rag, rp, Bo);
     g_check_launch();
     h->launches++;
   } else {
-    LAUNCH_PT(h, k_out_pack, std::max(w.OutC, rp), Bo, w, cur, w.OM, trqCur, w.TrqM, h->d_thetaOut, h->d_cartOut,
-              h->d_trqOut, strictQuat ? h->d_cartOutD : (double *)nullptr, h->d_outD, rp);
+    LAUNCH_PT(h, k_out_pack, std::max(w.OutC, rp), Bo, w, cur, w.OM, trqCur, w.TrqM, h->d_thetaOut, cartDst,
+              h->d_trqOut, strictQuat ? h->d_cartOutD : (double *)nullptr, h->d_outD, rp, rag);
   }
   LAUNCH_PT(h, k_pack_hist, std::max(w.Sc, hp), Bo, w, h->d_histOut, hp);
   h->phase = 4;
@@ -1972,6 +2004,7 @@ int batotp_cuda_load(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_
     h->lastHaveN0 = in->n0 != nullptr;
     h->inSet[0].src = h->inSet[1].src = nullptr;
     h->rowPitch = h->histPitch = 0;  // phase-wise calls pack at the device capacities
+    h->ragged = false;
     h->chunkFirst = 0;
     h->collectStragglers = false;
     const int rc = load_chunk(h, cfg, in, 0, in->B);
@@ -2059,10 +2092,27 @@ static void fetch_rows(batotp_handle h, batotp_batch_out *out, int first, cudaSt
   const Ws &w = h->w;
   const int Bo = w.Bo, g0 = first + w.b0;
   const size_t oc = (size_t)out->out_cap, rp = (size_t)row_pitch(h);
-  if (out->theta_out && oc > 0)
-    copy_rows(out->theta_out + (size_t)g0 * c.J * oc, oc, h->d_thetaOut, rp, (size_t)Bo * c.J, 4, cs);
-  if (out->trq_out && oc > 0 && c.trqOn)
-    copy_rows(out->trq_out + (size_t)g0 * c.J * oc, oc, h->d_trqOut, rp, (size_t)Bo * c.J, 4, cs);
+  if (h->ragged) {
+    // the sub-chunk's blocks, back to back in the staging set -> their place in the caller's buffer, in one copy;
+    // the offsets were computed when the sub-chunk was packed (do_interp_output)
+    const long long base = h->ragBase[h->curSet], total = h->ragTotal[h->curSet];
+    if (base + total > out->ragged_cap) {
+      char buf[160];
+      snprintf(buf, sizeof buf, "ragged_cap (%lld points) is too small: %lld points needed so far", out->ragged_cap,
+               base + total);
+      throw Err{buf};
+    }
+    for (int bl = 0; bl < Bo; ++bl) out->row_offset[g0 + bl] = base + h->ragOffHost[bl];
+    if (out->theta_out && total > 0)
+      g_d2h(out->theta_out + (size_t)base * c.J, h->d_thetaOut, (size_t)total * c.J * 4, cs);
+    if (out->trq_out && c.trqOn && total > 0)
+      g_d2h(out->trq_out + (size_t)base * c.J, h->d_trqOut, (size_t)total * c.J * 4, cs);
+  } else {
+    if (out->theta_out && oc > 0)
+      copy_rows(out->theta_out + (size_t)g0 * c.J * oc, oc, h->d_thetaOut, rp, (size_t)Bo * c.J, 4, cs);
+    if (out->trq_out && oc > 0 && c.trqOn)
+      copy_rows(out->trq_out + (size_t)g0 * c.J * oc, oc, h->d_trqOut, rp, (size_t)Bo * c.J, 4, cs);
+  }
   if (out->cart_out && oc > 0 && c.Cin > 0 && !(c.C == 7 && c.c.trig_mode != 0))
     copy_rows(out->cart_out + (size_t)g0 * c.Cin * oc, oc, h->d_cartOut, rp, (size_t)Bo * c.Cin, 4, cs);
   const size_t hc = (size_t)out->hist_cap, hp = (size_t)hist_pitch(h);
@@ -2104,7 +2154,8 @@ static void process_chunk(batotp_handle h, const batotp_cfg *cfg, const batotp_b
   h->lastHaveN0 = in->n0 != nullptr;
   h->chunkFirst = at;
   // the staging sets are packed at the caller's pitches: a sub-chunk then leaves in one contiguous copy
-  h->rowPitch = ((out->theta_out || out->cart_out || out->trq_out) && out->out_cap > 0) ? out->out_cap : 0;
+  h->ragged = out->row_offset != nullptr && h->ragNext != nullptr;
+  h->rowPitch = (!h->ragged && (out->theta_out || out->cart_out || out->trq_out) && out->out_cap > 0) ? out->out_cap : 0;
   h->histPitch = (out->hist && out->hist_cap > 0) ? out->hist_cap : 0;
   if (nextB > 0 && !in->on_device && !h->profile) {
     // the host rows of the next chunk travel while this one is computed
@@ -2285,7 +2336,10 @@ static void run_stragglers(batotp_handle h, const batotp_cfg *cfg, const batotp_
   in2.cart_f64 = f64 ? (const double *)pCa : nullptr;
   in2.timestamp = in->timestamp ? (in->on_device ? dTs : hTs.data()) : nullptr;
   // ---- results into host vectors with the caller's pitches
-  const size_t oc = (size_t)out->out_cap, hc = (size_t)out->hist_cap;
+  // (ragged layout: the stragglers are computed into a pitched temporary wide enough for the step ceiling and
+  // appended to the caller's buffer block by block)
+  const bool ragOut = out->row_offset != nullptr;
+  const size_t oc = ragOut ? (size_t)final_cap(h, h->maxSteps, 0) : (size_t)out->out_cap, hc = (size_t)out->hist_cap;
   std::vector<int> oI[6];
   std::vector<double> oD[4];
   for (auto &v : oI) v.assign(n, 0);
@@ -2294,7 +2348,7 @@ static void run_stragglers(batotp_handle h, const batotp_cfg *cfg, const batotp_
   std::vector<unsigned char> oFl;
   batotp_batch_out o2;
   memset(&o2, 0, sizeof(o2));
-  o2.out_cap = out->out_cap;
+  o2.out_cap = (int)oc;
   o2.hist_cap = out->hist_cap;
   o2.status = oI[0].data();
   o2.n_rev = oI[1].data();
@@ -2312,6 +2366,8 @@ static void run_stragglers(batotp_handle h, const batotp_cfg *cfg, const batotp_
   if (out->hist && hc) { oHist.assign((size_t)n * 4 * hc, 0.f); o2.hist = oHist.data(); }
   if (out->flags && hc) { oFl.assign((size_t)n * 2 * hc, 0); o2.flags = oFl.data(); }
   // ---- run them as one chunk with a larger step capacity; the capacity marks of the batch are put back after
+  std::atomic<long long> *const keepRag = h->ragNext;
+  h->ragNext = nullptr;  // the temporary is pitched
   const int keepHwSc = h->hwSc;
   const bool keepCollect = h->collectStragglers;
   h->collectStragglers = false;
@@ -2331,10 +2387,12 @@ static void run_stragglers(batotp_handle h, const batotp_cfg *cfg, const batotp_
   } catch (...) {
     h->hwSc = keepHwSc;
     h->collectStragglers = keepCollect;
+    h->ragNext = keepRag;
     throw;
   }
   h->hwSc = keepHwSc;
   h->collectStragglers = keepCollect;
+  h->ragNext = keepRag;
   free_ws(h);  // the large-capacity workspace is not what the next batch needs
   free_out(h);
   // ---- scatter
@@ -2353,9 +2411,20 @@ static void run_stragglers(batotp_handle h, const batotp_cfg *cfg, const batotp_
       if (dI[q]) put(dI[q] + g, &oI[q][k], sizeof(int));
     for (int q = 0; q < 4; ++q)
       if (dD[q]) put(dD[q] + g, &oD[q][k], sizeof(double));
-    if (o2.theta_out) put(out->theta_out + g * J * oc, oTh.data() + (size_t)k * J * oc, (size_t)J * oc * 4);
-    if (o2.cart_out) put(out->cart_out + g * Cin * oc, oCa.data() + (size_t)k * Cin * oc, (size_t)Cin * oc * 4);
-    if (o2.trq_out) put(out->trq_out + g * J * oc, oTq.data() + (size_t)k * J * oc, (size_t)J * oc * 4);
+    if (ragOut) {
+      const long long nn = oI[3][k];  // n_out
+      const long long base = keepRag->fetch_add(nn);
+      if (base + nn > out->ragged_cap) throw Err{"ragged_cap is too small for the re-run stragglers"};
+      out->row_offset[g] = base;
+      for (int r = 0; r < J; ++r) {
+        if (o2.theta_out) memcpy(out->theta_out + (size_t)base * J + (size_t)r * nn, oTh.data() + ((size_t)k * J + r) * oc, (size_t)nn * 4);
+        if (o2.trq_out) memcpy(out->trq_out + (size_t)base * J + (size_t)r * nn, oTq.data() + ((size_t)k * J + r) * oc, (size_t)nn * 4);
+      }
+    } else {
+      if (o2.theta_out) put(out->theta_out + g * J * oc, oTh.data() + (size_t)k * J * oc, (size_t)J * oc * 4);
+      if (o2.cart_out) put(out->cart_out + g * Cin * oc, oCa.data() + (size_t)k * Cin * oc, (size_t)Cin * oc * 4);
+      if (o2.trq_out) put(out->trq_out + g * J * oc, oTq.data() + (size_t)k * J * oc, (size_t)J * oc * 4);
+    }
     if (o2.hist) put(out->hist + g * 4 * hc, oHist.data() + (size_t)k * 4 * hc, 4 * hc * 4);
     if (o2.flags) put(out->flags + g * 2 * hc, oFl.data() + (size_t)k * 2 * hc, 2 * hc);
   }
@@ -2371,6 +2440,27 @@ static void run_stragglers(batotp_handle h, const batotp_cfg *cfg, const batotp_
 int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_in *in,
                                batotp_batch_out *out) {
   if (!h || !cfg || !in || !out) return -1;
+  std::atomic<long long> ragCounter{0};  // ragged layout: the next free point of the caller's row buffers
+  h->ragNext = nullptr;
+  if (out->row_offset) {
+    if (out->on_device || out->cart_out || !out->theta_out || out->ragged_cap <= 0 || cfg->is_interp_only) {
+      h->err = "ragged rows (row_offset): host buffers, theta_out (+ trq_out) only, cart_out = NULL, ragged_cap > 0, "
+               "not with isInterpOnly";
+      return -1;
+    }
+    h->ragNext = &ragCounter;
+  }
+  struct RagReset {
+    batotp_ctx *h;
+    ~RagReset() {
+      h->ragNext = nullptr;
+      h->ragged = false;
+      if (h->helper) {
+        h->helper->ragNext = nullptr;
+        h->helper->ragged = false;
+      }
+    }
+  } ragReset{h};
   bool first = true;
   int chunk = h->chunk > 0 ? h->chunk : auto_chunk(h, in->B);
   int mainB = in->B, tail = 0;
@@ -2425,6 +2515,7 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
           hp->sweepKernel = h->sweepKernel;
           hp->dynFn = h->dynFn;
           hp->dynUser = h->dynUser;
+          hp->ragNext = h->ragNext;
           hp->stragglers.clear();
           hp->stragglerSc = 0;
           hp->collectStragglers = true;
@@ -2523,6 +2614,7 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
           hp->sweepKernel = h->sweepKernel;
           hp->dynFn = h->dynFn;
           hp->dynUser = h->dynUser;
+          hp->ragNext = h->ragNext;
           hp->stragglers.clear();
           hp->stragglerSc = 0;
           hp->collectStragglers = true;

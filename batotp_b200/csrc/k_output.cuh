@@ -705,20 +705,26 @@ __host__ __device__ inline void q2aa_dev(const double q[4], double aa[3]) {
 // points fastest so that the float rows are written coalesced)
 // `pitch` = row stride (points) of the float32 outputs: the caller's out_cap when the rows travel on, so that a
 // sub-chunk leaves in one contiguous copy; the FP64 side outputs (cartOutD, outD) keep the capacity w.OutC.
+// `rag` (optional): ragged layout - trajectory bl's joint / torque block starts at rag[bl]*J floats and is
+// [J][nOut] with no padding (cartOut must be NULL then); see batotp_batch_out.row_offset.
 __global__ void k_out_pack(WSP, double *src, double *srcM, double *trqSrc, double *trqM, float *thetaOut,
-                           float *cartOut, float *trqOut, double *cartOutD, double *outD, int pitch, int npts, int nb) {
+                           float *cartOut, float *trqOut, double *cartOutD, double *outD, int pitch,
+                           const long long *rag, int npts, int nb) {
   PT_DECOMP(npts);
   if (bl >= nb) return;
   const TrajState &s = w.st[w.b0 + bl];
   const int J = CFG.J, C = CFG.C, Cin = CFG.Cin;
-  const bool inF = i < pitch, inD = i < w.OutC;
-  if (!inF && !inD) return;
   const bool fatal = (s.status & ST_FATAL_MASK) != 0;
+  // float rows: pitched [bl][row][pitch], or ragged [rag[bl]*J + row*nOut]
+  const size_t fBase = rag ? (size_t)rag[bl] * J : (size_t)bl * J * pitch;
+  const size_t fRow = rag ? (size_t)(fatal ? 0 : s.nOut) : (size_t)pitch;
+  const bool inF = rag ? (!fatal && i < s.nOut) : (i < pitch), inD = i < w.OutC;
+  if (!inF && !inD) return;
   // rows are zero beyond their length (and for trajectories that were not optimised)
   if ((fatal || i >= s.nOut) && inF) {
-    for (int r = 0; r < J; ++r) thetaOut[((size_t)bl * J + r) * pitch + i] = 0.f;
+    for (int r = 0; r < J; ++r) thetaOut[fBase + (size_t)r * fRow + i] = 0.f;
     if (trqOut && CFG.trqOn)
-      for (int r = 0; r < J; ++r) trqOut[((size_t)bl * J + r) * pitch + i] = 0.f;
+      for (int r = 0; r < J; ++r) trqOut[fBase + (size_t)r * fRow + i] = 0.f;
   }
   if (fatal || i >= s.nCartOut) {
     if (cartOut && inF)
@@ -746,7 +752,7 @@ __global__ void k_out_pack(WSP, double *src, double *srcM, double *trqSrc, doubl
         v = seg_value(seg_coef(orowv(src, w, bl, r), orowv(srcM, w, bl, r), seg), tau, tau2, tau3);
       else
         v = orowv(src, w, bl, r)[i];
-      if (inF) thetaOut[((size_t)bl * J + r) * pitch + i] = (float)v;
+      if (inF) thetaOut[fBase + (size_t)r * fRow + i] = (float)v;
       if (outD) outD[((size_t)bl * (CFG.R + J) + r) * w.OutC + i] = v;
     }
     if (trqOut && CFG.trqOn)
@@ -756,7 +762,7 @@ __global__ void k_out_pack(WSP, double *src, double *srcM, double *trqSrc, doubl
           v = seg_value(seg_coef(trqv(trqSrc, w, bl, r), trqv(trqM, w, bl, r), seg), tau, tau2, tau3);
         else
           v = trqv(trqSrc, w, bl, r)[i];
-        if (inF) trqOut[((size_t)bl * J + r) * pitch + i] = (float)v;
+        if (inF) trqOut[fBase + (size_t)r * fRow + i] = (float)v;
         if (outD) outD[((size_t)bl * (CFG.R + J) + CFG.R + r) * w.OutC + i] = v;
       }
   }
@@ -800,8 +806,8 @@ struct SView {
   int st;
   __host__ __device__ __forceinline__ double operator[](int i) const { return p[i * st]; }
 };
-__global__ void k_out_pack_rows(WSP, double *src, double *srcM, float *thetaOut, float *cartOut, int pitch, int npts,
-                                int nb) {
+__global__ void k_out_pack_rows(WSP, double *src, double *srcM, float *thetaOut, float *cartOut, int pitch,
+                                const long long *rag, int npts, int nb) {
   EMU_SHARED double sY[OP_WARPS][OP_CAP * MAXD];
   EMU_SHARED double sM[OP_WARPS][OP_CAP * MAXD];
   const int lane = threadIdx.x, wy = threadIdx.y;
@@ -816,6 +822,9 @@ __global__ void k_out_pack_rows(WSP, double *src, double *srcM, float *thetaOut,
   // ---------------- joint rows
   const int nOut = fatal ? 0 : imin_(s.nOut, npts);
   const bool live = i < nOut;
+  // float rows: pitched [bl][row][pitch], or ragged (rag[bl]*J + row*nOut: no padding, nothing beyond the length)
+  const size_t fBase = rag ? (size_t)rag[bl] * J : (size_t)bl * J * pitch;
+  const size_t fRow = rag ? (size_t)(fatal ? 0 : s.nOut) : (size_t)pitch;
   if (i0 < nOut) {  // warp-uniform
     const bool re = s.isReinterp != 0;
     int seg = live ? i : nOut - 1;
@@ -851,7 +860,7 @@ __global__ void k_out_pack_rows(WSP, double *src, double *srcM, float *thetaOut,
             v = seg_value(seg_coef(SView{&sY[wy][o + r], J}, SView{&sM[wy][o + r], J}, 0), tau, tau2, tau3);
           else
             v = sY[wy][o + r];
-          thetaOut[((size_t)bl * J + r) * pitch + i] = (float)v;
+          thetaOut[fBase + (size_t)r * fRow + i] = (float)v;
         }
       }
       __syncwarp();  // the staging buffer is reused below
@@ -862,12 +871,12 @@ __global__ void k_out_pack_rows(WSP, double *src, double *srcM, float *thetaOut,
           v = seg_value(seg_coef(orowv(src, w, bl, r), orowv(srcM, w, bl, r), seg), tau, tau2, tau3);
         else
           v = orowv(src, w, bl, r)[i];
-        thetaOut[((size_t)bl * J + r) * pitch + i] = (float)v;
+        thetaOut[fBase + (size_t)r * fRow + i] = (float)v;
       }
     }
   }
-  if (!live && inRange)  // rows are zero beyond their length (and for trajectories that were not optimised)
-    for (int r = 0; r < J; ++r) thetaOut[((size_t)bl * J + r) * pitch + i] = 0.f;
+  if (!live && inRange && !rag)  // rows are zero beyond their length (and for trajectories that were not optimised)
+    for (int r = 0; r < J; ++r) thetaOut[fBase + (size_t)r * fRow + i] = 0.f;
   // ---------------- Cartesian rows (generic robot: the source rows J.. at the same index, no re-interpolation)
   if (Cin > 0 && cartOut) {
     const int nC = fatal ? 0 : imin_(s.nCartOut, npts);
@@ -926,6 +935,38 @@ __global__ void k_pack_hist(WSP, float *histOut, int pitch, int npts, int nb) {
     }
     if (inS) fl[(size_t)w.Sc + i] = 0;
   }
+}
+
+// Ragged result layout: exclusive prefix sums of the output lengths of the sub-chunk (0 for a trajectory that was
+// not optimised) -> off[0..nb-1], total in off[nb].  One CTA; lengths are summed in chunks of blockDim.x.  (T)
+__global__ void k_rag_scan(WSP, long long *off, int nb) {
+  EMU_SHARED long long part[1024];
+  EMU_SHARED long long carry;
+  const int t = threadIdx.x, nt = blockDim.x;
+  if (t == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += nt) {
+    const int bl = base + t;
+    long long v = 0;
+    if (bl < nb) {
+      const TrajState &s = w.st[w.b0 + bl];
+      v = (s.status & ST_FATAL_MASK) ? 0 : s.nOut;
+    }
+    part[t] = v;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the CTA
+    for (int d = 1; d < nt; d <<= 1) {
+      const long long x = (t >= d) ? part[t - d] : 0;
+      __syncthreads();
+      part[t] += x;
+      __syncthreads();
+    }
+    if (bl < nb) off[bl] = carry + part[t] - v;
+    __syncthreads();
+    if (t == nt - 1) carry += part[t];
+    __syncthreads();
+  }
+  if (t == 0) off[nb] = carry;
 }
 
 // per-trajectory scalars of the output sub-chunk -> the caller's arrays when those live on the device

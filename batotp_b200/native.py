@@ -36,7 +36,8 @@ class BatchOut(C.Structure):
     _fields_ = [("out_cap", C.c_int), ("hist_cap", C.c_int), ("status", _ip), ("n_rev", _ip), ("n_fwd", _ip),
                 ("n_out", _ip), ("n_cart_out", _ip), ("n_grid", _ip), ("t_total", _dp), ("t_rev", _dp),
                 ("s_last_sec", _dp), ("out_sres", _dp), ("theta_out", C.c_void_p), ("cart_out", C.c_void_p),
-                ("trq_out", C.c_void_p), ("hist", C.c_void_p), ("flags", C.c_void_p), ("on_device", C.c_int)]
+                ("trq_out", C.c_void_p), ("hist", C.c_void_p), ("flags", C.c_void_p), ("on_device", C.c_int),
+                ("row_offset", C.POINTER(C.c_longlong)), ("ragged_cap", C.c_longlong)]
 
 
 class NativeError(RuntimeError):
@@ -138,7 +139,10 @@ class BatchResult:
     """Host-side view of a batotp_batch_out."""
 
     def __init__(self, B: int, J: int, Cin: int, out_cap: int, hist_cap: int, trq: bool, want_rows=True,
-                 want_hist=True, pinned=False):
+                 want_hist=True, pinned=False, ragged_cap: int = 0):
+        """ragged_cap > 0: ragged joint / torque rows (batotp_batch_out.row_offset): theta_out is a flat float32
+        array of ragged_cap * J values, trajectory b's block is rows(b) = theta_out[row_offset[b]*J ...] viewed as
+        [J, n_out[b]]; no Cartesian rows in this mode."""
         def arr(shape, dt):
             if pinned:
                 import torch
@@ -160,9 +164,17 @@ class BatchResult:
         self.t_rev = arr(B, np.float64)
         self.s_last_sec = arr(B, np.float64)
         self.out_sres = arr(B, np.float64)
-        self.theta_out = arr((B, J, out_cap), np.float32) if want_rows else None
-        self.cart_out = arr((B, max(Cin, 1), out_cap), np.float32) if (want_rows and Cin > 0) else None
-        self.trq_out = arr((B, J, out_cap), np.float32) if (want_rows and trq) else None
+        self.ragged_cap = int(ragged_cap)
+        if ragged_cap > 0:
+            self.theta_out = arr((ragged_cap * J,), np.float32)
+            self.cart_out = None
+            self.trq_out = arr((ragged_cap * J,), np.float32) if trq else None
+            self.row_offset = arr(B, np.int64)
+        else:
+            self.theta_out = arr((B, J, out_cap), np.float32) if want_rows else None
+            self.cart_out = arr((B, max(Cin, 1), out_cap), np.float32) if (want_rows and Cin > 0) else None
+            self.trq_out = arr((B, J, out_cap), np.float32) if (want_rows and trq) else None
+            self.row_offset = None
         self.hist = arr((B, 4, hist_cap), np.float32) if want_hist else None
         self.flags = arr((B, 2, hist_cap), np.uint8) if want_hist else None
         self.c = BatchOut()
@@ -175,6 +187,19 @@ class BatchResult:
             a = getattr(self, nm)
             setattr(self.c, nm, a.ctypes.data if a is not None else None)
         self.c.on_device = 0
+        if self.row_offset is not None:
+            self.c.row_offset = self.row_offset.ctypes.data_as(C.POINTER(C.c_longlong))
+            self.c.ragged_cap = self.ragged_cap
+            self.c.out_cap = 0
+
+    def rows(self, b: int, which: str = "theta_out") -> np.ndarray:
+        """[J, n_out[b]] view of trajectory b's rows (either layout)."""
+        a = getattr(self, which)
+        n = int(self.n_out[b])
+        if self.row_offset is None:
+            return a[b, :, :n]
+        o = int(self.row_offset[b]) * self.J
+        return a[o:o + self.J * n].reshape(self.J, n)
 
     def d2h_bytes(self) -> int:
         n = 0

@@ -89,6 +89,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-path latency block")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--pitched", action="store_true",
+                    help="e2e leg: rows at the pitch of the longest trajectory instead of the ragged layout")
     ap.add_argument("--lib", default=None, help="experiments only: alternative build of libbatotp_cuda.so")
     return ap.parse_args()
 
@@ -461,14 +463,22 @@ def main_b200(args):
     out_cap = int(res_s.n_out.max()) if ok else 4096
     h_np = h_pay.numpy()
     want_cart = cfg.n_cart > 0 and wl != "gen7dof"  # a generic robot has no Cartesian data: its rows are zeros
+    # ragged layout (the default where no Cartesian rows travel): every trajectory's [J][n_out] block at its own
+    # length, so no padding crosses the host link; the capacity is the sum of the lengths (known from the resident leg)
+    ragged = not args.pitched and not want_cart
+    rag_cap = int(res_s.n_out.astype(np.int64).sum()) + 1024
     sl = B
     res_e = None
     while res_e is None:
         try:
-            res_e = native.BatchResult(sl, J, cfg.n_cart if want_cart else 0, out_cap, 0, bool(cfg.is_trq_on),
-                                       want_rows=True, want_hist=False, pinned=True)
+            if ragged:
+                res_e = native.BatchResult(sl, J, 0, 0, 0, bool(cfg.is_trq_on), want_rows=True, want_hist=False,
+                                           pinned=True, ragged_cap=rag_cap)
+            else:
+                res_e = native.BatchResult(sl, J, cfg.n_cart if want_cart else 0, out_cap, 0, bool(cfg.is_trq_on),
+                                           want_rows=True, want_hist=False, pinned=True)
         except Exception:
-            if sl <= 1024:
+            if sl <= 1024 or ragged:
                 raise
             sl = (sl + 1) // 2
 
@@ -493,11 +503,18 @@ def main_b200(args):
         torch.cuda.synchronize()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         nsl = (B + sl - 1) // sl
+        if ragged:
+            rows_b = int(res_s.n_out.astype(np.int64).sum()) * J * 4 * (2 if cfg.is_trq_on else 1)
+            d2h_b = rows_b + sum(getattr(res_e, nm).nbytes for nm in ("status", "n_rev", "n_fwd", "n_out", "n_cart_out",
+                                                                       "n_grid", "t_total", "t_rev", "s_last_sec", "out_sres"))
+        else:
+            d2h_b = nsl * res_e.d2h_bytes()
         e2e = dict(value=total * args.steps / e2e_s, unit=UNIT, h2d_bytes_per_step=int(payload.nbytes),
-                   d2h_bytes_per_step=int(nsl * res_e.d2h_bytes()),
+                   d2h_bytes_per_step=int(d2h_b),
                    note="C-ABI batotp_cuda_optimize_batch on pinned host buffers, %d call(s) of %d paths per step per rank; "
-                        "float32 rows (pitch %d points = the longest trajectory) + per-trajectory scalars copied back; "
-                        "bytes per rank" % (nsl, sl, out_cap))
+                        "float32 rows (%s) + per-trajectory scalars copied back; bytes per rank"
+                        % (nsl, sl, "ragged: every trajectory at its own length, the payload of trajWriteBIN" if ragged
+                           else "pitch %d points = the longest trajectory" % out_cap))
 
     line = None
     if rank == 0:

@@ -163,6 +163,15 @@ typedef struct batotp_batch_out {
                             bits0-2 sub-steps limited by a velocity limit/MVC (ba.cpp:1093),
                             bits3-5 sub-steps with an active bisection, bit6 isOn_sdot (ba.cpp:1211) */
   int on_device;         /* 1: the pointers above are device pointers */
+  /* Ragged rows (optional; batotp_cuda_optimize_batch only).  With row_offset != NULL the float32 joint rows are
+   * packed at their own length instead of the pitch out_cap: trajectory g's block is
+   *     theta_out[row_offset[g] * nJoints ...] = [nJoints][n_out[g]]
+   * - exactly the joint payload trajWriteBIN writes (ba.cpp:2617-2647) - and trq_out likewise; blocks are laid out in
+   * completion order (row_offset says where), ragged_cap is the capacity of theta_out / trq_out in POINTS
+   * (sum of n_out over the batch; the call fails when it does not suffice).  No padding crosses the host link.
+   * cart_out must be NULL in this mode; host buffers only. */
+  long long *row_offset; /* [B] out: first point of trajectory g's block */
+  long long ragged_cap;  /* in: capacity in points */
 } batotp_batch_out;
 
 /* BA::optimize (ba.cpp:2538-2573) over a batch: interpInputData -> sweep(-1) -> sweep(+1) ->

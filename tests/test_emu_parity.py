@@ -586,3 +586,39 @@ def test_caller_supplied_dynamics(ctx):
     c3 = _kuka_torque_cfg(cfg)
     with pytest.raises(native.NativeError, match="dyn_source = 1 needs a point function"):
         P.run_device(ctx, c3, tres, th, ca, ts)
+
+
+def test_ragged_rows_hold_the_same_samples(ctx):
+    """batotp_batch_out.row_offset: joint rows packed at their own length ([J][n_out] blocks, the payload of
+    trajWriteBIN) instead of the pitch of the longest trajectory - same float32 samples as the pitched layout, blocks
+    disjoint and inside the capacity, also across chunks, output sub-chunks, the tail helper and re-run stragglers."""
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 400, 21)
+    a = P.run_device(ctx, cfg, tres, th, None, out_cap=4096, hist_cap=64)
+    total = int(a.n_out.sum())
+    steps = np.sort(np.maximum(a.n_rev, a.n_fwd))
+    ctx.set_chunk(8)
+    ctx.set_out_chunk(3)
+    try:
+        for hint in (0, int(steps[-3])):
+            ctx.set_step_hint(hint)
+            b = native.BatchResult(21, cfg.n_joints, cfg.n_cart, 0, 0, False, want_hist=False, ragged_cap=total + 5)
+            ctx.optimize_batch(cfg, ctx.make_in(th, None, tres), b)
+            assert np.array_equal(a.n_out, b.n_out) and np.array_equal(a.t_total, b.t_total)
+            spans = sorted((int(b.row_offset[k]), int(b.row_offset[k]) + int(b.n_out[k])) for k in range(21))
+            assert spans[0][0] >= 0 and spans[-1][1] <= total and all(x[1] <= y[0] for x, y in zip(spans, spans[1:]))
+            for k in range(21):
+                assert np.array_equal(b.rows(k), a.theta_out[k, :, :a.n_out[k]]), k
+        small = native.BatchResult(21, cfg.n_joints, cfg.n_cart, 0, 0, False, want_hist=False, ragged_cap=total // 2)
+        with pytest.raises(native.NativeError, match="ragged_cap"):
+            ctx.optimize_batch(cfg, ctx.make_in(th, None, tres), small)
+    finally:
+        ctx.set_step_hint(0)
+        ctx.set_chunk(16384)
+        ctx.set_out_chunk(8192)
+    # torque rows travel the same way (RR: serial torque)
+    cfg, tres, th, ca, ts = P.load_stock("RR")
+    p = P.run_device(ctx, cfg, tres, th, ca, ts)
+    r = native.BatchResult(1, cfg.n_joints, cfg.n_cart, 0, 0, True, want_hist=False, ragged_cap=4096)
+    ctx.optimize_batch(cfg, ctx.make_in(th, ca, tres, timestamp=ts), r)
+    n = int(p.n_out[0])
+    assert np.array_equal(r.rows(0), p.theta_out[0, :, :n]) and np.array_equal(r.rows(0, "trq_out"), p.trq_out[0, :, :n])
