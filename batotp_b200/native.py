@@ -147,7 +147,7 @@ class BatchResult:
             if pinned:
                 import torch
                 t = torch.zeros(shape, dtype={np.float32: torch.float32, np.float64: torch.float64,
-                                              np.int32: torch.int32, np.uint8: torch.uint8}[dt]).pin_memory()
+                                              np.int32: torch.int32, np.int64: torch.int64, np.uint8: torch.uint8}[dt]).pin_memory()
                 self._keep.append(t)
                 return t.numpy()
             return np.zeros(shape, dtype=dt)
