@@ -189,8 +189,8 @@ struct batotp_ctx {
   // contexts that work on one batch
   bool ragged = false;
   std::atomic<long long> *ragNext = nullptr;
-  long long *d_ragOff = nullptr;       // [capBo + 1] prefix sums of the sub-chunk's output lengths (device)
-  std::vector<long long> ragOffHost;  // the same on the host
+  std::vector<long long> ragOffHost;  // [B + 1] prefix sums of the resident chunk's output lengths (w.ragOff on the device)
+  long long ragChunkBase = 0;         // where the chunk's blocks start in the caller's buffers
   long long ragBase[NSETS] = {}, ragTotal[NSETS] = {};
   int curSet = 0;
   int maxSteps = 65536;           // largest RK-step capacity the automatic retries grow to (per sweep)
@@ -569,6 +569,7 @@ void ensure_ws(batotp_ctx *h, int B, int Nc, int Sc) {
     g_zero(w.A, b * 4 * MAXD * Nc * sizeof(double), h->stream);
   }
   w.queue = ws_alloc<int>(h, 4);
+  w.ragOff = ws_alloc<long long>(h, b + 1);
   h->capB = B;
   h->capNc = Nc;
   h->capSc = Sc;
@@ -632,7 +633,6 @@ void ensure_out(batotp_ctx *h, int Bo, int minOutC = 0) {
     h->capRowPitch = rowP;
     h->capHistPitch = histP;
     select_out_set(h, 0);
-    h->d_ragOff = out_alloc<long long>(h, b + 1);
     h->d_cartOutD = (c.C == 7) ? out_alloc<double>(h, b * 7 * OutC) : nullptr;
     h->d_outD = h->keepF64 ? out_alloc<double>(h, b * (R + c.J) * OutC) : nullptr;
     h->capBo = Bo;
@@ -1212,7 +1212,7 @@ int do_interp_only(batotp_ctx *h, bool haveN0) {
     if (h->d_trqOut) g_zero(h->d_trqOut, (size_t)h->B * c.J * rp * sizeof(float), h->stream);  // no torque rows here
     LAUNCH_PT(h, k_out_pack, std::max(w.OutC, rp), h->B, w, w.P, w.M, (double *)nullptr, (double *)nullptr, h->d_thetaOut,
               h->d_cartOut, (float *)nullptr, strictQuat ? h->d_cartOutD : (double *)nullptr, h->d_outD, rp,
-              (const long long *)nullptr);
+              (const long long *)nullptr, 0ll);
     LAUNCH_PT(h, k_pack_hist, std::max(w.Sc, hp), h->B, w, h->d_histOut, hp);
     h->phase = 4;
     return 0;
@@ -1308,22 +1308,15 @@ void do_interp_output(batotp_ctx *h, int b0, int Bo) {
   const bool strictQuat = (c.C == 7 && c.c.trig_mode != 0);
   const int rp = row_pitch(h), hp = hist_pitch(h);
   const long long *rag = nullptr;
+  long long rag0 = 0;
   if (h->ragged) {
-    // ragged layout: prefix sums of the output lengths (device), read back so that the host can reserve the
-    // sub-chunk's place in the caller's buffer and size the copy; the blocks are packed back to back
-    {
-      ProfScope ps_(h, "k_rag_scan");
-      BATOTP_LAUNCH_WARP(k_rag_scan, dim3(1), dim3(256), 0, h->stream, w, h->d_ragOff, Bo);
-      g_check_launch();
-      h->launches++;
-    }
-    h->ragOffHost.resize((size_t)Bo + 1);
-    g_d2h(h->ragOffHost.data(), h->d_ragOff, ((size_t)Bo + 1) * sizeof(long long), h->stream);
-    g_sync(h->stream);
-    const long long total = h->ragOffHost[Bo];
-    h->ragTotal[h->curSet] = total;
-    h->ragBase[h->curSet] = h->ragNext->fetch_add(total);
-    rag = h->d_ragOff;
+    // ragged layout: the chunk's block offsets were computed on the host from the sweep results (plan_ragged: the
+    // output length is a function of the step count) and uploaded once; the sub-chunk's blocks are packed back to
+    // back in the staging set, i.e. relative to the first of them
+    rag = h->w.ragOff + b0;
+    rag0 = h->ragOffHost[b0];
+    h->ragBase[h->curSet] = h->ragChunkBase + rag0;
+    h->ragTotal[h->curSet] = h->ragOffHost[b0 + Bo] - rag0;
   }
   float *cartDst = h->ragged ? (float *)nullptr : h->d_cartOut;
   if (c.c.robot_type == BATOTP_GENJNT && c.C != 7 && c.Cin <= MAXD && !c.trqOn && !h->d_outD && rp > 0 && Bo > 0) {
@@ -1332,12 +1325,12 @@ void do_interp_output(batotp_ctx *h, int b0, int Bo) {
     const long long gy = std::min<long long>(rows, 32768), gz = (rows + gy - 1) / gy;
     ProfScope ps_(h, "k_out_pack_rows");
     BATOTP_LAUNCH_WARP(k_out_pack_rows, dim3((unsigned)cdiv(rp, 32), (unsigned)gy, (unsigned)gz),
-                       dim3(32, OP_WARPS, 1), 0, h->stream, w, cur, w.OM, h->d_thetaOut, cartDst, rp, rag, rp, Bo);
+                       dim3(32, OP_WARPS, 1), 0, h->stream, w, cur, w.OM, h->d_thetaOut, cartDst, rp, rag, rag0, rp, Bo);
     g_check_launch();
     h->launches++;
   } else {
     LAUNCH_PT(h, k_out_pack, std::max(w.OutC, rp), Bo, w, cur, w.OM, trqCur, w.TrqM, h->d_thetaOut, cartDst,
-              h->d_trqOut, strictQuat ? h->d_cartOutD : (double *)nullptr, h->d_outD, rp, rag);
+              h->d_trqOut, strictQuat ? h->d_cartOutD : (double *)nullptr, h->d_outD, rp, rag, rag0);
   }
   LAUNCH_PT(h, k_pack_hist, std::max(w.Sc, hp), Bo, w, h->d_histOut, hp);
   h->phase = 4;
@@ -1926,6 +1919,40 @@ static int chunk_interp_input(batotp_handle h, bool haveN0) {
   return -1;
 }
 
+// Ragged result layout: the output length of a trajectory follows from its forward sweep (ba.cpp:1664-1685 output
+// resolution, 1838-1871 smoothing / decimation, 1873-1921 final sizes - the arithmetic of k_out_plan,
+// k_out_smooth_plan and k_out_final_plan), so the host lays the chunk's blocks out as soon as the sweeps are back:
+// prefix sums -> w.ragOff, and the chunk's place in the caller's buffers from the shared counter.  (A trajectory
+// the output phase rejects later keeps its reserved block and reports n_out = 0.)
+static void plan_ragged(batotp_handle h) {
+  const batotp_cfg &c = h->cfg.c;
+  const int B = h->B;
+  h->ragOffHost.resize((size_t)B + 1);
+  long long acc = 0;
+  for (int b = 0; b < B; ++b) {
+    h->ragOffHost[b] = acc;
+    const TrajState &s = h->hst[b];
+    if (s.status & ST_FATAL_MASK) continue;
+    const double outResT = c.out_res;
+    double outRes = outResT, outSmooth = c.out_smooth_fact;
+    bool re = false;
+    if (outRes < s.integRes) {
+      re = true;
+      outRes = s.integRes;
+      outSmooth *= std::max(outResT / outRes, 1.);
+    }
+    const double tLast = s.tStep * (double)(s.nFwd - 1);
+    int nOver = (int)(outSmooth * std::ceil(tLast / outRes + 1.));
+    nOver = std::max(nOver, 4);
+    const int nSm = outSmooth > 1.5 ? std::max((int)((nOver - 1) / outSmooth) + 1, 4) : nOver;
+    const int nOut = re ? std::max((int)(std::ceil(tLast / outResT)), 4) : nSm;
+    acc += nOut;
+  }
+  h->ragOffHost[B] = acc;
+  h->ragChunkBase = h->ragNext->fetch_add(acc);
+  g_h2d(h->w.ragOff, h->ragOffHost.data(), ((size_t)B + 1) * sizeof(long long), h->stream);
+}
+
 static int chunk_sweeps_output(batotp_handle h, bool haveN0) {
   for (int attempt = 0; attempt < 10; ++attempt) {
     if (do_sweeps(h) != 0) return -1;
@@ -1970,6 +1997,7 @@ static int chunk_sweeps_output(batotp_handle h, bool haveN0) {
         h->cntTraj++;
       }
       h->hwSc = std::max(h->hwSc, std::min(h->w.Sc, (int)(mxF * 1.25) + 64));
+      if (h->ragged) plan_ragged(h);
       return 0;
     }
     // A trajectory that crawls (e.g. an infeasible path whose bisection keeps failing, ba.cpp:1307-1319) runs
@@ -1984,6 +2012,7 @@ static int chunk_sweeps_output(batotp_handle h, bool haveN0) {
         h->cntTraj++;
       }
       h->hwSc = std::max(h->hwSc, h->w.Sc);  // the next chunks start with this capacity: one pass each
+      if (h->ragged) plan_ragged(h);
       return 0;
     }
     // grow the step capacity and redo the chunk from the start (the status word is sticky)
@@ -2102,7 +2131,7 @@ static void fetch_rows(batotp_handle h, batotp_batch_out *out, int first, cudaSt
                base + total);
       throw Err{buf};
     }
-    for (int bl = 0; bl < Bo; ++bl) out->row_offset[g0 + bl] = base + h->ragOffHost[bl];
+    for (int bl = 0; bl < Bo; ++bl) out->row_offset[g0 + bl] = h->ragChunkBase + h->ragOffHost[w.b0 + bl];
     if (out->theta_out && total > 0)
       g_d2h(out->theta_out + (size_t)base * c.J, h->d_thetaOut, (size_t)total * c.J * 4, cs);
     if (out->trq_out && c.trqOn && total > 0)

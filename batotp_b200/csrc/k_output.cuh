@@ -705,18 +705,18 @@ __host__ __device__ inline void q2aa_dev(const double q[4], double aa[3]) {
 // points fastest so that the float rows are written coalesced)
 // `pitch` = row stride (points) of the float32 outputs: the caller's out_cap when the rows travel on, so that a
 // sub-chunk leaves in one contiguous copy; the FP64 side outputs (cartOutD, outD) keep the capacity w.OutC.
-// `rag` (optional): ragged layout - trajectory bl's joint / torque block starts at rag[bl]*J floats and is
+// `rag` (optional): ragged layout - trajectory bl's joint / torque block starts at (rag[bl] - rag0)*J floats and is
 // [J][nOut] with no padding (cartOut must be NULL then); see batotp_batch_out.row_offset.
 __global__ void k_out_pack(WSP, double *src, double *srcM, double *trqSrc, double *trqM, float *thetaOut,
                            float *cartOut, float *trqOut, double *cartOutD, double *outD, int pitch,
-                           const long long *rag, int npts, int nb) {
+                           const long long *rag, long long rag0, int npts, int nb) {
   PT_DECOMP(npts);
   if (bl >= nb) return;
   const TrajState &s = w.st[w.b0 + bl];
   const int J = CFG.J, C = CFG.C, Cin = CFG.Cin;
   const bool fatal = (s.status & ST_FATAL_MASK) != 0;
   // float rows: pitched [bl][row][pitch], or ragged [rag[bl]*J + row*nOut]
-  const size_t fBase = rag ? (size_t)rag[bl] * J : (size_t)bl * J * pitch;
+  const size_t fBase = rag ? (size_t)(rag[bl] - rag0) * J : (size_t)bl * J * pitch;
   const size_t fRow = rag ? (size_t)(fatal ? 0 : s.nOut) : (size_t)pitch;
   const bool inF = rag ? (!fatal && i < s.nOut) : (i < pitch), inD = i < w.OutC;
   if (!inF && !inD) return;
@@ -807,7 +807,7 @@ struct SView {
   __host__ __device__ __forceinline__ double operator[](int i) const { return p[i * st]; }
 };
 __global__ void k_out_pack_rows(WSP, double *src, double *srcM, float *thetaOut, float *cartOut, int pitch,
-                                const long long *rag, int npts, int nb) {
+                                const long long *rag, long long rag0, int npts, int nb) {
   EMU_SHARED double sY[OP_WARPS][OP_CAP * MAXD];
   EMU_SHARED double sM[OP_WARPS][OP_CAP * MAXD];
   const int lane = threadIdx.x, wy = threadIdx.y;
@@ -823,7 +823,7 @@ __global__ void k_out_pack_rows(WSP, double *src, double *srcM, float *thetaOut,
   const int nOut = fatal ? 0 : imin_(s.nOut, npts);
   const bool live = i < nOut;
   // float rows: pitched [bl][row][pitch], or ragged (rag[bl]*J + row*nOut: no padding, nothing beyond the length)
-  const size_t fBase = rag ? (size_t)rag[bl] * J : (size_t)bl * J * pitch;
+  const size_t fBase = rag ? (size_t)(rag[bl] - rag0) * J : (size_t)bl * J * pitch;
   const size_t fRow = rag ? (size_t)(fatal ? 0 : s.nOut) : (size_t)pitch;
   if (i0 < nOut) {  // warp-uniform
     const bool re = s.isReinterp != 0;
@@ -935,38 +935,6 @@ __global__ void k_pack_hist(WSP, float *histOut, int pitch, int npts, int nb) {
     }
     if (inS) fl[(size_t)w.Sc + i] = 0;
   }
-}
-
-// Ragged result layout: exclusive prefix sums of the output lengths of the sub-chunk (0 for a trajectory that was
-// not optimised) -> off[0..nb-1], total in off[nb].  One CTA; lengths are summed in chunks of blockDim.x.  (T)
-__global__ void k_rag_scan(WSP, long long *off, int nb) {
-  EMU_SHARED long long part[1024];
-  EMU_SHARED long long carry;
-  const int t = threadIdx.x, nt = blockDim.x;
-  if (t == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < nb; base += nt) {
-    const int bl = base + t;
-    long long v = 0;
-    if (bl < nb) {
-      const TrajState &s = w.st[w.b0 + bl];
-      v = (s.status & ST_FATAL_MASK) ? 0 : s.nOut;
-    }
-    part[t] = v;
-    __syncthreads();
-    // Hillis-Steele inclusive scan over the CTA
-    for (int d = 1; d < nt; d <<= 1) {
-      const long long x = (t >= d) ? part[t - d] : 0;
-      __syncthreads();
-      part[t] += x;
-      __syncthreads();
-    }
-    if (bl < nb) off[bl] = carry + part[t] - v;
-    __syncthreads();
-    if (t == nt - 1) carry += part[t];
-    __syncthreads();
-  }
-  if (t == 0) off[nb] = carry;
 }
 
 // per-trajectory scalars of the output sub-chunk -> the caller's arrays when those live on the device
