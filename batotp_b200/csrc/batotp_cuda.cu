@@ -675,6 +675,7 @@ void set_cfg(batotp_ctx *h, const batotp_cfg *cfg) {
   d.R = d.J + d.C;
   d.RT = d.J + (d.cartOn ? 3 : 0) + (d.trqOn ? 4 * d.J : 0);
   d.quadThresh = cfg->cart_thresh * cfg->cart_thresh;
+  d.pm = h->pm;
   // strict trig on the device: the arithmetic variant of the host libm this process runs against (k_trig.cuh)
   d.trigDev = (cfg->trig_mode == 1) ? (host_libm_uses_fma() ? 3 : 1) : 0;
   const double Bt[6][6] = {{1. / 5, 3. / 40, 44. / 45, 19372. / 6561, 9017. / 3168, 35. / 384},
@@ -707,8 +708,9 @@ int check_cfg(batotp_ctx *h) {
     h->err = "isSVD=1 is outside the accelerated scope (SURVEY §8f rank 3)";
     return -1;
   }
-  if (c.is_trq_on && c.is_parallel && !c.is_par2ser) {
-    h->err = "parallel-mechanism torque limits without isPar2Ser are outside the accelerated scope (SURVEY §8f rank 3)";
+  if (c.is_trq_on && c.is_parallel && !c.is_par2ser && !(c.is_cart_vel_on || c.is_cart_acc_on)) {
+    h->err = "parallel-mechanism torque limits without isPar2Ser need a Cartesian limit switched on: setA reads the "
+             "Cartesian point, which the reference only refreshes then (ba.cpp:1363-1380, 1408-1411)";
     return -1;
   }
   if (c.is_trq_on && c.dyn_source == 1) {
@@ -846,17 +848,17 @@ void thomas_rows(batotp_ctx *h, double *src, double *dst, int nb, int b0, int ro
   LAUNCH_T(h, k_thomas_rows, nb * rows, h->w, src, dst, nb, b0, rows, rowsPerTraj, nsel, clamped, t);
 }
 
-template <int J, bool CART, bool TRQ>
+template <int J, bool CART, bool TRQ, bool PAR = false>
 void launch_sweep(batotp_ctx *h) {
   g_zero(h->w.queue, sizeof(int) * 4, h->stream);
-  const size_t smem = SweepLayout<J, CART, TRQ>::bytes;
+  const size_t smem = SweepLayout<J, CART, TRQ, PAR>::bytes;
 #ifndef BATOTP_HOST_EMU
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  CU_CHECK(cudaFuncSetAttribute(k_sweep<J, CART, TRQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU_CHECK(cudaFuncSetAttribute(k_sweep<J, CART, TRQ, PAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int perSm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_sweep<J, CART, TRQ>, SW_NT, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_sweep<J, CART, TRQ, PAR>, SW_NT, smem);
   if (perSm < 1) perSm = 1;
   int blocks = std::min(sms * perSm, cdiv(h->B, SW_NT));
   if (blocks < 1) blocks = 1;
@@ -870,7 +872,7 @@ void launch_sweep(batotp_ctx *h) {
 #endif
   {
     ProfScope ps_(h, "k_sweep");
-    BATOTP_LAUNCH_WARP((k_sweep<J, CART, TRQ>), dim3(blocks), dim3(SW_NT), smem, h->stream, h->w);
+    BATOTP_LAUNCH_WARP((k_sweep<J, CART, TRQ, PAR>), dim3(blocks), dim3(SW_NT), smem, h->stream, h->w);
     g_check_launch();
   }
 #ifndef BATOTP_HOST_EMU
@@ -927,6 +929,16 @@ bool use_group_kernel(const batotp_ctx *h) {
 int dispatch_sweep(batotp_ctx *h) {
   const DevCfg &c = h->cfg;
   const int key = c.J * 4 + (c.cartOn ? 2 : 0) + (c.trqOn ? 1 : 0);
+  if (c.trqOn && c.c.is_parallel && !c.c.is_par2ser) {
+    // torque limits of a parallel mechanism without Par2Ser (ba.cpp:1463-1491): one trajectory per lane only
+    h->lastSweepKernel = 1;
+    if (key == 3 * 4 + 3) {
+      launch_sweep<3, true, true, true>(h);
+      return 0;
+    }
+    h->err = "parallel-mechanism torque limits without isPar2Ser are instantiated for 3 joints + Cartesian limits (CSPR3DOF)";
+    return -1;
+  }
   h->lastSweepKernel = use_group_kernel(h) ? 2 : 1;
   if (use_group_kernel(h)) {
     switch (key) {

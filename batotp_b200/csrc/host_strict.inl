@@ -132,6 +132,10 @@ void launch_mvc(batotp_ctx *h, double sdotStart, double *d_out, int cap) {
 
 int run_mvc_per_sample(batotp_ctx *h, double sdotStart, double *sdot_out, int cap) {
   const DevCfg &c = h->cfg;
+  if (c.trqOn && c.c.is_parallel && !c.c.is_par2ser) {
+    h->err = "the per-sample MVC is not instantiated for parallel-mechanism torque limits without isPar2Ser";
+    return -1;
+  }
   double *d_out = (double *)g_alloc((size_t)h->B * cap * 8);
   g_zero(d_out, (size_t)h->B * cap * 8, h->stream);
   const int key = c.J * 4 + (c.cartOn ? 2 : 0) + (c.trqOn ? 1 : 0);

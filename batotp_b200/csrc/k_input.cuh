@@ -422,9 +422,6 @@ __global__ void k_in_decim_fix(WSP) {
 //       of the chunk it holds); evaluated for i < st.nPts (or nOver for the output).
 // robot.cpp:105-176 (KUKA; 3x3 products accumulated left to right as in oracle/eigen_standin),
 // 185-202 (RR), 243-278 + 291-322 (CSPR inverse kinematics / attachment points).
-struct Pmat {
-  double p[3][3];
-};
 __host__ __device__ inline void fk_kuka_point(const Trig &tg, const double *th, double *xyz) {
   const double D2R = 3.14159265358979323846 / 180.0;
   double c[7], s[7];

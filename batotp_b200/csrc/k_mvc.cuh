@@ -28,6 +28,7 @@ __global__ void k_mvc(WSP, double sdotStart, double *out, int cap, int npts, int
   const double tau = (sCur - sSeg) / (C.sresC * (double)(seg + 1) - sSeg);
   struct KGlobal {  // the segment table holds {c3,c2,c1,c0}; kinematic rows are read as {3c3, 2c2, c1, 6c3}
     const double *t;
+    __host__ __device__ __forceinline__ double raw(int r, int q) const { return t[r * 4 + q]; }
     __host__ __device__ __forceinline__ double operator()(int r, int q) const {
       if (r >= NK) return t[r * 4 + q];
       return q == 0 ? 3 * t[r * 4] : (q == 1 ? 2 * t[r * 4 + 1] : (q == 2 ? t[r * 4 + 2] : 6 * t[r * 4]));

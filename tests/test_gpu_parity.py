@@ -591,3 +591,22 @@ def test_ragged_rows_hold_the_same_samples(ctx):
     ctx.optimize_batch(cfg, ctx.make_in(th, ca, tres, timestamp=ts), r)
     n = int(p.n_out[0])
     assert np.array_equal(r.rows(0), p.theta_out[0, :, :n]) and np.array_equal(r.rows(0, "trq_out"), p.trq_out[0, :, :n])
+
+
+def test_parallel_torque_without_par2ser(ctx, tmp_path):
+    """cable-tension limits of the CSPR3DOF with isPar2Ser = 0 (ba.cpp:1463-1491: the structure
+    matrix is rebuilt at every point and every verification solves 2 x 3 three-by-three systems with a replaced
+    column) - k_sweep<3,true,true,PAR> against the oracle, which tests/test_oracle_vs_reference.py pins to the
+    unmodified reference for this option."""
+    cfg, tres, th, ca, ts = P.load_stock_variant("CSPR3DOF", tmp_path, isPar2Ser=0)
+    assert cfg.is_par2ser == 0
+    res = P.run_device(ctx, cfg, tres, th, ca, ts)
+    orc = P.OracleRun(cfg, tres, None, ca[0])
+    assert orc.ok and res.status[0] & native.ST_FATAL_MASK == 0
+    assert P.compare(cfg, res, 0, orc) == []
+    cfg2, tres2, _, ca2 = P.load_synth("CSPR3DOF", 50, 3)
+    cfg2 = cfg2.copy()
+    cfg2.is_par2ser = 0
+    r2 = P.run_device(ctx, cfg2, tres2, None, ca2)
+    for b in range(3):
+        assert P.compare(cfg2, r2, b, P.OracleRun(cfg2, tres2, None, ca2[b])) == [], b

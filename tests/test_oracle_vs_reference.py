@@ -226,3 +226,24 @@ def test_caller_supplied_dynamics_reproduce_the_reference_on_rr(tmp_path):
     for nm in ("theta", "trq"):
         for j in range(2):
             assert np.array_equal(r.vec(nm, j), o.vec(nm, j)), (nm, j)
+
+
+def test_parallel_torque_without_par2ser_matches(tmp_path):
+    """isPar2Ser = 0 on the CSPR3DOF folder (ba.cpp:1463-1491; no shipped config uses it): restatement against the
+    unmodified reference, every phase bit for bit."""
+    d = P.GOLD + "/stock/CSPR3DOF/"
+    r = Ref(P.variant_config("CSPR3DOF", tmp_path, isPar2Ser=0), d, str(tmp_path) + "/")
+    assert r.load_file() == 0
+    cfg, tres, th, ca, ts = P.load_stock_variant("CSPR3DOF", tmp_path, isPar2Ser=0)
+    o = Oracle(cfg)
+    o.load_raw(ca.shape[2], tres, None, ca[0], None)
+    assert r.interp_input() == 0 and o.interp_input() == 0
+    for dd, last in ((-1, 0), (1, 1)):
+        assert r.sweep(dd, last) == 0 and o.sweep(dd, last) == 0
+        assert np.array_equal(r.vec("sMVC"), o.vec("sMVC")) and np.array_equal(r.vec("sdot"), o.vec("sdot"))
+    assert r.scalar("tTotalTraj") == o.scalar("tTotalTraj")
+    r.interp_output()
+    o.interp_output()
+    for nm in ("theta", "trq"):
+        for j in range(3):
+            assert np.array_equal(r.vec(nm, j), o.vec(nm, j)), (nm, j)
