@@ -610,3 +610,28 @@ def test_parallel_torque_without_par2ser(ctx, tmp_path):
     r2 = P.run_device(ctx, cfg2, tres2, None, ca2)
     for b in range(3):
         assert P.compare(cfg2, r2, b, P.OracleRun(cfg2, tres2, None, ca2[b])) == [], b
+
+
+def test_max_integration_time_is_reported_like_the_reference(ctx):
+    """maxIntegTime (ba.cpp:1117-1122): a sweep that does not reach the end of the path within maxIntegTime/integRes
+    steps ends with BA::MAX_INTEGRATION_TIME in the reference (sweep returns -1); here the trajectory gets
+    BATOTP_ST_MAX_INTEG_TIME (not the internal step ceiling) and no output, the rest of the batch is untouched."""
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 900, 4)
+    ref = P.run_device(ctx, cfg, tres, th, None)
+    c2 = cfg.copy()
+    c2.max_integ_time = 0.6 * float(ref.t_total.min())  # every path needs longer than this
+    res = P.run_device(ctx, c2, tres, th, None)
+    assert ((res.status & 16) != 0).all() and ((res.status & 32) == 0).all() and (res.n_out == 0).all()
+    for b in range(2):
+        orc = P.OracleRun(c2, tres, th[b], None)
+        assert not orc.ok
+    c3 = cfg.copy()
+    c3.max_integ_time = 0.5 * (float(np.sort(ref.t_total)[1]) + float(np.sort(ref.t_total)[2]))  # two of the four finish
+    mix = P.run_device(ctx, c3, tres, th, None)
+    done = (mix.status & native.ST_FATAL_MASK) == 0
+    assert 1 <= done.sum() <= 3
+    for b in range(4):
+        orc = P.OracleRun(c3, tres, th[b], None)
+        assert orc.ok == bool(done[b]), b
+        if done[b]:
+            assert P.compare(c3, mix, b, orc) == [], b
