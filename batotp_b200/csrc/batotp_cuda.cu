@@ -490,7 +490,7 @@ int final_cap(const batotp_ctx *h, int Sc, int Os) {
 size_t chunk_bytes_per_traj(const DevCfg &c, int Nc, int Sc) {
   const size_t n = (size_t)Nc, sc = (size_t)Sc;
   size_t per = 3 * (size_t)c.R * n * 8 + n * 8 + 2 * n * 8 + n * (size_t)c.RT * 32 + 4 * sc * 8 + 2 * sc + sizeof(TrajState);
-  if (c.trqOn) per += 2 * (size_t)4 * MAXD * n * 8 + 2 * (size_t)c.R * n * 8;
+  if (c.trqOn) per += 2 * (size_t)4 * c.J * n * 8 + 2 * (size_t)c.R * n * 8;
   return per;
 }
 
@@ -517,7 +517,8 @@ void ensure_ws(batotp_ctx *h, int B, int Nc, int Sc) {
   const bool trq = c.trqOn != 0;
   // (with a step hint the capacity asked for is taken literally, not "at least")
   const bool scOk = h->stepHint > 0 ? (Sc == h->capSc) : (Sc <= h->capSc);
-  if (B <= h->capB && Nc <= h->capNc && scOk && c.R == h->capR && c.RT == h->capRT && trq == h->capTrq) {
+  if (B <= h->capB && Nc <= h->capNc && scOk && c.R == h->capR && c.RT == h->capRT && trq == h->capTrq &&
+      c.J == h->w.AD) {
     h->w.B = B;
     return;
   }
@@ -552,6 +553,7 @@ void ensure_ws(batotp_ctx *h, int B, int Nc, int Sc) {
   w.Sc = Sc;
   w.R = R;
   w.RT = RT;
+  w.AD = c.J;
   w.P = ws_alloc<double>(h, b * R * Nc);
   w.Q = ws_alloc<double>(h, b * R * Nc);
   w.M = ws_alloc<double>(h, b * R * Nc);
@@ -562,11 +564,11 @@ void ensure_ws(batotp_ctx *h, int B, int Nc, int Sc) {
   w.flags = ws_alloc<unsigned char>(h, b * 2 * Sc);
   w.st = ws_alloc<TrajState>(h, b);
   if (trq) {
-    w.A = ws_alloc<double>(h, b * 4 * MAXD * Nc);
-    w.AM = ws_alloc<double>(h, b * 4 * MAXD * Nc);
+    w.A = ws_alloc<double>(h, b * 4 * w.AD * Nc);
+    w.AM = ws_alloc<double>(h, b * 4 * w.AD * Nc);
     w.GD = ws_alloc<double>(h, b * R * Nc);
     w.GD2 = ws_alloc<double>(h, b * R * Nc);
-    g_zero(w.A, b * 4 * MAXD * Nc * sizeof(double), h->stream);
+    g_zero(w.A, b * 4 * w.AD * Nc * sizeof(double), h->stream);
   }
   w.queue = ws_alloc<int>(h, 4);
   w.ragOff = ws_alloc<long long>(h, b + 1);
@@ -1162,7 +1164,7 @@ int do_interp_input(batotp_ctx *h, bool haveN0, bool planSync) {
       host_dyn_rr_grid(h);
     else
       LAUNCH_TP(h, k_dyn_grid, w.Nc, B, w, h->pm);
-    thomas_rows(h, w.A, w.AM, B, 0, 4 * MAXD, 4 * MAXD, 0, 0);
+    thomas_rows(h, w.A, w.AM, B, 0, 4 * w.AD, 4 * w.AD, 0, 0);
   }
   if (!c.trqOn && w.RT <= BT_ROWS) {  // kinematic rows only: tiled through shared memory
     const long long rows = cdiv(w.Nc, BT_SEGS);
@@ -2763,9 +2765,9 @@ int batotp_cuda_get_f64(batotp_handle h, const char *name, int traj, int row, do
     const double *src = nullptr;
     size_t stride = 1;  // in doubles
     int len = 0;
-    const size_t pst = (size_t)w.B * c.R, ast = (size_t)w.B * 4 * MAXD;
+    const size_t pst = (size_t)w.B * c.R, ast = (size_t)w.B * 4 * w.AD;
     auto prow = [&](const double *base, int r) { return base + (size_t)traj * c.R + r; };
-    auto arow = [&](const double *base, int k, int r) { return base + (size_t)traj * 4 * MAXD + (size_t)k * MAXD + r; };
+    auto arow = [&](const double *base, int k, int r) { return base + (size_t)traj * 4 * w.AD + (size_t)k * w.AD + r; };
     if (n == "integ_res" || n == "t_step" || n == "t_total" || n == "t_rev") {
       // per-trajectory scalars of the sweeps (integRes may be the automatically chosen step, ba.cpp:493-556)
       const double v = n == "integ_res" ? s.integRes : (n == "t_step" ? s.tStep : (n == "t_total" ? s.tFwd : s.tRev));

@@ -43,7 +43,7 @@ void host_dyn_rr_grid(batotp_ctx *h) {
     if (!(h->hst[b].status & ST_FATAL_MASK)) nmax = std::max(nmax, h->hst[b].nPts);
   if (nmax <= 0) return;
   const size_t cnt = (size_t)nmax * B * R;
-  std::vector<double> q(cnt), d1(cnt), d2(cnt), A((size_t)nmax * B * 4 * MAXD, 0.0);
+  std::vector<double> q(cnt), d1(cnt), d2(cnt), A((size_t)nmax * B * 4 * w.AD, 0.0);
   g_d2h(q.data(), w.Q, cnt * 8, h->stream);
   g_d2h(d1.data(), w.GD, cnt * 8, h->stream);
   g_d2h(d2.data(), w.GD2, cnt * 8, h->stream);
@@ -58,9 +58,9 @@ void host_dyn_rr_grid(batotp_ctx *h) {
         double a1[MAXD] = {0}, a2[MAXD] = {0}, a3[MAXD] = {0}, a4[MAXD] = {0};
         host_dyn_point(h, &q[off], &d1[off], &d2[off], a1, a2, a3, a4);
         const double *aa[4] = {a1, a2, a3, a4};
-        double *Ab = &A[((size_t)i * B + b) * 4 * MAXD];
+        double *Ab = &A[((size_t)i * B + b) * 4 * w.AD];
         for (int k = 0; k < 4; ++k)
-          for (int j = 0; j < J; ++j) Ab[k * MAXD + j] = aa[k][j];
+          for (int j = 0; j < J; ++j) Ab[k * w.AD + j] = aa[k][j];
       }
     }
   });

@@ -118,9 +118,9 @@ __global__ void k_dyn_grid(WSP, Pmat pm, int npts, int nb) {
     }
     dyn_rr_point(Trig{CFG.trigDev}, th, d1, d2, a[0], a[1], a[2], a[3]);
   }
-  double *Ab = w.A + ((size_t)i * w.B + b) * 4 * MAXD;
+  double *Ab = w.A + ((size_t)i * w.B + b) * 4 * w.AD;
   for (int k = 0; k < 4; ++k)
-    for (int q = 0; q < MAXD; ++q) Ab[k * MAXD + q] = a[k][q];
+    for (int q = 0; q < w.AD; ++q) Ab[k * w.AD + q] = a[k][q];
 }
 
 // ----------------------------------------------------------------------------- output plan (T)
