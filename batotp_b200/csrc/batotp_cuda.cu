@@ -119,7 +119,12 @@ inline void g_check_launch() {}
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 #ifndef SWEEP_GROUP_MAX_B
-#define SWEEP_GROUP_MAX_B 16384  // chunks up to this size take the group-per-trajectory sweep kernel (automatic mode)
+#define SWEEP_GROUP_MAX_B 16384  // chunks up to this size take the group-per-trajectory sweep kernel (automatic mode) ...
+#endif
+#ifndef SWEEP_GROUP_MAX_B_EXACT
+#define SWEEP_GROUP_MAX_B_EXACT 32768  // ... or this size when the limits need the exact verification (Cartesian / torque
+                                       // rows: no float filters, so the lane kernel pays 14+ IEEE divisions per
+                                       // verification and the group kernel stays ahead for longer: CSPR x19072 351 vs ~270 ms)
 #endif
 // bytes the device can still hand out (host emulation: "plenty")
 inline size_t g_free_bytes() {
@@ -925,7 +930,8 @@ void launch_sweep_group(batotp_ctx *h) {
 bool use_group_kernel(const batotp_ctx *h) {
   if (h->sweepKernel == 1) return false;
   if (h->sweepKernel == 2) return true;
-  return h->B <= SWEEP_GROUP_MAX_B;
+  const bool exact = h->cfg.cartOn || h->cfg.trqOn;
+  return h->B <= (exact ? SWEEP_GROUP_MAX_B_EXACT : SWEEP_GROUP_MAX_B);
 }
 
 int dispatch_sweep(batotp_ctx *h) {
