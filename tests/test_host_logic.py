@@ -72,3 +72,23 @@ def test_product_library_refuses_to_run_without_gpu():
         pytest.skip("a CUDA device is present")
     with pytest.raises(native.NativeError):
         native.Context(0)
+
+
+def test_cspr_paths_are_redrawn_into_the_static_workspace():
+    """a CSPR candidate is kept only if the cable tensions that hold the platform at rest stay within
+    [1.05, 11.5] N along it (inside the static workspace the reference's bisection cannot fail); a rejected index
+    draws its next candidate, so every path depends on (index) only."""
+    raw = synth.cspr_paths(0, 64, redraw=False)[1]
+    ok = synth.cspr_accept(raw)
+    assert 0.5 < ok.mean() < 0.95  # a good part of the raw family leaves the workspace
+    tres, pay = synth.cspr_paths(0, 64)
+    assert synth.cspr_accept(pay).all() and synth.cspr_accept(pay, stride=1).all()
+    assert np.array_equal(pay[ok], raw[ok])  # accepted first draws are kept as they are
+    assert np.array_equal(synth.cspr_paths(40, 8)[1], pay[40:48])
+    tau = synth.cspr_static_tensions(pay[:4])
+    assert tau.shape == (4, pay.shape[2], 3) and tau.min() >= 1.05 and tau.max() <= 11.5
+    # the static tensions solve A tau = (0, 0, g) with A's columns the unit vectors along the cables
+    x = pay[0, :, 100].astype(np.float64)
+    d = x[:, None] - synth.cspr_pmat()
+    A = d / np.sqrt((d * d).sum(axis=0, keepdims=True))
+    assert np.allclose(A @ tau[0, 100], [0.0, 0.0, 9.81], atol=1e-12)
