@@ -1172,16 +1172,22 @@ int do_interp_input(batotp_ctx *h, bool haveN0, bool planSync) {
       LAUNCH_TP(h, k_dyn_grid, w.Nc, B, w, h->pm);
     thomas_rows(h, w.A, w.AM, B, 0, 4 * w.AD, 4 * w.AD, 0, 0);
   }
-  if (!c.trqOn && w.RT <= BT_ROWS) {  // kinematic rows only: tiled through shared memory
+  {  // the segment table, tiled through shared memory
     const long long rows = cdiv(w.Nc, BT_SEGS);
     const long long gy = std::min<long long>(rows, 32768), gz = (rows + gy - 1) / gy;
     ProfScope ps_(h, "k_build_table_tile");
-    BATOTP_LAUNCH_WARP(k_build_table_tile, dim3((unsigned)cdiv(B, BT_TRAJ), (unsigned)gy, (unsigned)gz),
-                       dim3(BT_TRAJ, BT_SEGS, 1), 0, h->stream, w, w.Nc, B);
+    if (!c.trqOn && w.RT <= BT_ROWS) {  // kinematic rows only
+      BATOTP_LAUNCH_WARP((k_build_table_tile<BT_TRAJ, BT_ROWS>), dim3((unsigned)cdiv(B, BT_TRAJ), (unsigned)gy, (unsigned)gz),
+                         dim3(BT_TRAJ, BT_SEGS, 1), 0, h->stream, w, w.Nc, B);
+    } else if (w.RT <= BT_ROWS_DYN) {  // with the dynamics rows
+      BATOTP_LAUNCH_WARP((k_build_table_tile<BT_TRAJ_DYN, BT_ROWS_DYN>),
+                         dim3((unsigned)cdiv(B, BT_TRAJ_DYN), (unsigned)gy, (unsigned)gz), dim3(BT_TRAJ_DYN, BT_SEGS, 1), 0,
+                         h->stream, w, w.Nc, B);
+    } else {
+      LAUNCH_TP(h, k_build_table, w.Nc, B, w);
+    }
     g_check_launch();
     h->launches++;
-  } else {
-    LAUNCH_TP(h, k_build_table, w.Nc, B, w);
   }
   h->phase = 2;
   return 0;

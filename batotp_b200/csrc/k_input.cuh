@@ -983,24 +983,36 @@ __global__ void k_build_table(WSP, int npts, int nb) {
   }
 }
 
-// The same table for runs without dynamics rows (RT <= 10), built through shared-memory tiles of 16 segments
-// x 8 trajectories: the knots are read with trajectories fastest (the point-major order of P/M), the table is
-// written one trajectory at a time as contiguous 16*RT*32-byte runs.  Block (8, 16).
+// The same table built through shared-memory tiles of BT_SEGS segments x TRAJ trajectories: the knots are read with
+// trajectories fastest (the point-major order of P/M and A/AM), the table is written one trajectory at a time as
+// contiguous BT_SEGS*RT*32-byte runs.  Block (TRAJ, BT_SEGS).  Two shapes: 8 trajectories x 10 rows (kinematic rows
+// only: GEN7DOF, KUKA, UR5) and 4 trajectories x 18 rows (with the 4*J dynamics rows of the 2- and 3-joint robots: RR, CSPR3DOF; 7-joint robots
+// with a caller-supplied model take the untiled k_build_table).
 #define BT_TRAJ 8
 #define BT_SEGS 16
 #define BT_ROWS 10
+#define BT_TRAJ_DYN 4
+#define BT_ROWS_DYN 18
+template <int TRAJ, int ROWS>
 __global__ void k_build_table_tile(WSP, int npts, int nb) {
-  EMU_SHARED double tile[BT_TRAJ][BT_SEGS][BT_ROWS * 4];
+  EMU_SHARED double tile[TRAJ][BT_SEGS][ROWS * 4];
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int b0 = (int)blockIdx.x * BT_TRAJ, i0 = (int)(blockIdx.z * gridDim.y + blockIdx.y) * BT_SEGS;
+  const int b0 = (int)blockIdx.x * TRAJ, i0 = (int)(blockIdx.z * gridDim.y + blockIdx.y) * BT_SEGS;
   const int RT = w.RT;
+  const int nKin = CFG.J + (CFG.cartOn ? 3 : 0);
   {
     const int b = b0 + tx, i = i0 + ty;
     if (b < nb && i < npts) {
       const TrajState &s = w.st[b];
       if (!(s.status & ST_FATAL_MASK) && i < s.nPtsC - 1) {
         for (int r = 0; r < RT; ++r) {
-          const Seg4 c = seg_coef(rowv(w.P, w, b, r), rowv(w.M, w, b, r), i);
+          Seg4 c;
+          if (r < nKin)
+            c = seg_coef(rowv(w.P, w, b, r), rowv(w.M, w, b, r), i);
+          else {
+            const int q = r - nKin, a = q / CFG.J, j = q - a * CFG.J;
+            c = seg_coef(arowv(w.A, w, b, a, j), arowv(w.AM, w, b, a, j), i);
+          }
           tile[tx][ty][r * 4 + 0] = c.c3;
           tile[tx][ty][r * 4 + 1] = c.c2;
           tile[tx][ty][r * 4 + 2] = c.c1;
@@ -1010,8 +1022,8 @@ __global__ void k_build_table_tile(WSP, int npts, int nb) {
     }
   }
   __syncthreads();
-  const int tid = ty * BT_TRAJ + tx, per = RT * 4, run = BT_SEGS * per;
-  for (int bl = 0; bl < BT_TRAJ; ++bl) {
+  const int tid = ty * TRAJ + tx, per = RT * 4;
+  for (int bl = 0; bl < TRAJ; ++bl) {
     const int b = b0 + bl;
     if (b >= nb) break;
     const TrajState &s = w.st[b];
@@ -1019,8 +1031,7 @@ __global__ void k_build_table_tile(WSP, int npts, int nb) {
     const int nSeg = imin_(imin_(s.nPtsC - 1, npts) - i0, BT_SEGS);  // valid segments of this tile
     if (nSeg <= 0) continue;
     double *t = w.tab + ((size_t)b * w.Nc + i0) * (size_t)per;
-    for (int e = tid; e < nSeg * per; e += BT_TRAJ * BT_SEGS) t[e] = tile[bl][e / per][e % per];
-    (void)run;
+    for (int e = tid; e < nSeg * per; e += TRAJ * BT_SEGS) t[e] = tile[bl][e / per][e % per];
   }
 }
 
