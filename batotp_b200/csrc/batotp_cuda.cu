@@ -276,6 +276,7 @@ struct batotp_ctx {
   // context (own streams and workspaces, one host thread) next to the output / input phases of the full chunks
   batotp_ctx *helper = nullptr;
   bool tailOverlap = true;
+  bool marchGroup = getenv("BATOTP_MARCH_LANE") == nullptr;  // interpSpecial march: a group of lanes per trajectory (tuning aid: the env var restores one thread per trajectory)
   int pipeline = 0;  // two-context chunk pipeline of batotp_cuda_optimize_batch: 0 off, 1 automatic (large batches),
                      // n > 1: chunks of n trajectories whatever the batch size (tuning / tests)
   // stragglers: the few trajectories of a chunk that outgrow the step capacity keep BATOTP_ST_STEP_CAP for the
@@ -1142,7 +1143,12 @@ int do_interp_input(batotp_ctx *h, bool haveN0, bool planSync) {
       if (need > w.Nc) return need;  // caller grows the workspace and restarts the chunk
     }
     thomas_rows(h, w.P, w.M, B, 0, c.R, c.R, 0, 0);
-    if (c.J == 7 && c.C == 3)
+    if (h->marchGroup && c.J + MAXD <= MG && c.R <= MG) {  // a group of lanes per trajectory (k_input.cuh)
+      ProfScope ps_(h, "k_march_group");
+      BATOTP_LAUNCH_WARP(k_march_group, dim3((unsigned)(((long long)B * MG + 127) / 128)), dim3(128), 0, h->stream, w);
+      g_check_launch();
+      h->launches++;
+    } else if (c.J == 7 && c.C == 3)
       LAUNCH_T(h, (k_march<7, 3>), B, w);
     else if (c.J == 6 && c.C == 7)
       LAUNCH_T(h, (k_march<6, 7>), B, w);

@@ -854,6 +854,134 @@ __global__ void k_march(WSP) {
   if (s.nPts < 4) traj_linear_to4(w, w.Q, b, s, R);
 }
 
+// The same march with MG lanes per trajectory: lane r owns coordinate row r (its previously emitted value, its
+// knot gathers, its segment coefficients and its store), the scalar control (arc-length bookkeeping, cursor, tau) is
+// computed redundantly by every lane of the group.  k_march is bound by the latency of one iteration (two square
+// roots, a division, 7..10 rows of coefficient arithmetic, three dependent gathers) at one warp per 32 trajectories;
+// here an iteration costs a lane one row, and the machine holds MG times as many warps.  Bit-exactness: the squared
+// row differences are summed in the reference's order (ba.cpp:681-690: joint 0 first) from values every lane
+// fetches by shuffle; all other expressions are k_march's, row by row.  Shuffles name the group's own lanes, so the
+// two groups of a warp may diverge.  Rows: r < J joints; J <= r < J + MAXD the Cartesian rows / Traj::cartpt.
+#define MG 16
+__global__ void k_march_group(WSP) {
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = gt / MG, r = gt % MG;
+  const int lane = (int)(threadIdx.x & 31u), gbase = lane & ~(MG - 1);
+  const unsigned gmask = ((MG == 32) ? 0xffffffffu : ((1u << MG) - 1u)) << gbase;
+  if (b >= w.B) return;  // (a whole group leaves together)
+  TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  const int J = CFG.J, C = CFG.C, R = J + C;
+  const bool isJ = r < J, isC = r >= J && r < R, isC3 = r >= J && r < J + 3, isCp = r >= J && r - J < MAXD;
+  const int nPts = s.nPts;
+  const RV sC = vecv(w.sC, w, b);
+  const size_t pst = (size_t)w.B * w.R;
+  const double *P = w.P + (size_t)b * w.R, *M = w.M + (size_t)b * w.R;
+  double *Q = w.Q + (size_t)b * w.R;
+  const int Nc = w.Nc;
+  if (r < R) Q[r] = P[r];
+  double last = (isJ || isC3) ? P[r] : 0.0;  // the previously emitted point: theta rows, cart xyz
+  double cartpt = isCp ? s.cartpt[r - J] : 0.0;
+  double sPrv = 0, prv_ds = 0;
+  int CurNewPt = 1, CurOldPt = 1;
+  int seg = 0;
+  bool isDone = false;
+  const int lastSeg = nPts - 2;
+  const bool cartEval = CFG.cartOn != 0;
+  const double sCend = sC[nPts - 1];
+  const double teach = s.tTeachFact * s.sResi, thetaNormFact = s.thetaNormFact, cartPosNormFact = s.cartPosNormFact;
+  const double sResNew = s.sResNew;
+  while (!isDone) {
+    const double *po = P + (size_t)CurOldPt * pst;
+    double dsq = 0.0;
+    if (isJ || isC3) {
+      const double d = po[r] - last;
+      dsq = d * d;
+    }
+    double dthetaSQ = 0;
+    for (int j = 0; j < J; ++j) dthetaSQ += __shfl_sync(gmask, dsq, gbase + j);
+    double dcartSQ = 0;
+    for (int j = 0; j < 3; ++j) dcartSQ += __shfl_sync(gmask, dsq, gbase + J + j);
+    const double cur_ds = teach * (double)CurOldPt + thetaNormFact * sqrt(dthetaSQ) + cartPosNormFact * sqrt(dcartSQ);
+    if (cur_ds > sResNew) {
+      const double sNew = sPrv + sResNew - prv_ds;
+      prv_ds = 0;
+      sPrv = sNew;
+      const double sCur = sPrv;
+      if (sCur > sCend) isDone = true;
+      if (!isDone) {
+        // updateCurSeg (ba.cpp:1617-1652) on the non-uniform sites
+        double sSeg, sNext;
+        int guard = 0;
+        for (;;) {
+          sSeg = sC[seg];
+          sNext = sC[seg + 1];
+          if (sCur >= sSeg && sCur <= sNext) break;
+          if (sCur > sSeg) {
+            if (seg >= lastSeg) {
+              seg = lastSeg;
+              break;
+            }
+            seg++;
+          }
+          if (sCur < sSeg) {
+            if (seg <= 0) {
+              seg = 0;
+              break;
+            }
+            seg--;
+          }
+          if (++guard > 4 * nPts + 16) {
+            if (r == 0) s.status |= ST_NUMERIC;
+            return;
+          }
+        }
+        const double tau = (sCur - sSeg) / (sC[seg + 1] - sSeg);
+        const double tau2 = tau * tau, tau3 = tau2 * tau;
+        if (CurNewPt >= Nc - 1) {
+          if (r == 0) s.status |= ST_GRID_CAP;
+          return;
+        }
+        double *qo = Q + (size_t)CurNewPt * pst;
+        if (isJ || (isC && cartEval)) {
+          const double *y0 = P + (size_t)seg * pst, *y1 = y0 + pst, *m0 = M + (size_t)seg * pst, *m1 = m0 + pst;
+          Seg4 c;
+          c.c3 = sdiv::div6(m1[r] - m0[r]);
+          c.c2 = m0[r] / 2.0;
+          c.c1 = y1[r] - y0[r] - sdiv::div6(m1[r] + 2 * m0[r]);
+          c.c0 = y0[r];
+          const double v = seg_value(c, tau, tau2, tau3);
+          if (isJ) {
+            qo[r] = v;
+            last = v;
+          } else
+            cartpt = v;
+        }
+        if (isC) qo[r] = cartpt;
+        if (isC3) last = cartpt;
+        CurOldPt = seg + 1;
+        CurNewPt++;
+      }
+    } else {
+      if (CurOldPt == nPts - 1) {
+        isDone = true;
+      } else {
+        prv_ds = cur_ds;
+        sPrv = sC[CurOldPt];
+        CurOldPt++;
+      }
+    }
+  }
+  if (r < R) Q[(size_t)CurNewPt * pst + r] = P[(size_t)(nPts - 1) * pst + r];
+  if (isCp) s.cartpt[r - J] = cartpt;
+  __syncwarp(gmask);  // the rows of every lane are in place before lane 0 re-reads them (fewer than 4 points)
+  if (r == 0) {
+    s.nPts = CurNewPt + 1;
+    s.sres = sResNew;
+    if (s.nPts < 4) traj_linear_to4(w, w.Q, b, s, R);
+  }
+}
+
 // ----------------------------------------------------------------------------- resample (TP)
 // evalSplineFullTraj, regular pass (ba.cpp:835-859): sites sMVC[i] = sScale*i located in the
 // non-uniform sC by findInterpSegs, values by interp1spline.  Source P/M/sC -> Q.
