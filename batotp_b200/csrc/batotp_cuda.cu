@@ -1136,6 +1136,7 @@ int do_interp_input(batotp_ctx *h, bool haveN0, bool planSync) {
   }
   apply_kinematics(h, 0);
   if (adjust) {
+    LAUNCH_TP(h, k_adjust_inc, w.Nc, B, w);
     LAUNCH_T(h, k_adjust_s, B, w, 1);
     if (planSync) {
       const int mx = read_plan_max(h, nullptr);
@@ -1160,9 +1161,11 @@ int do_interp_input(batotp_ctx *h, bool haveN0, bool planSync) {
       LAUNCH_T(h, (k_march<0, 0>), B, w);
     std::swap(w.P, w.Q);
     apply_kinematics(h, 1);
+    LAUNCH_TP(h, k_adjust_inc, w.Nc, B, w);
     LAUNCH_T(h, k_adjust_s, B, w, 0);
     thomas_rows(h, w.P, w.M, B, 0, c.R, c.R, 0, 0);
     LAUNCH_TP(h, k_resample, w.Nc, B, w);
+    LAUNCH_TP(h, k_resample_check, w.Nc, B, w);
     LAUNCH_T(h, k_resample_commit, B, w);
     std::swap(w.P, w.Q);
     apply_kinematics(h, 1);
@@ -1232,6 +1235,7 @@ int do_interp_only(batotp_ctx *h, bool haveN0) {
     }
     thomas_rows(h, w.P, w.M, h->B, 0, c.R, c.R, 0, 0);
     LAUNCH_TP(h, k_resample, w.Nc, h->B, w);
+    LAUNCH_TP(h, k_resample_check, w.Nc, h->B, w);
     LAUNCH_T(h, k_resample_commit, h->B, w);
     std::swap(w.P, w.Q);
     ensure_out(h, h->B, mx + 8);

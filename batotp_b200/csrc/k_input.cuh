@@ -540,10 +540,39 @@ __global__ void k_aa2q(WSP) {
   }
 }
 
-// ----------------------------------------------------------------------------- adjust_s, first half (T)
+// ----------------------------------------------------------------------------- adjust_s, first half (TP + T)
 // ba.cpp:412-590: cumulative norms, optional automatic integration resolution, scale selection,
 // the weighted arc-length sites sC, and (regular pass) the resample plan of evalSplineFullTraj
 // (ba.cpp:794-819).  ptsOrig is an iota at both call sites (ba.cpp:283, 778) so ptsOrig[i] == i.
+// First the increments of the two cumulative norms (ba.cpp:423-446), one thread per (point, trajectory): the square
+// roots and the ten coordinate differences of a point are independent of the running sums, so only the additions stay
+// sequential (k_adjust_s below reads an increment from the slot its sum goes to).   (TP)
+__global__ void k_adjust_inc(WSP, int npts, int nb) {
+  TP_DECOMP(nb);
+  if (i >= npts) return;
+  const int b = bl;
+  const TrajState &s = w.st[b];
+  if (s.status & ST_FATAL_MASK) return;
+  if (s.sWeights[1] + s.sWeights[2] < 1e-8) return;
+  if (i >= s.nPts - 1) return;
+  const int J = CFG.J;
+  const size_t pst = (size_t)w.B * w.R;
+  const double *p0 = w.P + (size_t)b * w.R + (size_t)i * pst, *nx = p0 + pst;
+  double dthetaSQ = 0;
+  for (int j = 0; j < J; ++j) {
+    const double d = nx[j] - p0[j];
+    dthetaSQ += d * d;
+  }
+  double dcartSQ = 0;
+  for (int j = 0; j < 3; ++j) {
+    const double d = nx[J + j] - p0[J + j];
+    dcartSQ += d * d;
+  }
+  double *o = w.nrm + ((size_t)(i + 1) * w.B + b) * 2;
+  o[0] = sqrt(dthetaSQ);
+  o[1] = sqrt(dcartSQ);
+}
+
 __global__ void k_adjust_s(WSP, int special) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= w.B) return;
@@ -562,33 +591,15 @@ __global__ void k_adjust_s(WSP, int special) {
   double thetaNormLast = 0, cartPosNormLast = 0;
   const double DEG2RAD = 3.14159265358979323846 / 180.0, RAD2DEG = 180.0 / 3.14159265358979323846;
   if (!CFG.c.are_jnt_deg) thetaWindow *= DEG2RAD;
-  const size_t pst = (size_t)w.B * w.R;
-  const double *p0 = w.P + (size_t)b * w.R;
   double tn = 0.0, cn = 0.0;
   thetaNorm[0] = 0.0;
   cartPosNorm[0] = 0.0;
-  double cur[MAXD + 3];
-  for (int j = 0; j < J; ++j) cur[j] = p0[j];
-  for (int j = 0; j < 3; ++j) cur[MAXD + j] = p0[J + j];
+  // the increments sqrt(dthetaSQ), sqrt(dcartSQ) of point i+1 were left in its slots by k_adjust_inc
+#pragma unroll 4
   for (int i = 0; i < nPts - 1; ++i) {
-    const double *nx = p0 + (size_t)(i + 1) * pst;
-    double dthetaSQ = 0;
-    for (int j = 0; j < J; ++j) {
-      const double v = nx[j];
-      const double d = v - cur[j];
-      dthetaSQ += d * d;
-      cur[j] = v;
-    }
-    tn = tn + sqrt(dthetaSQ);
+    tn = tn + thetaNorm[i + 1];
     thetaNorm[i + 1] = tn;
-    double dcartSQ = 0;
-    for (int j = 0; j < 3; ++j) {
-      const double v = nx[J + j];
-      const double d = v - cur[MAXD + j];
-      dcartSQ += d * d;
-      cur[MAXD + j] = v;
-    }
-    cn = cn + sqrt(dcartSQ);
+    cn = cn + cartPosNorm[i + 1];
     cartPosNorm[i + 1] = cn;
     if (CFG.c.is_auto_integ_res) {
       const double thetaChange = tn - thetaNormLast;
@@ -1018,21 +1029,21 @@ __global__ void k_resample(WSP, int npts, int nb) {
   }
 }
 // spline.cpp:78-87: a zero-length input segment aborts findInterpSegs (status only) (T)
+// one thread per (input segment, trajectory) flags the trajectory (TP), then the commit (T)
+__global__ void k_resample_check(WSP, int npts, int nb) {
+  TP_DECOMP(nb);
+  if (i >= npts) return;
+  TrajState &s = w.st[bl];
+  if (s.status & ST_FATAL_MASK & ~ST_DIV0) return;
+  if (i >= s.nPts - 1) return;
+  const RV sC = vecv(w.sC, w, bl);
+  if (sC[i + 1] - sC[i] < 1e-20) atomicOr(&s.status, (int)ST_DIV0);
+}
 __global__ void k_resample_commit(WSP) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= w.B) return;
   TrajState &s = w.st[b];
-  if (s.status & ST_FATAL_MASK) return;
-  const RV sC = vecv(w.sC, w, b);
-  double prev = sC[0];
-  for (int i = 0; i < s.nPts - 1; ++i) {
-    const double nx = sC[i + 1];
-    if (nx - prev < 1e-20) {
-      s.status |= ST_DIV0;
-      return;
-    }
-    prev = nx;
-  }
+  if (s.status & ST_FATAL_MASK) return;  // includes ST_DIV0 from k_resample_check
   s.nPts = s.nNew;
 }
 
