@@ -276,7 +276,7 @@ struct batotp_ctx {
   // context (own streams and workspaces, one host thread) next to the output / input phases of the full chunks
   batotp_ctx *helper = nullptr;
   bool tailOverlap = true;
-  bool marchGroup = getenv("BATOTP_MARCH_LANE") == nullptr;  // interpSpecial march: a group of lanes per trajectory (tuning aid: the env var restores one thread per trajectory)
+  int walkerKernel = 0;  // sequential walkers of the input phase (cumulative norms, interpSpecial march): 0 by chunk size, 1 one thread per trajectory, 2 point-parallel increments + a group of lanes per trajectory
   int pipeline = 0;  // two-context chunk pipeline of batotp_cuda_optimize_batch: 0 off, 1 automatic (large batches),
                      // n > 1: chunks of n trajectories whatever the batch size (tuning / tests)
   // stragglers: the few trajectories of a chunk that outgrow the step capacity keep BATOTP_ST_STEP_CAP for the
@@ -1117,6 +1117,7 @@ int read_plan_max(batotp_ctx *h, int *anyGridCap) {
   return mx;
 }
 
+#define WALKER_GROUP_MAX_B 32768
 int do_interp_input(batotp_ctx *h, bool haveN0, bool planSync) {
   const DevCfg &c = h->cfg;
   Ws &w = h->w;
@@ -1136,15 +1137,19 @@ int do_interp_input(batotp_ctx *h, bool haveN0, bool planSync) {
   }
   apply_kinematics(h, 0);
   if (adjust) {
-    LAUNCH_TP(h, k_adjust_inc, w.Nc, B, w);
-    LAUNCH_T(h, k_adjust_s, B, w, 1);
+    // chunks that do not fill the machine are bound by the latency of one trajectory in the one-thread-per-trajectory
+    // walkers: their per-point work goes to point-parallel / group kernels (measured on the B200: KUKA x4096 march
+    // 107 -> 24.5 ms, cumulative norms 23.5 -> 12.4 ms; GEN7DOF x56832 19.5 -> 22.6 and 2.2 -> 3.1 ms, hence the switch)
+    const bool smallChunk = h->walkerKernel == 2 || (h->walkerKernel == 0 && B <= WALKER_GROUP_MAX_B);
+    if (smallChunk) LAUNCH_TP(h, k_adjust_inc, w.Nc, B, w);
+    LAUNCH_T(h, k_adjust_s, B, w, 1, smallChunk ? 1 : 0);
     if (planSync) {
       const int mx = read_plan_max(h, nullptr);
       const int need = (int)(mx * 1.125) + 64;
       if (need > w.Nc) return need;  // caller grows the workspace and restarts the chunk
     }
     thomas_rows(h, w.P, w.M, B, 0, c.R, c.R, 0, 0);
-    if (h->marchGroup && c.J + MAXD <= MG && c.R <= MG) {  // a group of lanes per trajectory (k_input.cuh)
+    if (smallChunk && c.J + MAXD <= MG && c.R <= MG) {  // a group of lanes per trajectory (k_input.cuh)
       ProfScope ps_(h, "k_march_group");
       BATOTP_LAUNCH_WARP(k_march_group, dim3((unsigned)(((long long)B * MG + 127) / 128)), dim3(128), 0, h->stream, w);
       g_check_launch();
@@ -1161,8 +1166,8 @@ int do_interp_input(batotp_ctx *h, bool haveN0, bool planSync) {
       LAUNCH_T(h, (k_march<0, 0>), B, w);
     std::swap(w.P, w.Q);
     apply_kinematics(h, 1);
-    LAUNCH_TP(h, k_adjust_inc, w.Nc, B, w);
-    LAUNCH_T(h, k_adjust_s, B, w, 0);
+    if (smallChunk) LAUNCH_TP(h, k_adjust_inc, w.Nc, B, w);
+    LAUNCH_T(h, k_adjust_s, B, w, 0, smallChunk ? 1 : 0);
     thomas_rows(h, w.P, w.M, B, 0, c.R, c.R, 0, 0);
     LAUNCH_TP(h, k_resample, w.Nc, B, w);
     LAUNCH_TP(h, k_resample_check, w.Nc, B, w);
@@ -2578,6 +2583,7 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
           hp->stepHint = h->stepHint;
           hp->keepF64 = h->keepF64;
           hp->sweepKernel = h->sweepKernel;
+          hp->walkerKernel = h->walkerKernel;
           hp->dynFn = h->dynFn;
           hp->dynUser = h->dynUser;
           hp->ragNext = h->ragNext;
@@ -2677,6 +2683,7 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
           hp->stepHint = h->stepHint;
           hp->keepF64 = h->keepF64;
           hp->sweepKernel = h->sweepKernel;
+          hp->walkerKernel = h->walkerKernel;
           hp->dynFn = h->dynFn;
           hp->dynUser = h->dynUser;
           hp->ragNext = h->ragNext;
@@ -2870,6 +2877,13 @@ int batotp_cuda_set_sweep_kernel(batotp_handle h, int mode) {
   if (!h || mode < 0 || mode > 2) return -1;
   h->sweepKernel = mode;
   if (h->helper) h->helper->sweepKernel = mode;
+  return 0;
+}
+
+int batotp_cuda_set_walker_kernel(batotp_handle h, int mode) {
+  if (!h || mode < 0 || mode > 2) return -1;
+  h->walkerKernel = mode;
+  if (h->helper) h->helper->walkerKernel = mode;
   return 0;
 }
 

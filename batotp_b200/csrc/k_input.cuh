@@ -573,7 +573,7 @@ __global__ void k_adjust_inc(WSP, int npts, int nb) {
   o[1] = sqrt(dcartSQ);
 }
 
-__global__ void k_adjust_s(WSP, int special) {
+__global__ void k_adjust_s(WSP, int special, int haveInc) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= w.B) return;
   TrajState &s = w.st[b];
@@ -594,12 +594,43 @@ __global__ void k_adjust_s(WSP, int special) {
   double tn = 0.0, cn = 0.0;
   thetaNorm[0] = 0.0;
   cartPosNorm[0] = 0.0;
-  // the increments sqrt(dthetaSQ), sqrt(dcartSQ) of point i+1 were left in its slots by k_adjust_inc
-#pragma unroll 4
+  // haveInc: the increments sqrt(dthetaSQ), sqrt(dcartSQ) of point i+1 were left in its slots by k_adjust_inc (small
+  // chunks: the pass is bound by the latency of one trajectory); otherwise they are formed here (full chunks: one
+  // pass over the points instead of two)
+  const size_t pst = (size_t)w.B * w.R;
+  const double *p0 = w.P + (size_t)b * w.R;
+  double cur[MAXD + 3];
+  if (!haveInc) {
+    for (int j = 0; j < J; ++j) cur[j] = p0[j];
+    for (int j = 0; j < 3; ++j) cur[MAXD + j] = p0[J + j];
+  }
   for (int i = 0; i < nPts - 1; ++i) {
-    tn = tn + thetaNorm[i + 1];
+    double it, ic;
+    if (haveInc) {
+      it = thetaNorm[i + 1];
+      ic = cartPosNorm[i + 1];
+    } else {
+      const double *nx = p0 + (size_t)(i + 1) * pst;
+      double dthetaSQ = 0;
+      for (int j = 0; j < J; ++j) {
+        const double v = nx[j];
+        const double d = v - cur[j];
+        dthetaSQ += d * d;
+        cur[j] = v;
+      }
+      double dcartSQ = 0;
+      for (int j = 0; j < 3; ++j) {
+        const double v = nx[J + j];
+        const double d = v - cur[MAXD + j];
+        dcartSQ += d * d;
+        cur[MAXD + j] = v;
+      }
+      it = sqrt(dthetaSQ);
+      ic = sqrt(dcartSQ);
+    }
+    tn = tn + it;
     thetaNorm[i + 1] = tn;
-    cn = cn + cartPosNorm[i + 1];
+    cn = cn + ic;
     cartPosNorm[i + 1] = cn;
     if (CFG.c.is_auto_integ_res) {
       const double thetaChange = tn - thetaNormLast;

@@ -70,6 +70,7 @@ def load(path: Optional[str] = None):
     L.batotp_cuda_set_dyn_callback.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.batotp_cuda_set_pipeline.argtypes = [C.c_void_p, C.c_int]
     L.batotp_cuda_set_sweep_kernel.argtypes = [C.c_void_p, C.c_int]
+    L.batotp_cuda_set_walker_kernel.argtypes = [C.c_void_p, C.c_int]
     L.batotp_cuda_launch_count.argtypes = [C.c_void_p]
     L.batotp_cuda_launch_count.restype = C.c_long
     L.batotp_cuda_stats.argtypes = [C.c_void_p, _dp, C.c_int]
@@ -248,6 +249,10 @@ class Context:
     def set_sweep_kernel(self, mode: int):
         """0 automatic, 1 one trajectory per lane, 2 a group of lanes per trajectory."""
         self.L.batotp_cuda_set_sweep_kernel(self.h, mode)
+
+    def set_walker_kernel(self, mode: int):
+        """0 automatic, 1 one thread per trajectory, 2 point-parallel increments + a group of lanes per trajectory."""
+        self.L.batotp_cuda_set_walker_kernel(self.h, mode)
 
     def set_pipeline(self, on: int):
         """0 off, 1 automatic, n > 1: two-context pipeline with chunks of n trajectories."""

@@ -54,6 +54,11 @@ int batotp_cuda_set_max_steps(batotp_handle h, int n);
  * (k_sweep_group.cuh: a fraction of the latency per Runge-Kutta stage, for small batches and single paths).  Both
  * produce the same bits. */
 int batotp_cuda_set_sweep_kernel(batotp_handle h, int mode);
+/* the strictly sequential walkers of interpInputData (cumulative norms of adjust_s, ba.cpp:423-446; the constant-ds
+ * march of interpSpecial, ba.cpp:651-781).  0 (default) = by chunk size; 1 = one thread per trajectory (chunks that fill
+ * the device); 2 = point-parallel norm increments + a group of 16 lanes per trajectory for the march (small chunks:
+ * the walk is bound by the latency of one trajectory).  Both produce the same bits. */
+int batotp_cuda_set_walker_kernel(batotp_handle h, int mode);
 /* Runge-Kutta step capacity (per sweep) a chunk starts with; 0 (default) = automatic: max(1024, 2 x grid points),
  * then what earlier chunks of the same configuration needed.  Inside batotp_cuda_optimize_batch the few trajectories
  * of a chunk that outgrow the capacity ("stragglers", at most max(8, chunk/64)) are re-run together with a

@@ -666,3 +666,46 @@ def test_max_integration_time_is_reported_like_the_reference(ctx):
         assert orc.ok == bool(done[b]), b
         if done[b]:
             assert P.compare(c3, mix, b, orc) == [], b
+
+
+@pytest.mark.parametrize("name", P.STOCK)
+def test_walker_kernels_give_the_same_bytes(ctx, name):
+    """The sequential walkers of interpInputData exist in two shapes: one thread per trajectory (k_adjust_s forming the
+    norm increments itself, k_march) for chunks that fill the device, and point-parallel increments (k_adjust_inc) + a
+    group of 16 lanes per trajectory (k_march_group: one coordinate row per lane, the squared differences summed in the
+    reference's order from shuffled values) for small chunks.  Every stock robot through both, byte for byte the
+    reference's files - incl. the Cartesian rows that are only carried along (Traj::cartpt) and the UR5's 13 rows."""
+    cfg, tres, th, ca, ts = P.load_stock(name)
+    d = P.GOLD + "/stock/" + name
+    out = []
+    for mode in (1, 2):
+        ctx.set_walker_kernel(mode)
+        try:
+            res = P.run_device(ctx, cfg, tres, th, ca, ts)
+        finally:
+            ctx.set_walker_kernel(0)
+        assert P.device_traj_out_bytes(cfg, res, 0) == open(d + "/ref_traj_out.dat", "rb").read(), mode
+        assert P.device_s_sdot_bytes(res, 0) == open(d + "/ref_s-sdot.dat", "rb").read(), mode
+        out.append(res)
+    assert np.array_equal(out[0].n_grid, out[1].n_grid)
+
+
+def test_walker_kernels_on_a_ragged_batch(ctx):
+    """Two groups per warp with trajectories of different lengths (the groups of a warp diverge), degenerate paths
+    (fewer than 4 points after the march: the linear stretch to 4 points), automatic integration resolution."""
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 700, 9)
+    n0 = np.array([400, 400, 57, 400, 3, 400, 1, 400, 400], dtype=np.int32)
+    runs = []
+    for auto in (0, 1):
+        cfg.is_auto_integ_res = auto
+        for mode in (1, 2):
+            ctx.set_walker_kernel(mode)
+            try:
+                runs.append(P.run_device(ctx, cfg, tres, th, None, n0=n0, out_cap=8192, hist_cap=8192))
+            finally:
+                ctx.set_walker_kernel(0)
+        a, b = runs[-2:]
+        for nm in ("status", "n_rev", "n_fwd", "n_out", "n_grid", "t_total", "s_last_sec", "theta_out", "hist", "flags"):
+            assert np.array_equal(getattr(a, nm), getattr(b, nm)), (auto, nm)
+    cfg.is_auto_integ_res = 0
+    assert P.compare(cfg, runs[1], 3, P.OracleRun(cfg, tres, th[3], None)) == []

@@ -635,3 +635,43 @@ def test_max_integration_time_is_reported_like_the_reference(ctx):
         assert orc.ok == bool(done[b]), b
         if done[b]:
             assert P.compare(c3, mix, b, orc) == [], b
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", P.STOCK)
+def test_walker_kernels_give_the_same_bytes(ctx, name):
+    """Both shapes of the sequential walkers of interpInputData (one thread per trajectory; point-parallel norm
+    increments + k_march_group, 16 lanes per trajectory) reproduce the reference's files on every stock robot."""
+    cfg, tres, th, ca, ts = P.load_stock(name)
+    d = P.GOLD + "/stock/" + name
+    for mode in (1, 2):
+        ctx.set_walker_kernel(mode)
+        try:
+            res = P.run_device(ctx, cfg, tres, th, ca, ts)
+        finally:
+            ctx.set_walker_kernel(0)
+        assert P.device_traj_out_bytes(cfg, res, 0) == open(d + "/ref_traj_out.dat", "rb").read(), mode
+        assert P.device_s_sdot_bytes(res, 0) == open(d + "/ref_s-sdot.dat", "rb").read(), mode
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,count", [("GEN7DOF", 3000), ("KUKA", 96), ("CSPR3DOF", 300)])
+def test_walker_kernels_on_batches(ctx, name, count):
+    """The two walker shapes on batches (many groups per CTA, ragged lengths): every result array identical, and a
+    sample of the paths bit for bit against the oracle."""
+    cfg, tres, th, ca = P.load_synth(name, 1000, count)
+    n0 = np.full(count, (th if th is not None else ca).shape[2], np.int32)
+    n0[::7] = np.maximum(n0[::7] // 3, 5)
+    runs = []
+    for mode in (1, 2):
+        ctx.set_walker_kernel(mode)
+        try:
+            runs.append(P.run_device(ctx, cfg, tres, th, ca, n0=n0, out_cap=65536, hist_cap=65536))
+        finally:
+            ctx.set_walker_kernel(0)
+    a, b = runs
+    for nm in ("status", "n_rev", "n_fwd", "n_out", "n_grid", "t_total", "s_last_sec", "theta_out", "hist", "flags"):
+        assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
+    for k in (0, 7, count - 1):
+        orc = P.OracleRun(cfg, tres, None if th is None else th[k], None if ca is None else ca[k], n0=int(n0[k]))
+        assert P.compare(cfg, b, k, orc) == [], k
