@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--max-steps", type=int, default=0)
     ap.add_argument("--skip-host", action="store_true")
     ap.add_argument("--sweep-kernel", type=int, default=0, help="0 automatic, 1 lane per trajectory, 2 group per trajectory")
+    ap.add_argument("--walker-kernel", type=int, default=0, help="0 automatic, 1 thread per trajectory, 2 point-parallel + group march")
     a = ap.parse_args()
     import torch
     from batotp_b200 import native, synth
@@ -51,6 +52,7 @@ def main():
         ctx.set_max_steps(a.max_steps)
     ctx.set_out_chunk(a.out_chunk)
     ctx.set_sweep_kernel(a.sweep_kernel)
+    ctx.set_walker_kernel(a.walker_kernel)
     J = cfg.n_joints
     bi_dev = ctx.make_in(tres=tres, device_ptrs=dict(theta=None if is_cart else d_theta.data_ptr(),
                                                      cart=d_theta.data_ptr() if is_cart else None, B=B, n0_max=theta.shape[2]))

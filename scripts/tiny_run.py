@@ -16,6 +16,7 @@ n = int(os.environ.get("TINY_N", "48"))
 cfg, tres, th, ca = P.load_synth("GEN7DOF", 0, n)
 for kernel in (1, 2):
     ctx.set_sweep_kernel(kernel)
+    ctx.set_walker_kernel(kernel)  # 1: one thread per trajectory, 2: point-parallel increments + group march
     ctx.set_chunk(max(8, n // 3))
     ctx.set_out_chunk(7)
     res = P.run_device(ctx, cfg, tres, th, ca, out_cap=8192, hist_cap=8192)
@@ -24,6 +25,7 @@ for kernel in (1, 2):
     print("GEN7DOF kernel", kernel, "ok", int((res.status & native.ST_FATAL_MASK == 0).sum()), "of", n,
           "t_total sum", float(res.t_total.sum()), "ragged equal", bool((rag.rows(1) == res.theta_out[1, :, :res.n_out[1]]).all()))
 ctx.set_sweep_kernel(0)
+ctx.set_walker_kernel(0)
 ctx.set_chunk(0)
 ctx.set_out_chunk(40)
 cfg, tres, th, ca = P.load_synth("CSPR3DOF", 0, 3)
