@@ -604,12 +604,38 @@ __global__ void k_adjust_s(WSP, int special, int haveInc) {
     for (int j = 0; j < J; ++j) cur[j] = p0[j];
     for (int j = 0; j < 3; ++j) cur[MAXD + j] = p0[J + j];
   }
-  for (int i = 0; i < nPts - 1; ++i) {
-    double it, ic;
-    if (haveInc) {
-      it = thetaNorm[i + 1];
-      ic = cartPosNorm[i + 1];
-    } else {
+  // one point of the two running sums (+ the window bookkeeping of the automatic integration resolution)
+  auto add_point = [&](int i, double it, double ic) {
+    tn = tn + it;
+    thetaNorm[i + 1] = tn;
+    cn = cn + ic;
+    cartPosNorm[i + 1] = cn;
+    if (CFG.c.is_auto_integ_res) {
+      const double thetaChange = tn - thetaNormLast;
+      const double cartChange = cn - cartPosNormLast;
+      if (thetaChange > thetaWindow) {
+        MinRatio = dmin_(MinRatio, 3.0 * cartChange / thetaChange);
+        thetaNormLast = tn;
+        cartPosNormLast = cn;
+      }
+    }
+  };
+  if (haveInc) {
+    // the additions are the only chain: eight points' increments are fetched ahead of it (independent loads)
+    int i = 0;
+    for (; i + 8 <= nPts - 1; i += 8) {
+      double it[8], ic[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        it[k] = thetaNorm[i + 1 + k];
+        ic[k] = cartPosNorm[i + 1 + k];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) add_point(i + k, it[k], ic[k]);
+    }
+    for (; i < nPts - 1; ++i) add_point(i, thetaNorm[i + 1], cartPosNorm[i + 1]);
+  } else {
+    for (int i = 0; i < nPts - 1; ++i) {
       const double *nx = p0 + (size_t)(i + 1) * pst;
       double dthetaSQ = 0;
       for (int j = 0; j < J; ++j) {
@@ -625,21 +651,7 @@ __global__ void k_adjust_s(WSP, int special, int haveInc) {
         dcartSQ += d * d;
         cur[MAXD + j] = v;
       }
-      it = sqrt(dthetaSQ);
-      ic = sqrt(dcartSQ);
-    }
-    tn = tn + it;
-    thetaNorm[i + 1] = tn;
-    cn = cn + ic;
-    cartPosNorm[i + 1] = cn;
-    if (CFG.c.is_auto_integ_res) {
-      const double thetaChange = tn - thetaNormLast;
-      const double cartChange = cn - cartPosNormLast;
-      if (thetaChange > thetaWindow) {
-        MinRatio = dmin_(MinRatio, 3.0 * cartChange / thetaChange);
-        thetaNormLast = tn;
-        cartPosNormLast = cn;
-      }
+      add_point(i, sqrt(dthetaSQ), sqrt(dcartSQ));
     }
   }
   const double tnLast = tn, cnLast = cn;
