@@ -268,6 +268,9 @@ struct batotp_ctx {
   };
   std::vector<SweepRec> sweepLog;
   int lastSweepKernel = 1;
+  // trajectories one launch of the sweep kernels keeps resident (SMs x CTAs per SM x lanes / lanes per trajectory),
+  // learnt from the launches of the current configuration ([0] lane kernel, [1] group kernel; key = its dispatch key)
+  int sweepCap[2] = {0, 0}, sweepCapKey = -1;
   long long cntVerify = 0, cntSteps = 0, cntTraj = 0;
   // optional per-kernel device timing (batotp_cuda_set_profile): serialises every launch
   bool profile = false;
@@ -870,6 +873,7 @@ void launch_sweep(batotp_ctx *h) {
   if (perSm < 1) perSm = 1;
   int blocks = std::min(sms * perSm, cdiv(h->B, SW_NT));
   if (blocks < 1) blocks = 1;
+  h->sweepCap[0] = sms * perSm * SW_NT;
   if (!h->evS0) {
     CU_CHECK(cudaEventCreate(&h->evS0));
     CU_CHECK(cudaEventCreate(&h->evS1));
@@ -877,6 +881,7 @@ void launch_sweep(batotp_ctx *h) {
   CU_CHECK(cudaEventRecord(h->evS0, h->stream));
 #else
   int blocks = 1;
+  if (const char *e = getenv("BATOTP_EMU_SWEEP_CAP")) h->sweepCap[0] = atoi(e);  // TEST-ONLY: pretend this occupancy
 #endif
   {
     ProfScope ps_(h, "k_sweep");
@@ -904,6 +909,7 @@ void launch_sweep_group(batotp_ctx *h) {
   if (perSm < 1) perSm = 1;
   int blocks = (int)std::min<long long>((long long)sms * perSm, ((long long)h->B * G + SWG_NT - 1) / SWG_NT);
   if (blocks < 1) blocks = 1;
+  h->sweepCap[1] = sms * perSm * SWG_NT / G;
   if (!h->evS0) {
     CU_CHECK(cudaEventCreate(&h->evS0));
     CU_CHECK(cudaEventCreate(&h->evS1));
@@ -911,6 +917,7 @@ void launch_sweep_group(batotp_ctx *h) {
   CU_CHECK(cudaEventRecord(h->evS0, h->stream));
 #else
   int blocks = 1;
+  if (const char *e = getenv("BATOTP_EMU_SWEEP_CAP")) h->sweepCap[1] = atoi(e);  // TEST-ONLY: pretend this occupancy
 #endif
   {
     ProfScope ps_(h, "k_sweep_group");
@@ -938,6 +945,11 @@ bool use_group_kernel(const batotp_ctx *h) {
 int dispatch_sweep(batotp_ctx *h) {
   const DevCfg &c = h->cfg;
   const int key = c.J * 4 + (c.cartOn ? 2 : 0) + (c.trqOn ? 1 : 0);
+  const int capKey = key * 2 + ((c.trqOn && c.c.is_parallel && !c.c.is_par2ser) ? 1 : 0);
+  if (capKey != h->sweepCapKey) {  // another kernel instance: its occupancy is not known yet
+    h->sweepCap[0] = h->sweepCap[1] = 0;
+    h->sweepCapKey = capKey;
+  }
   if (c.trqOn && c.c.is_parallel && !c.c.is_par2ser) {
     // torque limits of a parallel mechanism without Par2Ser (ba.cpp:1463-1491): one trajectory per lane only
     h->lastSweepKernel = 1;
@@ -2307,13 +2319,31 @@ static void sync_quiet(batotp_handle h) {
   h->copiesPending = false;
 }
 
+// trajectories per round of the sweep kernel a chunk of B trajectories of this configuration would take (0: not known)
+static int sweep_round_capacity(batotp_handle h, const batotp_cfg *cfg, int B) {
+  if (!h->haveCfg || memcmp(&h->cfg.c, cfg, sizeof(batotp_cfg)) != 0) return 0;  // learnt for another configuration
+  if (h->cfg.trqOn && h->cfg.c.is_parallel && !h->cfg.c.is_par2ser) return h->sweepCap[0];
+  const bool exact = h->cfg.cartOn || h->cfg.trqOn;
+  const bool group = h->sweepKernel == 2 || (h->sweepKernel == 0 && B <= (exact ? SWEEP_GROUP_MAX_B_EXACT : SWEEP_GROUP_MAX_B));
+  return h->sweepCap[group ? 1 : 0];
+}
+
 // The chunks [0, mainB) of a batch on context h, one after the other (out-of-memory: smaller chunks)
 static void run_chunks(batotp_handle h, const batotp_cfg *cfg, const batotp_batch_in *in, batotp_batch_out *out,
                        int from, int mainB, int &chunk, bool &first) {
   for (int at = from; at < mainB;) {
-    const int B = std::min(chunk, mainB - at);
+    // A sweep launch lasts whole rounds of the trajectories it keeps resident (it is bound by the latency of one
+    // trajectory), so a chunk a little over a multiple of that number pays a round for the remainder (CSPR3DOF:
+    // memory allows 19072 paths, two rounds hold 18944).  Once the occupancy of the configuration's kernel is
+    // known, a chunk whose last round would be less than a quarter full is cut to whole rounds (a fuller last round is
+    // cheaper than another chunk).
+    auto whole_rounds = [&](int n) {
+      const int cap = sweep_round_capacity(h, cfg, n);
+      return (cap > 0 && n > cap && n % cap < cap / 4) ? n / cap * cap : n;
+    };
+    const int B = whole_rounds(std::min(chunk, mainB - at));
     try {
-      process_chunk(h, first ? cfg : nullptr, in, out, at, B, std::min(chunk, mainB - at - B));
+      process_chunk(h, first ? cfg : nullptr, in, out, at, B, whole_rounds(std::min(chunk, mainB - at - B)));
     } catch (const Err &e) {
       // a workspace did not fit (long paths, many rows): release everything and go on with smaller chunks
       if (!e.oom) throw;

@@ -709,3 +709,26 @@ def test_walker_kernels_on_a_ragged_batch(ctx):
             assert np.array_equal(getattr(a, nm), getattr(b, nm)), (auto, nm)
     cfg.is_auto_integ_res = 0
     assert P.compare(cfg, runs[1], 3, P.OracleRun(cfg, tres, th[3], None)) == []
+
+
+def test_chunks_are_cut_to_whole_sweep_rounds(ctx, monkeypatch):
+    """A sweep launch lasts whole rounds of the trajectories it keeps resident, so once the occupancy of the
+    configuration's sweep kernel is known (from its first launch) chunks of more than one round are cut to whole
+    rounds (CSPR3DOF on the B200: memory allows 19072 paths per chunk, two rounds hold 18944).  TEST-ONLY knob:
+    BATOTP_EMU_SWEEP_CAP makes the emulated launches report an occupancy of 10 trajectories (21 paths: the third round would be less than a quarter full)."""
+    cfg, tres, th, _ = P.load_synth("GEN7DOF", 2000, 21)
+    a = P.run_device(ctx, cfg, tres, th, None)
+    monkeypatch.setenv("BATOTP_EMU_SWEEP_CAP", "10")
+    P.run_device(ctx, cfg, tres, th, None)  # learns the occupancy: 21 paths in one chunk
+    ctx.stats_reset()
+    b = P.run_device(ctx, cfg, tres, th, None)  # 20 + 1: the third round would hold 1 of 10
+    st = ctx.stats()
+    monkeypatch.delenv("BATOTP_EMU_SWEEP_CAP")
+    assert st["sweep_launches"] == 2 and st["trajectories"] == 21
+    for nm in ("status", "n_rev", "n_fwd", "n_out", "t_total", "s_last_sec", "theta_out", "hist", "flags"):
+        assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
+    other, tres2, th2, ca2, ts2 = P.load_stock("RR")  # another configuration forgets what was learnt
+    P.run_device(ctx, other, tres2, th2, ca2, ts2)
+    ctx.stats_reset()
+    c = P.run_device(ctx, cfg, tres, th, None)
+    assert ctx.stats()["sweep_launches"] == 1 and np.array_equal(c.theta_out, a.theta_out)
