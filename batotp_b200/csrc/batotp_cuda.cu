@@ -7,6 +7,7 @@
 // -DBATOTP_HOST_EMU into a TEST-ONLY emulation library (see emu.h) used by the CPU CI.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -39,6 +40,7 @@ struct Err {
   std::string msg;
   bool oom = false;  // a device allocation failed (or would fail): the batch call retries with smaller chunks
   int fitB = 0;      // with oom: how many trajectories per chunk the free memory would hold (0 = unknown)
+  bool planned = false;  // with oom: refused by the planner before anything was freed or allocated (workspaces intact)
 };
 
 #ifndef BATOTP_HOST_EMU
@@ -52,9 +54,21 @@ struct Err {
       throw Err{buf_};                                                                      \
     }                                                                                       \
   } while (0)
+// tuning aid: BATOTP_TRACE=1 prints the chunk decisions of a batch call, the planner's refusals and the time spent in
+// cudaMalloc / cudaFree to stderr
+inline bool g_trace() {
+  static const bool on = getenv("BATOTP_TRACE") != nullptr;
+  return on;
+}
+inline double g_now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static double g_allocMs = 0, g_freeMs = 0;
 inline void *g_alloc(size_t bytes) {
   void *p = nullptr;
+  const double t0 = g_trace() ? g_now_ms() : 0;
   const cudaError_t e = cudaMalloc(&p, bytes ? bytes : 8);
+  if (g_trace()) g_allocMs += g_now_ms() - t0;
   if (e != cudaSuccess) {
     cudaGetLastError();  // not sticky: clear it
     char buf[256];
@@ -66,7 +80,9 @@ inline void *g_alloc(size_t bytes) {
   return p;
 }
 inline void g_free(void *p) {
+  const double t0 = g_trace() ? g_now_ms() : 0;
   if (p) cudaFree(p);
+  if (g_trace()) g_freeMs += g_now_ms() - t0;
 }
 inline void g_zero(void *p, size_t bytes, cudaStream_t s) { CU_CHECK(cudaMemsetAsync(p, 0, bytes, s)); }
 inline void g_h2d(void *d, const void *h, size_t bytes, cudaStream_t s) {
@@ -92,6 +108,14 @@ inline void g_event_record(cudaEvent_t e, cudaStream_t s) { CU_CHECK(cudaEventRe
 inline void g_stream_wait(cudaStream_t s, cudaEvent_t e) { CU_CHECK(cudaStreamWaitEvent(s, e, 0)); }
 inline void g_check_launch() { CU_CHECK(cudaGetLastError()); }
 #else
+inline bool g_trace() {
+  static const bool on = getenv("BATOTP_TRACE") != nullptr;
+  return on;
+}
+inline double g_now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static double g_allocMs = 0, g_freeMs = 0;
 inline void *g_alloc(size_t bytes) { return calloc(1, bytes ? bytes : 8); }
 inline void g_free(void *p) { free(p); }
 inline void g_zero(void *p, size_t bytes, cudaStream_t) { memset(p, 0, bytes); }
@@ -183,6 +207,8 @@ struct batotp_ctx {
   int capB = 0, capNc = 0, capSc = 0, capR = 0, capRT = 0;
   bool capTrq = false;
   std::vector<void *> wsAllocs;   // chunk-resident arrays
+  size_t wsBytes = 0, outBytes = 0;  // bytes held by wsAllocs / outAllocs
+  int learnedChunk = 0;              // automatic chunking: the chunk size the last batch call of this configuration ended with
   int capBo = 0, capOc = 0, capOs = 0, capOutC = 0, capOSc = 0;
   std::vector<void *> outAllocs;  // output sub-chunk arrays
   int outChunk = 8192;            // trajectories per output pass
@@ -385,11 +411,13 @@ inline void tp_dims(long long fast, long long slow, dim3 &grid, dim3 &block) {
 void free_ws(batotp_ctx *h) {
   for (void *p : h->wsAllocs) g_free(p);
   h->wsAllocs.clear();
+  h->wsBytes = 0;
   h->capB = 0;
 }
 void free_out(batotp_ctx *h) {
   for (void *p : h->outAllocs) g_free(p);
   h->outAllocs.clear();
+  h->outBytes = 0;
   h->capBo = 0;
   h->capRowPitch = h->capHistPitch = 0;
 }
@@ -398,12 +426,14 @@ template <class T>
 T *ws_alloc(batotp_ctx *h, size_t count) {
   void *p = g_alloc(count * sizeof(T));
   h->wsAllocs.push_back(p);
+  h->wsBytes += count * sizeof(T);
   return (T *)p;
 }
 template <class T>
 T *out_alloc(batotp_ctx *h, size_t count) {
   void *p = g_alloc(count * sizeof(T));
   h->outAllocs.push_back(p);
+  h->outBytes += count * sizeof(T);
   return (T *)p;
 }
 
@@ -531,14 +561,18 @@ void ensure_ws(batotp_ctx *h, int B, int Nc, int Sc) {
     h->w.B = B;
     return;
   }
-  free_ws(h);
-  free_out(h);
   h->allocPhase = 0;
   {
     // footprint of one trajectory in the chunk-resident arrays below; a chunk that cannot fit is refused before
-    // anything is allocated, with the size that would fit (the batch call continues with smaller chunks)
+    // anything is freed or allocated, with the size that would fit (the batch call continues with smaller chunks -
+    // and finds the workspace of its previous call intact: releasing and re-allocating ~130 GB costs 170 ms)
+#ifndef BATOTP_HOST_EMU
+    const size_t held = h->wsBytes + h->outBytes;  // released below if the new workspace goes ahead
+#else
+    const size_t held = 0;  // (BATOTP_EMU_FREE_MB is what this context may use in total)
+#endif
     const size_t per = chunk_bytes_per_traj(c, Nc, Sc);
-    const size_t fr = g_free_bytes();
+    const size_t fr = g_free_bytes() + held;
     // what else this context will ask for: the output sub-chunk arrays (ensure_out) and some slack for the
     // staging sets / the tail helper
     const size_t reserve = ((size_t)2 << 30) + out_bytes_per_traj(h, Sc) * (size_t)std::min(B, h->outChunk);
@@ -549,9 +583,12 @@ void ensure_ws(batotp_ctx *h, int B, int Nc, int Sc) {
       Err er{buf};
       er.oom = true;
       er.fitB = (int)std::min<double>(2.0e9, 0.9 * (double)(fr > reserve ? fr - reserve : 0) / (double)per);
+      er.planned = true;
       throw er;
     }
   }
+  free_ws(h);
+  free_out(h);
   Ws &w = h->w;
   memset(&w, 0, sizeof(w));
   w.cfg = h->cfg;
@@ -1643,6 +1680,7 @@ const char *batotp_cuda_last_error(batotp_handle h) { return h ? h->err.c_str() 
 int batotp_cuda_set_chunk(batotp_handle h, int chunk) {
   if (!h || chunk < 0) return -1;
   h->chunk = chunk;
+  h->learnedChunk = 0;
   return 0;
 }
 
@@ -2342,17 +2380,24 @@ static void run_chunks(batotp_handle h, const batotp_cfg *cfg, const batotp_batc
       return (cap > 0 && n > cap && n % cap < cap / 4) ? n / cap * cap : n;
     };
     const int B = whole_rounds(std::min(chunk, mainB - at));
+    const double tC0 = g_trace() ? g_now_ms() : 0;
+    if (g_trace())
+      fprintf(stderr, "[batotp] chunk at %d: %d paths (chunk setting %d, round capacity %d; capB %d capNc %d capSc %d; alloc %.1f ms free %.1f ms so far)\n",
+              at, B, chunk, sweep_round_capacity(h, cfg, B), h->capB, h->capNc, h->capSc, g_allocMs, g_freeMs);
     try {
       process_chunk(h, first ? cfg : nullptr, in, out, at, B, whole_rounds(std::min(chunk, mainB - at - B)));
     } catch (const Err &e) {
       // a workspace did not fit (long paths, many rows): release everything and go on with smaller chunks
       if (!e.oom) throw;
+      if (g_trace()) fprintf(stderr, "[batotp]   refused after %.1f ms: %s (fits: %d, alloc phase %d)\n", g_now_ms() - tC0, e.msg.c_str(), e.fitB, h->allocPhase);
       g_sync(h->stream);
       g_sync(h->copyStream);
       h->copiesPending = false;
       h->inSet[0].src = h->inSet[1].src = nullptr;
-      free_ws(h);
-      free_out(h);
+      if (!e.planned) {  // (a refusal by the planner has left the workspaces of the previous chunks / calls as they were)
+        free_ws(h);
+        free_out(h);
+      }
       const int chunk0 = chunk, out0 = h->outChunk;
       if (e.fitB > 0 && e.fitB < B)  // the workspace planner knows what fits
         chunk = std::max(1, e.fitB >= SW_NT ? e.fitB / SW_NT * SW_NT : e.fitB);
@@ -2363,6 +2408,7 @@ static void run_chunks(batotp_handle h, const batotp_cfg *cfg, const batotp_batc
       if ((chunk >= chunk0 || chunk >= B) && h->outChunk >= std::min(out0, B)) throw;  // nothing left to shrink
       continue;
     }
+    if (g_trace()) fprintf(stderr, "[batotp]   done in %.1f ms (Nc %d Sc %d, stragglers so far %zu)\n", g_now_ms() - tC0, h->w.Nc, h->w.Sc, h->stragglers.size());
     first = false;
     at += B;
   }
@@ -2563,6 +2609,12 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
   } ragReset{h};
   bool first = true;
   int chunk = h->chunk > 0 ? h->chunk : auto_chunk(h, in->B);
+  const int chunkAuto = chunk;
+  // what the workspace planner allowed in the previous call of this configuration: start there (a refused first
+  // attempt costs the staging of its inputs)
+  const bool sameCfg = h->haveCfg && memcmp(&h->cfg.c, cfg, sizeof(batotp_cfg)) == 0;
+  if (h->chunk == 0 && sameCfg && h->learnedChunk > 0) chunk = std::min(chunk, h->learnedChunk);
+  if (!sameCfg) h->learnedChunk = 0;
   int mainB = in->B, tail = 0;
   std::thread tailThread;
   std::mutex mu;
@@ -2753,6 +2805,7 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
       }
     }
     run_chunks(h, cfg, in, out, 0, mainB, chunk, first);
+    if (h->chunk == 0 && chunk < chunkAuto) h->learnedChunk = chunk;  // the out-of-memory handling shrank it
     finish_tail(1);
     if (tail > 0) {
       batotp_ctx *hp = h->helper;

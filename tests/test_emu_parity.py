@@ -482,9 +482,15 @@ def test_chunks_shrink_until_the_workspace_fits(ctx, monkeypatch):
     try:
         monkeypatch.setenv("BATOTP_EMU_FREE_MB", str(2048 + 8))  # room for a few trajectories
         b = P.run_device(fresh, cfg, tres, th, None, out_cap=4096, hist_cap=4096)
-        assert fresh.stats()["sweep_launches"] >= 3
+        n1 = fresh.stats()["sweep_launches"]
+        assert n1 >= 3
         for nm in ("status", "n_rev", "n_fwd", "n_out", "t_total", "theta_out", "hist", "flags"):
             assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
+        # the next call of the same configuration starts with the chunk size that fitted (no refused attempt, the
+        # workspace of the first call is reused as it is)
+        fresh.stats_reset()
+        b2 = P.run_device(fresh, cfg, tres, th, None, out_cap=4096, hist_cap=4096)
+        assert fresh.stats()["sweep_launches"] <= n1 and np.array_equal(b2.theta_out, a.theta_out)
         cfg2, tres2, th2, ca2, ts2 = P.load_stock("KUKA-LWR-IV")  # another robot: the workspace is planned anew
         monkeypatch.setenv("BATOTP_EMU_FREE_MB", "2048")
         with pytest.raises(native.NativeError, match="of workspace"):
