@@ -2371,21 +2371,23 @@ static void run_chunks(batotp_handle h, const batotp_cfg *cfg, const batotp_batc
                        int from, int mainB, int &chunk, bool &first) {
   for (int at = from; at < mainB;) {
     // A sweep launch lasts whole rounds of the trajectories it keeps resident (it is bound by the latency of one
-    // trajectory), so a chunk a little over a multiple of that number pays a round for the remainder (CSPR3DOF:
-    // memory allows 19072 paths, two rounds hold 18944).  Once the occupancy of the configuration's kernel is
-    // known, a chunk whose last round would be less than a quarter full is cut to whole rounds (a fuller last round is
-    // cheaper than another chunk).
-    auto whole_rounds = [&](int n) {
+    // trajectory), so a chunk of 1.5 rounds pays for 2 (CSPR3DOF on the B200: 9472 paths per round; memory allows
+    // 14464..19072 per chunk).  Once the occupancy of the configuration's kernel is known, a chunk that is not the
+    // last one of its batch is cut to whole rounds - what it leaves moves on to the next chunk - and the last one when
+    // its final round would be less than a quarter full (a fuller round is cheaper than another chunk).
+    auto whole_rounds = [&](int n, int left) {
       const int cap = sweep_round_capacity(h, cfg, n);
-      return (cap > 0 && n > cap && n % cap < cap / 4) ? n / cap * cap : n;
+      if (cap <= 0 || n <= cap) return n;
+      return (left > n || n % cap < cap / 4) ? n / cap * cap : n;
     };
-    const int B = whole_rounds(std::min(chunk, mainB - at));
+    const int B = whole_rounds(std::min(chunk, mainB - at), mainB - at);
+    const int nextB = whole_rounds(std::min(chunk, mainB - at - B), mainB - at - B);
     const double tC0 = g_trace() ? g_now_ms() : 0;
     if (g_trace())
       fprintf(stderr, "[batotp] chunk at %d: %d paths (chunk setting %d, round capacity %d; capB %d capNc %d capSc %d; alloc %.1f ms free %.1f ms so far)\n",
               at, B, chunk, sweep_round_capacity(h, cfg, B), h->capB, h->capNc, h->capSc, g_allocMs, g_freeMs);
     try {
-      process_chunk(h, first ? cfg : nullptr, in, out, at, B, whole_rounds(std::min(chunk, mainB - at - B)));
+      process_chunk(h, first ? cfg : nullptr, in, out, at, B, nextB);
     } catch (const Err &e) {
       // a workspace did not fit (long paths, many rows): release everything and go on with smaller chunks
       if (!e.oom) throw;
