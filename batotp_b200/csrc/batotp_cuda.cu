@@ -2617,6 +2617,12 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
   const bool sameCfg = h->haveCfg && memcmp(&h->cfg.c, cfg, sizeof(batotp_cfg)) == 0;
   if (h->chunk == 0 && sameCfg && h->learnedChunk > 0) chunk = std::min(chunk, h->learnedChunk);
   if (!sameCfg) h->learnedChunk = 0;
+  {
+    // whole rounds of the sweep kernel (run_chunks): applied to the chunk setting itself when the occupancy is already
+    // known, so that the tail below is what whole-round chunks leave over
+    const int cap = sweep_round_capacity(h, cfg, chunk);
+    if (cap > 0 && chunk > cap && in->B > chunk) chunk = chunk / cap * cap;
+  }
   int mainB = in->B, tail = 0;
   std::thread tailThread;
   std::mutex mu;
