@@ -62,11 +62,7 @@ __device__ __forceinline__ double group_max(double v, int lane) {
 }
 
 template <int J, bool CART, bool TRQ>
-// (SWG_MINB_TRQ: resident CTAs per SM the torque instantiations are compiled for - 247 registers and 2 CTAs when 1)
-#ifndef SWG_MINB_TRQ
-#define SWG_MINB_TRQ 1
-#endif
-__global__ void __launch_bounds__(SWG_NT, TRQ ? SWG_MINB_TRQ : 1) k_sweep_group(WSP) {
+__global__ void __launch_bounds__(SWG_NT) k_sweep_group(WSP) {
   constexpr int G = GroupShape<J, CART>::G;
   constexpr int NK = J + (CART ? 3 : 0);
   constexpr int RT = NK + (TRQ ? 4 * J : 0);
