@@ -2376,7 +2376,7 @@ static void run_chunks(batotp_handle h, const batotp_cfg *cfg, const batotp_batc
     // last one of its batch is cut to whole rounds - what it leaves moves on to the next chunk - and the last one when
     // its final round would be less than a quarter full (a fuller round is cheaper than another chunk).
     auto whole_rounds = [&](int n, int left) {
-      const int cap = sweep_round_capacity(h, cfg, n);
+      const int cap = h->chunk == 0 ? sweep_round_capacity(h, cfg, n) : 0;  // (an explicit chunk setting is taken literally)
       if (cap <= 0 || n <= cap) return n;
       return (left > n || n % cap < cap / 4) ? n / cap * cap : n;
     };
@@ -2620,7 +2620,7 @@ int batotp_cuda_optimize_batch(batotp_handle h, const batotp_cfg *cfg, const bat
   {
     // whole rounds of the sweep kernel (run_chunks): applied to the chunk setting itself when the occupancy is already
     // known, so that the tail below is what whole-round chunks leave over
-    const int cap = sweep_round_capacity(h, cfg, chunk);
+    const int cap = h->chunk == 0 ? sweep_round_capacity(h, cfg, chunk) : 0;
     if (cap > 0 && chunk > cap && in->B > chunk) chunk = chunk / cap * cap;
   }
   int mainB = in->B, tail = 0;

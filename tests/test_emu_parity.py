@@ -724,6 +724,7 @@ def test_chunks_are_cut_to_whole_sweep_rounds(ctx, monkeypatch):
     BATOTP_EMU_SWEEP_CAP makes the emulated launches report an occupancy of 10 trajectories (21 paths: the third round would be less than a quarter full)."""
     cfg, tres, th, _ = P.load_synth("GEN7DOF", 2000, 21)
     a = P.run_device(ctx, cfg, tres, th, None)
+    ctx.set_chunk(0)  # automatic chunking (an explicit chunk setting is taken literally)
     monkeypatch.setenv("BATOTP_EMU_SWEEP_CAP", "10")
     P.run_device(ctx, cfg, tres, th, None)  # learns the occupancy: 21 paths in one chunk
     ctx.stats_reset()
@@ -738,3 +739,4 @@ def test_chunks_are_cut_to_whole_sweep_rounds(ctx, monkeypatch):
     ctx.stats_reset()
     c = P.run_device(ctx, cfg, tres, th, None)
     assert ctx.stats()["sweep_launches"] == 1 and np.array_equal(c.theta_out, a.theta_out)
+    ctx.set_chunk(16384)
